@@ -1,0 +1,135 @@
+/*  stochqn_b200.h - device-side extensions of the stochQN C ABI (B200 / sm_100a build)
+ *
+ *  stochqn.h is the drop-in part: the reference's nine entry points with unchanged
+ *  signatures.  This header adds what a GPU-resident caller needs and the reference,
+ *  being a host library, never had: device / stream selection, sharding of one
+ *  optimizer over several GPUs, the bundled device callbacks (Rosenbrock; binary
+ *  logistic gradient / Hessian-vector / loss of the reference's R/logistic.R:1-37), and
+ *  workspace export / import in the reference's own field layout.
+ *
+ *  Plain C: pointers and sizes only, no CUDA or torch types in any signature
+ *  (`void *stream` is a cudaStream_t, `void *comm` an opaque handle).
+ *  Every function returns 0 on success and a negative code on failure unless stated;
+ *  stochqn_b200_last_error() gives the message.  `ws` is a pointer returned by
+ *  initialize_oLBFGS / initialize_SQN / initialize_adaQN.
+ */
+#ifndef STOCHQN_B200_INCLUDE
+#define STOCHQN_B200_INCLUDE
+
+#include "stochqn.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library information -------------------------------------------------------------- */
+int         stochqn_b200_version(void);          /* 100*major + minor */
+int         stochqn_b200_real_bytes(void);       /* sizeof(real_t) of this build: 8 or 4 */
+const char* stochqn_b200_last_error(void);       /* message of the last failure on this thread */
+/* number of CUDA kernels this library has launched since it was loaded (all workspaces) */
+unsigned long long stochqn_b200_launch_count(void);
+
+/* ---- device / stream ------------------------------------------------------------------- */
+/* initialize_*() allocates on the CUDA device that is current when it is called.  All work
+   of a workspace is enqueued on one stream: the legacy default stream unless set here
+   (pass e.g. torch.cuda.current_stream().cuda_stream).  run_*() returns after that stream
+   has drained, so results are final on return, as with the reference. */
+int stochqn_b200_set_stream(void *ws, void *stream);
+
+/* ---- per-workspace options --------------------------------------------------------------- */
+enum stochqn_b200_option {
+    /* 1 (default): `grad` holds the search direction after a step (oLBFGS: -step*direction),
+       exactly what the reference leaves there (src/stochqn.c:838,1006).  0: `grad` is left
+       untouched by device-pointer calls - saves one n-vector write per step; the reference
+       documents the array only as "modified in place" (include/stochqn.h:342). */
+    STOCHQN_B200_OPT_GRAD_WRITEBACK = 1,
+    /* host-pointer calls only. 0 (default): `x` is uploaded on every call that reads it, as
+       the reference re-reads the caller's array each call.  1: trust the device mirror (the
+       caller promises not to modify x between calls) - saves one host->device copy per step. */
+    STOCHQN_B200_OPT_TRUST_X_MIRROR = 2,
+    /* 1: bracket the streaming kernels of each call (K1 multi-dot, K3 combine/update, K4 pair) with CUDA
+       events on the workspace stream and accumulate their device times; setting it (to 0 or 1) resets the
+       accumulators.  Read them with stochqn_b200_get_stat.  Default 0. */
+    STOCHQN_B200_OPT_PROFILE = 3
+};
+int stochqn_b200_set_option(void *ws, int option, long long value);
+
+enum stochqn_b200_stat {
+    STOCHQN_B200_STAT_K1_MS = 1, STOCHQN_B200_STAT_K1_COUNT = 2,     /* accumulated device ms / launches (profile mode) */
+    STOCHQN_B200_STAT_K3_MS = 3, STOCHQN_B200_STAT_K3_COUNT = 4,
+    STOCHQN_B200_STAT_K4_MS = 5, STOCHQN_B200_STAT_K4_COUNT = 6,
+    STOCHQN_B200_STAT_LAST_BOUND = 7                                  /* bound on ||direction|| of the last step */
+};
+int stochqn_b200_get_stat(void *ws, int what, double *out);
+
+/* leading dimension (in elements) of s_mem / y_mem / F rows: rows are padded to a multiple
+   of 128 bytes so that every row is 16-byte aligned whatever n is; row j of s_mem starts
+   at s_mem + j * row_stride. */
+size_t stochqn_b200_row_stride(void *ws);
+
+/* ---- sharding one optimizer over several GPUs (one process per GPU) ---------------------
+   Every n-vector is split into contiguous blocks; each rank creates its workspace with
+   n = its own block length and registers a communicator.  Inside a step the only exchange
+   is one small all-reduce (sum, fp64, <= 4*mem_size+2 values) per reduction phase.
+   Bootstrap: rank 0 obtains a 128-byte id, the host program ships it to the other ranks
+   (torch.distributed broadcast, MPI, a file ...), every rank calls comm_init. */
+int stochqn_b200_comm_unique_id(void *id128);
+int stochqn_b200_comm_init(const void *id128, int rank, int world_size, void **comm);
+int stochqn_b200_comm_destroy(void *comm);
+/* n_global = sum of all ranks' n: the reference's step-rejection limit is 1e3 * n
+   (src/stochqn.c:829) and must use the length of the whole vector */
+int stochqn_b200_set_comm(void *ws, void *comm, long long n_global);
+/* in-place sum of `count` doubles in device memory over the communicator, on `stream`
+   (exposed so that callbacks can ride on the same communicator) */
+int stochqn_b200_allreduce_f64(void *comm, double *dev_buf, size_t count, void *stream);
+
+/* ---- bundled device callbacks -------------------------------------------------------------
+   Chained Rosenbrock, formulas of the reference's example (example/c_rosen.c:13-41), on a
+   contiguous shard x[0..n_local) of a vector of length n_global that starts at global index
+   `offset`.  `halo` = {x[offset-1], x[offset+n_local]} in DEVICE memory (ignored at the ends
+   of the global vector; may be NULL when the shard is the whole vector). */
+int stochqn_b200_rosenbrock_x0(real_t *x, long long n_local, long long offset, void *stream);
+int stochqn_b200_rosenbrock_grad(const real_t *x, real_t *grad, long long n_local, long long offset,
+                                 long long n_global, const real_t *halo, void *stream);
+/* writes the local part of the objective (fp64) to *f_dev (device memory) */
+int stochqn_b200_rosenbrock_fun(const real_t *x, long long n_local, long long offset, long long n_global,
+                                const real_t *halo, double *f_dev, void *stream);
+
+/* Binary logistic regression, the closed forms of R/logistic.R:1-37.  X is ROW-major
+   [nrows][ncols] with leading dimension ldx (a batch is a row range: no copy); y in {0,1};
+   sample weights `sw` may be NULL.  All pointers are device pointers.
+     grad     = X'((sigmoid(Xw) - y) .* sw) / sum(sw) + 2*lambda*w          (logistic.R:12-21)
+     hess_vec = X'( p(1-p) .* sw .* (Xv) ) / sum(sw) + 2*lambda*v           (logistic.R:23-37)
+     loss     = -sum(sw .* (y log p + (1-y) log(1-p))) / sum(sw) + lambda*|w|^2   (logistic.R:1-10)
+   `work` is device scratch of at least stochqn_b200_logistic_work_size(nrows, ncols) bytes. */
+size_t stochqn_b200_logistic_work_size(long long nrows, long long ncols);
+int stochqn_b200_logistic_grad(const real_t *X, long long ldx, const real_t *y, const real_t *sw,
+                               long long nrows, long long ncols, const real_t *w, real_t lambda,
+                               real_t *grad, void *work, void *stream);
+int stochqn_b200_logistic_hess_vec(const real_t *X, long long ldx, const real_t *y, const real_t *sw,
+                                   long long nrows, long long ncols, const real_t *w, const real_t *v,
+                                   real_t lambda, real_t *hess_vec, void *work, void *stream);
+int stochqn_b200_logistic_loss(const real_t *X, long long ldx, const real_t *y, const real_t *sw,
+                               long long nrows, long long ncols, const real_t *w, real_t lambda,
+                               double *loss_dev, void *work, void *stream);
+
+/* ---- workspace export / import (checkpoint / resume) ----------------------------------------
+   The reference keeps all state in host-language arrays, so saveRDS / pickle of the R / Python
+   object was a checkpoint (R/allocators.R, stochqn/_optimizers.py:791-879).  These copy the same
+   fields between the device workspace and dense host arrays in the reference's layout
+   (s_mem / y_mem / F row-major [mem_size][n] without padding).  Pass NULL for fields that do not
+   exist in the optimizer or are not wanted.  Scalars travel through the public struct itself. */
+typedef struct {
+    real_t *s_mem, *y_mem;          /* [mem_size][n] */
+    real_t *grad_prev;              /* [n] */
+    real_t *x_sum, *x_avg_prev;     /* [n]  (SQN, adaQN) */
+    real_t *grad_sum_sq;            /* [n]  (adaQN) */
+    real_t *F;                      /* [fisher_size][n] (adaQN, Fisher mode) */
+} stochqn_b200_host_state;
+int stochqn_b200_export(void *ws, stochqn_b200_host_state *out);
+int stochqn_b200_import(void *ws, const stochqn_b200_host_state *in);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STOCHQN_B200_INCLUDE */

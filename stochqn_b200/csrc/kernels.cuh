@@ -1,0 +1,1001 @@
+// kernels.cuh - device kernels of the B200-native stochastic quasi-Newton step (sm_100a).
+//
+// The reference computes H*g with the latency-chained two-loop recursion
+// (src/stochqn.c:663-708): 4m dependent dot products and 2m axpys, each a full sweep
+// over an n-vector (about 12m+5 vector transfers).  Here the same product is evaluated in
+// the compact (Byrd-Nocedal-Schnabel) form, which needs only TWO sweeps over the
+// correction pairs:
+//
+//   K1  k1_dots      one coalesced pass over g, S, Y: all S'g, Y'g (+ the Gram column of
+//                    the newest pair, + g'g), fp64 accumulation, deterministic block partials
+//   K2  k2_solve     one CTA: sums the partials, folds the new Gram column in, solves the
+//                    m x m triangular systems, emits 2m+1 coefficients and the accept flag
+//   K3  k3_combine   one coalesced pass: d = gamma*g + S a + gamma*Y b, x -= step*d, and the
+//                    optimizer-specific epilogue (oLBFGS: s slot; SQN/adaQN: x_sum += x)
+//   K4  k4_pair      y = g_new - g_prev (+ y_reg*s)  | y = hess_vec, with s'y and s's
+//
+// Everything is HBM-bound streaming work (about 0.25 flop/byte); there is no GEMM here and
+// none is manufactured.  All kernels are templated on the storage type T (double / float);
+// every reduction accumulates in fp64 whatever T is.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <type_traits>
+
+namespace sqn {
+
+constexpr int kThreads = 256;          // threads per CTA for the streaming kernels
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxMem = 64;            // largest mem_size handled by the compact solve
+
+// status word written by K2 (device + mapped host copy)
+enum : int { ST_ACCEPT = 0, ST_REJECT_NONFINITE = 1, ST_NEED_EXACT_NORM = 2 };
+
+// ---- 16-byte vector access -------------------------------------------------------------
+template <typename T, int VEC> struct Pack;
+template <> struct Pack<double, 2> { double2 v; __device__ __forceinline__ double get(int i) const { return i == 0 ? v.x : v.y; }
+                                     __device__ __forceinline__ void set(int i, double a) { if (i == 0) v.x = a; else v.y = a; } };
+template <> struct Pack<float, 4>  { float4 v;  __device__ __forceinline__ float get(int i) const { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+                                     __device__ __forceinline__ void set(int i, float a) { if (i == 0) v.x = a; else if (i == 1) v.y = a; else if (i == 2) v.z = a; else v.w = a; } };
+template <typename T> struct Pack<T, 1> { T v; __device__ __forceinline__ T get(int) const { return v; }
+                                          __device__ __forceinline__ void set(int, T a) { v = a; } };
+
+template <typename T, int VEC>
+__device__ __forceinline__ Pack<T, VEC> ld_stream(const T* p)
+{
+    Pack<T, VEC> r;
+    if constexpr (VEC == 1) r.v = __ldg(p);
+    else if constexpr (sizeof(T) == 8) r.v = __ldg(reinterpret_cast<const double2*>(p));
+    else r.v = __ldg(reinterpret_cast<const float4*>(p));
+    return r;
+}
+// plain (coherent) load for buffers that the same kernel also writes
+template <typename T, int VEC>
+__device__ __forceinline__ Pack<T, VEC> ld_rw(const T* p)
+{
+    Pack<T, VEC> r;
+    if constexpr (VEC == 1) r.v = *p;
+    else if constexpr (sizeof(T) == 8) r.v = *reinterpret_cast<const double2*>(p);
+    else r.v = *reinterpret_cast<const float4*>(p);
+    return r;
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void st_vec(T* p, const Pack<T, VEC>& r)
+{
+    if constexpr (VEC == 1) *p = r.v;
+    else if constexpr (sizeof(T) == 8) *reinterpret_cast<double2*>(p) = r.v;
+    else *reinterpret_cast<float4*>(p) = r.v;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic CTA reduction of `count` per-thread accumulators: lane 0 of every warp
+// parks its warp sum in shared memory, then thread p adds the kWarps values in fixed order.
+// `emit(p, value)` is called once per accumulator by the thread that owns it.
+template <int COUNT_MAX, typename Get, typename Emit>
+__device__ __forceinline__ void block_reduce(int count, Get get, Emit emit)
+{
+    __shared__ double red[kWarps][COUNT_MAX];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    #pragma unroll
+    for (int p = 0; p < COUNT_MAX; ++p) {
+        if (p < count) {
+            double v = warp_sum(get(p));
+            if (lane == 0) red[warp][p] = v;
+        }
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < count; p += kThreads) {
+        double v = 0;
+        #pragma unroll
+        for (int w = 0; w < kWarps; ++w) v += red[w][p];
+        emit(p, v);
+    }
+}
+
+// =========================================================================================
+// K1: fused multi-dot pass.
+//
+// Layout of one partial / sum record (m = mem_size, all fp64), index k*m + j for slot j:
+//   k=0: s_j'g   k=1: y_j'g   k=2: s_j'y_c   k=3: y_j'y_c      (c = pending newest pair, rows sc_row / yc_row)
+//   [4m] g'g     [4m+1] s_c's_c
+// Rows are addressed by PHYSICAL slot; valid slots are always 0..used-1 (the ring fills
+// from slot 0 after every flush and all slots are valid once it is full).
+// Also writes grad_prev <- g when asked (the oLBFGS copy of stochqn.c:996 rides along).
+// Replaces: stochqn.c:671-679 and 702-707 (the 4m chained dots), 996.
+// =========================================================================================
+template <typename T, int MMAX, bool PENDING, int VEC>
+__global__ void __launch_bounds__(kThreads)
+k1_dots(const T* __restrict__ g, const T* __restrict__ S, const T* __restrict__ Y, size_t ld,
+        int msize, int used, int j0, const T* __restrict__ sc_row, const T* __restrict__ yc_row, long long n,
+        T* __restrict__ grad_prev, double* __restrict__ partials)
+{
+    // rows handled by this launch: physical slots j0 .. min(used, j0+MMAX)-1 (mem_size > MMAX takes several launches;
+    // g'g, s_c's_c and the grad_prev copy belong to the launch with j0 == 0)
+    S += (size_t) j0 * ld;
+    Y += (size_t) j0 * ld;
+    used -= j0;
+    if (j0 > 0) grad_prev = nullptr;
+    double a_sg[MMAX], a_yg[MMAX], a_sy[MMAX], a_yy[MMAX];
+    double a_gg = 0, a_ss = 0;
+    #pragma unroll
+    for (int j = 0; j < MMAX; ++j) { a_sg[j] = 0; a_yg[j] = 0; a_sy[j] = 0; a_yy[j] = 0; }
+
+    const long long nchunks = n / VEC;
+    const long long stride = (long long) gridDim.x * kThreads;
+    for (long long c = (long long) blockIdx.x * kThreads + threadIdx.x; c < nchunks; c += stride) {
+        const size_t off = (size_t) c * VEC;
+        Pack<T, VEC> gv = ld_stream<T, VEC>(g + off);
+        if (grad_prev) st_vec<T, VEC>(grad_prev + off, gv);
+        Pack<T, VEC> yc, sc;
+        if constexpr (PENDING) {
+            yc = ld_stream<T, VEC>(yc_row + off);
+            sc = ld_stream<T, VEC>(sc_row + off);
+        }
+        #pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            double ge = (double) gv.get(e);
+            a_gg = fma(ge, ge, a_gg);
+            if constexpr (PENDING) { double se = (double) sc.get(e); a_ss = fma(se, se, a_ss); }
+        }
+        #pragma unroll
+        for (int j = 0; j < MMAX; ++j) {
+            if (j < used) {
+                Pack<T, VEC> sv = ld_stream<T, VEC>(S + (size_t) j * ld + off);
+                Pack<T, VEC> yv = ld_stream<T, VEC>(Y + (size_t) j * ld + off);
+                #pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    double ge = (double) gv.get(e), se = (double) sv.get(e), ye = (double) yv.get(e);
+                    a_sg[j] = fma(se, ge, a_sg[j]);
+                    a_yg[j] = fma(ye, ge, a_yg[j]);
+                    if constexpr (PENDING) {
+                        double yce = (double) yc.get(e);
+                        a_sy[j] = fma(se, yce, a_sy[j]);
+                        a_yy[j] = fma(ye, yce, a_yy[j]);
+                    }
+                }
+            }
+        }
+    }
+    // scalar tail (n not a multiple of VEC): the first CTA's leading threads take one element each
+    if (VEC > 1 && blockIdx.x == 0) {
+        const long long i = nchunks * VEC + threadIdx.x;
+        if (i < n) {
+            T gs = g[i];
+            if (grad_prev) grad_prev[i] = gs;
+            double ge = (double) gs;
+            a_gg = fma(ge, ge, a_gg);
+            double yce = 0;
+            if constexpr (PENDING) {
+                yce = (double) yc_row[i];
+                double se = (double) sc_row[i];
+                a_ss = fma(se, se, a_ss);
+            }
+            #pragma unroll
+            for (int j = 0; j < MMAX; ++j) {
+                if (j < used) {
+                    double se = (double) S[(size_t) j * ld + i], ye = (double) Y[(size_t) j * ld + i];
+                    a_sg[j] = fma(se, ge, a_sg[j]);
+                    a_yg[j] = fma(ye, ge, a_yg[j]);
+                    if constexpr (PENDING) { a_sy[j] = fma(se, yce, a_sy[j]); a_yy[j] = fma(ye, yce, a_yy[j]); }
+                }
+            }
+        }
+    }
+
+    const int P = 4 * msize + 2;
+    double* out = partials + (size_t) blockIdx.x * P;
+    constexpr int NK = PENDING ? 4 : 2;
+    // reduce the (k, j) accumulators, then the two scalars
+    block_reduce<NK * MMAX + 2>(NK * MMAX + 2,
+        [&](int p) -> double {
+            if (p < MMAX) return a_sg[p < MMAX ? p : 0];
+            if (p < 2 * MMAX) return a_yg[(p - MMAX) < MMAX ? (p - MMAX) : 0];
+            if (PENDING && p < 3 * MMAX) return a_sy[(p - 2 * MMAX) < MMAX ? (p - 2 * MMAX) : 0];
+            if (PENDING && p < 4 * MMAX) return a_yy[(p - 3 * MMAX) < MMAX ? (p - 3 * MMAX) : 0];
+            return (p == NK * MMAX) ? a_gg : a_ss;
+        },
+        [&](int p, double v) {
+            if (p >= NK * MMAX) { if (j0 == 0) out[4 * msize + (p - NK * MMAX)] = v; return; }
+            const int k = p / MMAX, j = p % MMAX;
+            if (j0 + j < msize) out[k * msize + j0 + j] = (j < used) ? v : 0.0;
+        });
+    if (!PENDING && j0 == 0) {   // keep the record fully defined
+        for (int p = threadIdx.x; p < 2 * msize; p += kThreads) out[2 * msize + p] = 0.0;
+    }
+}
+
+// =========================================================================================
+// K2: partial sums -> Gram update -> compact-form coefficients (one CTA).
+//
+// Gram state (fp64, physical-slot indexed, row-major m x m):  SY[i][j] = s_i'y_j,
+// YY[i][j] = y_i'y_j, SS[i] = s_i's_i.  With pairs in logical order oldest..newest,
+// R = upper(SY), D = diag(SY), p = S'g, q0 = Y'g, and H0 = gamma*I:
+//     u = R^-1 p ;  b = -u ;  a = R^-T [ (D + gamma*YY) u - gamma*q0 ]
+//     H g = gamma*g + S a + gamma * Y b
+// gamma = hess_init if > 0, else s_l'y_l / y_l'y_l of the newest pair (stochqn.c:683-699).
+// With no pairs: d = g (stochqn.c:808-812).  The triangular solves propagate Inf/NaN exactly
+// where the two-loop's rho = 1/(y's) would (a zeroed slot gives 0/0).
+//
+// Accept test (stochqn.c:825-835): the reference rejects when the direction has a non-finite
+// entry or ||d|| > 1e3*n.  Here: non-finite sums / coefficients -> ST_REJECT_NONFINITE;
+// otherwise the triangle-inequality bound U >= ||d|| (no cancellation) - if U <= 0.99*limit the
+// step is certainly acceptable and K3 may update x in the same pass; else ST_NEED_EXACT_NORM
+// makes the host take the two-pass route that measures ||d|| exactly before touching x.
+//
+// coef layout: [0,m) a by physical slot, [m,2m) gamma*b by physical slot, [2m] gamma,
+//              [2m+1] U bound, [2m+2] g'g.
+// =========================================================================================
+struct SolveArgs {
+    int msize, used, oldest, pend;      // pend < 0: no pending pair
+    int nblocks;                        // partial records to sum (0: sums already reduced, e.g. after an all-reduce)
+    int do_solve;                       // 0: only reduce partials into sums (multi-GPU phase A)
+    int check_nan;
+    double h0;                          // hess_init (oLBFGS) or 0
+    double limit;                       // 1e3 * n_global
+};
+
+__device__ __forceinline__ bool finite_d(double v) { return isfinite(v); }
+
+__global__ void __launch_bounds__(kThreads)
+k2_solve(SolveArgs A, const double* __restrict__ partials, double* __restrict__ sums,
+         double* __restrict__ SY, double* __restrict__ YY, double* __restrict__ SS,
+         double* __restrict__ coef, int* __restrict__ status_dev, volatile int* status_host,
+         volatile double* info_host)
+{
+    const int m = A.msize;
+    const int P = 4 * m + 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (A.nblocks > 0) {
+        // fixed-order sum over CTAs: lanes stride over records, then a shuffle tree
+        for (int p = warp; p < P; p += kWarps) {
+            double v = 0;
+            for (int b = lane; b < A.nblocks; b += 32) v += partials[(size_t) b * P + p];
+            v = warp_sum(v);
+            if (lane == 0) sums[p] = v;
+        }
+        __syncthreads();
+    }
+    if (!A.do_solve || threadIdx.x != 0) return;
+
+    __shared__ double Rm[kMaxMem][kMaxMem + 1];
+    __shared__ double u[kMaxMem], w[kMaxMem], av[kMaxMem];
+    const int used = A.used;
+    const double gg = sums[4 * m];
+    if (A.pend >= 0) {                       // fold the newest pair's Gram column in
+        const int c = A.pend;
+        for (int j = 0; j < used; ++j) {
+            SY[j * m + c] = sums[2 * m + j];
+            const double yy = sums[3 * m + j];
+            YY[j * m + c] = yy;
+            YY[c * m + j] = yy;
+        }
+        SS[c] = sums[4 * m + 1];
+    }
+    double gamma = 1.0, U = sqrt(gg);
+    bool ok = finite_d(gg);
+    for (int j = 0; j < 2 * m; ++j) coef[j] = 0.0;
+    if (used > 0) {
+        auto ph = [&](int i) { int s = A.oldest + i; return s >= m ? s - m : s; };
+        if (A.h0 > 0) gamma = A.h0;
+        else { const int l = ph(used - 1); gamma = SY[l * m + l] / YY[l * m + l]; }
+        for (int i = 0; i < used; ++i)
+            for (int j = i; j < used; ++j) Rm[i][j] = SY[ph(i) * m + ph(j)];
+        for (int i = used - 1; i >= 0; --i) {          // u = R^-1 p
+            double t = sums[ph(i)];
+            for (int j = i + 1; j < used; ++j) t -= Rm[i][j] * u[j];
+            u[i] = t / Rm[i][i];
+        }
+        for (int i = 0; i < used; ++i) {               // w = (D + gamma*YY) u - gamma*q0
+            double t = 0;
+            for (int j = 0; j < used; ++j) t += YY[ph(i) * m + ph(j)] * u[j];
+            w[i] = Rm[i][i] * u[i] + gamma * t - gamma * sums[m + ph(i)];
+        }
+        for (int i = 0; i < used; ++i) {               // a = R^-T w
+            double t = w[i];
+            for (int j = 0; j < i; ++j) t -= Rm[j][i] * av[j];
+            av[i] = t / Rm[i][i];
+        }
+        U = fabs(gamma) * sqrt(gg);
+        for (int i = 0; i < used; ++i) {
+            const int s = ph(i);
+            const double a = av[i], gb = -gamma * u[i];
+            coef[s] = a;
+            coef[m + s] = gb;
+            U += fabs(a) * sqrt(SS[s]) + fabs(gb) * sqrt(YY[s * m + s]);
+            ok = ok && finite_d(a) && finite_d(gb);
+        }
+        ok = ok && finite_d(gamma);
+    }
+    ok = ok && finite_d(U);
+    coef[2 * m] = gamma;
+    coef[2 * m + 1] = U;
+    coef[2 * m + 2] = gg;
+    int st = ST_ACCEPT;
+    if (A.check_nan) {
+        if (!ok) st = ST_REJECT_NONFINITE;
+        else if (!(U <= 0.99 * A.limit)) st = ST_NEED_EXACT_NORM;
+    }
+    *status_dev = st;
+    *status_host = st;
+    info_host[0] = U;
+    info_host[1] = gamma;
+    info_host[2] = gg;
+    __threadfence_system();
+}
+
+// =========================================================================================
+// K3: fused combine + update pass.
+//   d = gamma*g + sum_j a_j s_j + sum_j (gamma b_j) y_j            (T arithmetic, FMA chain)
+//   MODE_OLBFGS : x -= step*d ; s_slot <- -step*d ; grad <- -step*d  (stochqn.c:838,1006-1007)
+//   MODE_AVG    : x -= step*d ; x_sum += x ; grad <- d               (stochqn.c:838,1067 / 1191)
+//   MODE_DIRONLY: grad <- d, and sum d^2 / non-finite count into partials (exact-norm route)
+// Does nothing unless *status_dev == ST_ACCEPT (or `force`), so a rejected direction never
+// touches x - the reference's check-before-update order (stochqn.c:825-838).
+// =========================================================================================
+enum : int { MODE_OLBFGS = 0, MODE_AVG = 1, MODE_DIRONLY = 2 };
+
+template <typename T, int MMAX, int MODE, int VEC>
+__global__ void __launch_bounds__(kThreads)
+k3_combine(const T* g_in, T* grad_out, const T* S_ro, const T* __restrict__ Y,
+           T* S_rw, size_t ld, int msize, int used, int new_slot, long long n,
+           T* __restrict__ x, T* __restrict__ x_sum, T step, const double* __restrict__ coef,
+           const int* __restrict__ status_dev, int force, double* __restrict__ partials)
+{
+    if (!force && *status_dev != ST_ACCEPT) return;
+    T ca[MMAX], cb[MMAX];
+    #pragma unroll
+    for (int j = 0; j < MMAX; ++j) {
+        ca[j] = (j < used) ? (T) coef[j] : (T) 0;
+        cb[j] = (j < used) ? (T) coef[msize + j] : (T) 0;
+    }
+    const T gamma = (T) coef[2 * msize];
+    const T nstep = -step;
+    double a_dd = 0, a_bad = 0;
+
+    auto one = [&](size_t off, auto vtag) {
+        constexpr int V = decltype(vtag)::value;
+        Pack<T, V> gv = ld_rw<T, V>(g_in + off);
+        Pack<T, V> d;
+        #pragma unroll
+        for (int e = 0; e < V; ++e) d.set(e, gamma * gv.get(e));
+        #pragma unroll
+        for (int j = 0; j < MMAX; ++j) {
+            if (j < used) {
+                // the slot about to be overwritten with the new s is still a valid (oldest) pair: read it first
+                Pack<T, V> sv = ld_rw<T, V>(S_ro + (size_t) j * ld + off);
+                Pack<T, V> yv = ld_stream<T, V>(Y + (size_t) j * ld + off);
+                #pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    T t = d.get(e);
+                    t = fma(ca[j], sv.get(e), t);
+                    t = fma(cb[j], yv.get(e), t);
+                    d.set(e, t);
+                }
+            }
+        }
+        if constexpr (MODE == MODE_DIRONLY) {
+            #pragma unroll
+            for (int e = 0; e < V; ++e) {
+                double de = (double) d.get(e);
+                a_dd = fma(de, de, a_dd);
+                if (!isfinite(de)) a_bad += 1.0;
+            }
+            st_vec<T, V>(grad_out + off, d);
+        } else {
+            Pack<T, V> xv = ld_rw<T, V>(x + off);
+            #pragma unroll
+            for (int e = 0; e < V; ++e) xv.set(e, fma(nstep, d.get(e), xv.get(e)));
+            st_vec<T, V>(x + off, xv);
+            if constexpr (MODE == MODE_OLBFGS) {
+                Pack<T, V> sn;
+                #pragma unroll
+                for (int e = 0; e < V; ++e) sn.set(e, nstep * d.get(e));
+                st_vec<T, V>(S_rw + (size_t) new_slot * ld + off, sn);
+                if (grad_out) st_vec<T, V>(grad_out + off, sn);
+            } else {
+                Pack<T, V> xs = ld_rw<T, V>(x_sum + off);
+                #pragma unroll
+                for (int e = 0; e < V; ++e) xs.set(e, xs.get(e) + xv.get(e));
+                st_vec<T, V>(x_sum + off, xs);
+                if (grad_out) st_vec<T, V>(grad_out + off, d);
+            }
+        }
+    };
+
+    const long long nchunks = n / VEC;
+    const long long stride = (long long) gridDim.x * kThreads;
+    for (long long c = (long long) blockIdx.x * kThreads + threadIdx.x; c < nchunks; c += stride)
+        one((size_t) c * VEC, std::integral_constant<int, VEC>{});
+    if (VEC > 1 && blockIdx.x == 0) {
+        const long long i = nchunks * VEC + threadIdx.x;
+        if (i < n) one((size_t) i, std::integral_constant<int, 1>{});
+    }
+    if constexpr (MODE == MODE_DIRONLY) {
+        double* out = partials + (size_t) blockIdx.x * 2;
+        block_reduce<2>(2, [&](int p) { return p == 0 ? a_dd : a_bad; }, [&](int p, double v) { out[p] = v; });
+    }
+}
+
+// After MODE_DIRONLY decided "accept": x -= step*d with d read back from grad, plus the epilogue.
+template <typename T, int MODE, int VEC>
+__global__ void __launch_bounds__(kThreads)
+k3_apply(T* grad, T* S_rw, size_t ld, int new_slot, long long n,
+         T* __restrict__ x, T* __restrict__ x_sum, T step)
+{
+    const T nstep = -step;
+    auto one = [&](size_t off, auto vtag) {
+        constexpr int V = decltype(vtag)::value;
+        Pack<T, V> d = ld_rw<T, V>(grad + off);
+        Pack<T, V> xv = ld_rw<T, V>(x + off);
+        #pragma unroll
+        for (int e = 0; e < V; ++e) xv.set(e, fma(nstep, d.get(e), xv.get(e)));
+        st_vec<T, V>(x + off, xv);
+        if constexpr (MODE == MODE_OLBFGS) {
+            Pack<T, V> sn;
+            #pragma unroll
+            for (int e = 0; e < V; ++e) sn.set(e, nstep * d.get(e));
+            st_vec<T, V>(S_rw + (size_t) new_slot * ld + off, sn);
+            st_vec<T, V>(grad + off, sn);
+        } else {
+            Pack<T, V> xs = ld_rw<T, V>(x_sum + off);
+            #pragma unroll
+            for (int e = 0; e < V; ++e) xs.set(e, xs.get(e) + xv.get(e));
+            st_vec<T, V>(x_sum + off, xs);
+        }
+    };
+    const long long nchunks = n / VEC;
+    const long long stride = (long long) gridDim.x * kThreads;
+    for (long long c = (long long) blockIdx.x * kThreads + threadIdx.x; c < nchunks; c += stride)
+        one((size_t) c * VEC, std::integral_constant<int, VEC>{});
+    if (VEC > 1 && blockIdx.x == 0) {
+        const long long i = nchunks * VEC + threadIdx.x;
+        if (i < n) one((size_t) i, std::integral_constant<int, 1>{});
+    }
+}
+
+// =========================================================================================
+// K4: correction-pair construction with the curvature dots.
+//   PAIR_GRAD_DIFF: y_slot = g - g_prev (+ y_reg*s)   (stochqn.c:915-923)
+//   PAIR_COPY     : y_slot = src (Hessian-vector product, stochqn.c:964)
+//   PAIR_DOTS_ONLY: y_slot already holds y (Fisher product)
+// partial record: [0] s'y  [1] s's   (the two dots of stochqn.c:892)
+// Optional fused copies on acceptance are done by separate tiny kernels (the decision is
+// taken on the host after the dots are known).
+// =========================================================================================
+enum : int { PAIR_GRAD_DIFF = 0, PAIR_COPY = 1, PAIR_DOTS_ONLY = 2 };
+
+template <typename T, int KIND, int VEC>
+__global__ void __launch_bounds__(kThreads)
+k4_pair(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ s, T* __restrict__ y,
+        T y_reg, long long n, double* __restrict__ partials)
+{
+    double a_sy = 0, a_ss = 0;
+    auto one = [&](size_t off, auto vtag) {
+        constexpr int V = decltype(vtag)::value;
+        Pack<T, V> sv = ld_stream<T, V>(s + off);
+        Pack<T, V> yv;
+        if constexpr (KIND == PAIR_GRAD_DIFF) {
+            Pack<T, V> av = ld_stream<T, V>(a + off), bv = ld_stream<T, V>(b + off);
+            #pragma unroll
+            for (int e = 0; e < V; ++e) {
+                T t = av.get(e) - bv.get(e);
+                if (y_reg > (T) 0) t = fma(y_reg, sv.get(e), t);
+                yv.set(e, t);
+            }
+            st_vec<T, V>(y + off, yv);
+        } else if constexpr (KIND == PAIR_COPY) {
+            yv = ld_stream<T, V>(a + off);
+            st_vec<T, V>(y + off, yv);
+        } else {
+            yv = ld_rw<T, V>(y + off);
+        }
+        #pragma unroll
+        for (int e = 0; e < V; ++e) {
+            double se = (double) sv.get(e), ye = (double) yv.get(e);
+            a_sy = fma(se, ye, a_sy);
+            a_ss = fma(se, se, a_ss);
+        }
+    };
+    const long long nchunks = n / VEC;
+    const long long stride = (long long) gridDim.x * kThreads;
+    for (long long c = (long long) blockIdx.x * kThreads + threadIdx.x; c < nchunks; c += stride)
+        one((size_t) c * VEC, std::integral_constant<int, VEC>{});
+    if (VEC > 1 && blockIdx.x == 0) {
+        const long long i = nchunks * VEC + threadIdx.x;
+        if (i < n) one((size_t) i, std::integral_constant<int, 1>{});
+    }
+    double* out = partials + (size_t) blockIdx.x * 2;
+    block_reduce<2>(2, [&](int p) { return p == 0 ? a_sy : a_ss; }, [&](int p, double v) { out[p] = v; });
+}
+
+// Sum `count`-wide partial records over CTAs into `sums` (device) and, when asked, into mapped
+// host memory.  One CTA.  Used for the 2-value records of K4 / MODE_DIRONLY.
+__global__ void __launch_bounds__(kThreads)
+k_finalize(const double* __restrict__ partials, int nblocks, int count, double* __restrict__ sums,
+           volatile double* host_out)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int p = warp; p < count; p += kWarps) {
+        double v = 0;
+        for (int b = lane; b < nblocks; b += 32) v += partials[(size_t) b * count + p];
+        v = warp_sum(v);
+        if (lane == 0) { sums[p] = v; if (host_out) host_out[p] = v; }
+    }
+    if (host_out) __threadfence_system();
+}
+
+// device -> mapped-host copy of a few doubles (after an all-reduce landed them in `sums`)
+__global__ void k_publish(const double* __restrict__ sums, int count, volatile double* host_out)
+{
+    if (threadIdx.x < count) host_out[threadIdx.x] = sums[threadIdx.x];
+    __threadfence_system();
+}
+
+// Gram bookkeeping for a slot that was zeroed by a rejected pair (quirk Q1): the slot now holds
+// s = y = 0, so every product with it is 0.
+__global__ void k_gram_zero_slot(double* SY, double* YY, double* SS, int m, int c)
+{
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        SY[j * m + c] = 0; SY[c * m + j] = 0;
+        YY[j * m + c] = 0; YY[c * m + j] = 0;
+    }
+    if (threadIdx.x == 0) SS[c] = 0;
+}
+
+// ---- iterate averaging helpers (SQN / adaQN) ---------------------------------------------
+enum : int { AVG_ADD = 0, AVG_ARCHIVE = 1, AVG_S_VECTOR = 2, AVG_SCALE = 3 };
+// AVG_ADD      : x_sum += x                                   (stochqn.c:268-284; used when a step was rejected, Q7)
+// AVG_ARCHIVE  : x_avg_prev = x_sum*inv ; x_sum = 0           (stochqn.c:1080-1081: average_from_sum + archive_x_avg)
+// AVG_S_VECTOR : x_sum *= inv ; s_slot = x_sum - x_avg_prev   (stochqn.c:861-870)
+// AVG_SCALE    : x_sum *= inv                                 (stochqn.c:1229)
+template <typename T, int OP, int VEC>
+__global__ void __launch_bounds__(kThreads)
+k_avg(T* __restrict__ x_sum, T* __restrict__ other, T* __restrict__ s_slot, T inv, long long n)
+{
+    auto one = [&](size_t off, auto vtag) {
+        constexpr int V = decltype(vtag)::value;
+        Pack<T, V> xs = ld_rw<T, V>(x_sum + off);
+        if constexpr (OP == AVG_ADD) {
+            Pack<T, V> xv = ld_rw<T, V>(other + off);
+            #pragma unroll
+            for (int e = 0; e < V; ++e) xs.set(e, xs.get(e) + xv.get(e));
+            st_vec<T, V>(x_sum + off, xs);
+        } else if constexpr (OP == AVG_ARCHIVE) {
+            Pack<T, V> z;
+            #pragma unroll
+            for (int e = 0; e < V; ++e) { xs.set(e, xs.get(e) * inv); z.set(e, (T) 0); }
+            st_vec<T, V>(other + off, xs);
+            st_vec<T, V>(x_sum + off, z);
+        } else if constexpr (OP == AVG_S_VECTOR) {
+            Pack<T, V> xp = ld_rw<T, V>(other + off), sv;
+            #pragma unroll
+            for (int e = 0; e < V; ++e) { xs.set(e, xs.get(e) * inv); sv.set(e, xs.get(e) - xp.get(e)); }
+            st_vec<T, V>(x_sum + off, xs);
+            st_vec<T, V>(s_slot + off, sv);
+        } else {
+            #pragma unroll
+            for (int e = 0; e < V; ++e) xs.set(e, xs.get(e) * inv);
+            st_vec<T, V>(x_sum + off, xs);
+        }
+    };
+    const long long nchunks = n / VEC;
+    const long long stride = (long long) gridDim.x * kThreads;
+    for (long long c = (long long) blockIdx.x * kThreads + threadIdx.x; c < nchunks; c += stride)
+        one((size_t) c * VEC, std::integral_constant<int, VEC>{});
+    if (VEC > 1 && blockIdx.x == 0) {
+        const long long i = nchunks * VEC + threadIdx.x;
+        if (i < n) one((size_t) i, std::integral_constant<int, 1>{});
+    }
+}
+
+
+// =========================================================================================
+// adaQN kernels.
+//
+// The reference's take_step for adaQN (stochqn.c:808-822 with 720-783) first updates the
+// AdaGrad / RMSProp accumulator G, then
+//   no pairs : d = g / sqrt(G + eps)
+//   pairs    : "H0" = h = g / sqrt(G + eps) (the RESCALED GRADIENT, quirk Q2) and the two-loop
+//              multiplies by it elementwise, i.e. H0 = diag(h).
+// Compact form with a diagonal H0 = diag(h):   p = S'g,  q = Y'(h.g),  W = Y' diag(h) Y,
+//   u = R^-1 p ; b = -u ; a = R^-T [ (D + W) u - q ] ;  d = h.(g + Y b) + S a
+// h depends on the current gradient, so q and W are recomputed every step.
+// =========================================================================================
+
+template <typename T>
+__device__ __forceinline__ T ada_accumulate(T g, T G, T w_old, T w_new, bool rms)
+{
+    // stochqn.c:738 / 745
+    return rms ? (w_old * G + w_new * (g * g)) : (G + g * g);
+}
+
+// KA1: one pass over g, G (+ S, Y rows j0..): updates G (and the Fisher ring row) when j0 == 0,
+// accumulates  k=0: s_j'g   k=1: y_j'(h.g)   k=2: s_j'y_c (pending)   then scalars.
+// record layout (m = mem_size): [0,m) p  [m,2m) q  [2m,3m) s_j'y_c  [3m] sum (h g)^2 (pairs) or sum h^2 (no pairs)
+//                               [3m+1] sum h^2   [3m+2] s_c's_c   [3m+3] y_c'y_c   [3m+4 ...) W (m x m, row-major, upper filled)
+template <typename T, int MMAX, bool PENDING, int VEC>
+__global__ void __launch_bounds__(kThreads)
+ka1_dots(const T* __restrict__ g, T* __restrict__ G, const T* __restrict__ S, const T* __restrict__ Y, size_t ld,
+         int msize, int used, int j0, const T* __restrict__ sc_row, const T* __restrict__ yc_row, long long n,
+         T* __restrict__ fisher_row, T scal_reg, T rmsprop_weight, double* __restrict__ partials)
+{
+    S += (size_t) j0 * ld;
+    Y += (size_t) j0 * ld;
+    const int used_all = used;
+    used -= j0;
+    const bool first = (j0 == 0);
+    const bool rms = (rmsprop_weight > (T) 0 && rmsprop_weight < (T) 1);
+    const T w_new = (T) 1 - rmsprop_weight;
+    double a_p[MMAX], a_q[MMAX], a_sy[MMAX];
+    double a_hg = 0, a_hh = 0, a_ss = 0, a_yy = 0;
+    #pragma unroll
+    for (int j = 0; j < MMAX; ++j) { a_p[j] = 0; a_q[j] = 0; a_sy[j] = 0; }
+
+    auto one = [&](size_t off, auto vtag) {
+        constexpr int V = decltype(vtag)::value;
+        Pack<T, V> gv = ld_stream<T, V>(g + off);
+        Pack<T, V> Gv = ld_rw<T, V>(G + off);
+        Pack<T, V> hv;
+        if (first) {
+            #pragma unroll
+            for (int e = 0; e < V; ++e) Gv.set(e, ada_accumulate<T>(gv.get(e), Gv.get(e), rmsprop_weight, w_new, rms));
+            st_vec<T, V>(G + off, Gv);
+            if (fisher_row) st_vec<T, V>(fisher_row + off, gv);
+        }
+        #pragma unroll
+        for (int e = 0; e < V; ++e) hv.set(e, gv.get(e) / sqrt(Gv.get(e) + scal_reg));     // stochqn.c:778 / 781
+        Pack<T, V> yc, sc;
+        if constexpr (PENDING) { yc = ld_stream<T, V>(yc_row + off); sc = ld_stream<T, V>(sc_row + off); }
+        if (first) {
+            #pragma unroll
+            for (int e = 0; e < V; ++e) {
+                double he = (double) hv.get(e), ge = (double) gv.get(e);
+                a_hh = fma(he, he, a_hh);
+                if (used_all > 0) { double t = he * ge; a_hg = fma(t, t, a_hg); }
+                if constexpr (PENDING) {
+                    double se = (double) sc.get(e), ye = (double) yc.get(e);
+                    a_ss = fma(se, se, a_ss);
+                    a_yy = fma(ye, ye, a_yy);
+                }
+            }
+        }
+        #pragma unroll
+        for (int j = 0; j < MMAX; ++j) {
+            if (j < used) {
+                Pack<T, V> sv = ld_stream<T, V>(S + (size_t) j * ld + off);
+                Pack<T, V> yv = ld_stream<T, V>(Y + (size_t) j * ld + off);
+                #pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    double ge = (double) gv.get(e), he = (double) hv.get(e);
+                    double se = (double) sv.get(e), ye = (double) yv.get(e);
+                    a_p[j] = fma(se, ge, a_p[j]);
+                    a_q[j] = fma(ye, he * ge, a_q[j]);
+                    if constexpr (PENDING) a_sy[j] = fma(se, (double) yc.get(e), a_sy[j]);
+                }
+            }
+        }
+    };
+    const long long nchunks = n / VEC;
+    const long long stride = (long long) gridDim.x * kThreads;
+    for (long long c = (long long) blockIdx.x * kThreads + threadIdx.x; c < nchunks; c += stride)
+        one((size_t) c * VEC, std::integral_constant<int, VEC>{});
+    if (VEC > 1 && blockIdx.x == 0) {
+        const long long i = nchunks * VEC + threadIdx.x;
+        if (i < n) one((size_t) i, std::integral_constant<int, 1>{});
+    }
+    const int P = 3 * msize + 4 + msize * msize;
+    double* out = partials + (size_t) blockIdx.x * P;
+    block_reduce<3 * MMAX + 4>(3 * MMAX + 4,
+        [&](int p) -> double {
+            if (p < MMAX) return a_p[p < MMAX ? p : 0];
+            if (p < 2 * MMAX) return a_q[(p - MMAX) < MMAX ? (p - MMAX) : 0];
+            if (p < 3 * MMAX) return a_sy[(p - 2 * MMAX) < MMAX ? (p - 2 * MMAX) : 0];
+            const int r = p - 3 * MMAX;
+            return r == 0 ? (used_all > 0 ? a_hg : a_hh) : r == 1 ? a_hh : r == 2 ? a_ss : a_yy;
+        },
+        [&](int p, double v) {
+            if (p >= 3 * MMAX) { if (first) out[3 * msize + (p - 3 * MMAX)] = v; return; }
+            const int k = p / MMAX, j = p % MMAX;
+            if (j0 + j < msize) out[k * msize + j0 + j] = (j < used) ? v : 0.0;
+        });
+}
+
+// KA2: one block (JB x KB) of the weighted Gram matrix W[j][k] = sum_i y_j[i] h[i] y_k[i],
+// rows j in [ja, ja+JB), k in [ka, ka+KB), restricted to j <= k entries being meaningful.
+// Reads g and the ALREADY UPDATED G to rebuild h.  Writes into the same partial record as KA1.
+template <typename T, int JB, int KB, int VEC>
+__global__ void __launch_bounds__(kThreads)
+ka2_wgram(const T* __restrict__ g, const T* __restrict__ G, const T* __restrict__ Y, size_t ld,
+          int msize, int used, int ja, int ka, long long n, T scal_reg, double* __restrict__ partials)
+{
+    double acc[JB][KB];
+    #pragma unroll
+    for (int j = 0; j < JB; ++j)
+        #pragma unroll
+        for (int k = 0; k < KB; ++k) acc[j][k] = 0;
+    auto one = [&](size_t off, auto vtag) {
+        constexpr int V = decltype(vtag)::value;
+        Pack<T, V> gv = ld_stream<T, V>(g + off), Gv = ld_stream<T, V>(G + off);
+        double h[V];
+        #pragma unroll
+        for (int e = 0; e < V; ++e) h[e] = (double) (gv.get(e) / sqrt(Gv.get(e) + scal_reg));
+        Pack<T, V> yk[KB];
+        #pragma unroll
+        for (int k = 0; k < KB; ++k) if (ka + k < used) yk[k] = ld_stream<T, V>(Y + (size_t) (ka + k) * ld + off);
+        #pragma unroll
+        for (int j = 0; j < JB; ++j) {
+            if (ja + j < used) {
+                Pack<T, V> yj = ld_stream<T, V>(Y + (size_t) (ja + j) * ld + off);
+                #pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    double t = (double) yj.get(e) * h[e];
+                    #pragma unroll
+                    for (int k = 0; k < KB; ++k) if (ka + k < used) acc[j][k] = fma(t, (double) yk[k].get(e), acc[j][k]);
+                }
+            }
+        }
+    };
+    const long long nchunks = n / VEC;
+    const long long stride = (long long) gridDim.x * kThreads;
+    for (long long c = (long long) blockIdx.x * kThreads + threadIdx.x; c < nchunks; c += stride)
+        one((size_t) c * VEC, std::integral_constant<int, VEC>{});
+    if (VEC > 1 && blockIdx.x == 0) {
+        const long long i = nchunks * VEC + threadIdx.x;
+        if (i < n) one((size_t) i, std::integral_constant<int, 1>{});
+    }
+    const int P = 3 * msize + 4 + msize * msize;
+    double* out = partials + (size_t) blockIdx.x * P + 3 * msize + 4;
+    block_reduce<JB * KB>(JB * KB,
+        [&](int p) -> double { return acc[(p / KB) < JB ? (p / KB) : 0][p % KB]; },
+        [&](int p, double v) {
+            const int j = ja + p / KB, k = ka + p % KB;
+            if (j < msize && k < msize) out[j * msize + k] = (j < used && k < used) ? v : 0.0;
+        });
+}
+
+// KA-solve: adaQN flavour of K2 (same Gram bookkeeping, diagonal-H0 algebra).
+// coef layout: [0,m) a, [m,2m) b (NOT scaled), [2m] unused, [2m+1] U, [2m+2] first scalar of the record.
+__global__ void __launch_bounds__(kThreads)
+ka_solve(SolveArgs A, const double* __restrict__ partials, double* __restrict__ sums,
+         double* __restrict__ SY, double* __restrict__ YY, double* __restrict__ SS,
+         double* __restrict__ coef, int* __restrict__ status_dev, volatile int* status_host,
+         volatile double* info_host)
+{
+    const int m = A.msize;
+    const int P = 3 * m + 4 + m * m;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (A.nblocks > 0) {
+        for (int p = warp; p < P; p += kWarps) {
+            double v = 0;
+            for (int b = lane; b < A.nblocks; b += 32) v += partials[(size_t) b * P + p];
+            v = warp_sum(v);
+            if (lane == 0) sums[p] = v;
+        }
+        __syncthreads();
+    }
+    if (!A.do_solve || threadIdx.x != 0) return;
+    __shared__ double Rm[kMaxMem][kMaxMem + 1];
+    __shared__ double u[kMaxMem], w[kMaxMem], av[kMaxMem];
+    const int used = A.used;
+    const double* W = sums + 3 * m + 4;
+    if (A.pend >= 0) {
+        const int c = A.pend;
+        for (int j = 0; j < used; ++j) SY[j * m + c] = sums[2 * m + j];
+        SS[c] = sums[3 * m + 2];
+        YY[c * m + c] = sums[3 * m + 3];
+    }
+    const double n0 = sums[3 * m];            // sum (h g)^2 with pairs, sum h^2 without
+    const double hh = sums[3 * m + 1];
+    for (int j = 0; j < 2 * m; ++j) coef[j] = 0.0;
+    double U = sqrt(n0);
+    bool ok = finite_d(n0);
+    if (used > 0) {
+        auto ph = [&](int i) { int s = A.oldest + i; return s >= m ? s - m : s; };
+        auto Wsym = [&](int a, int b) { return a <= b ? W[a * m + b] : W[b * m + a]; };
+        for (int i = 0; i < used; ++i)
+            for (int j = i; j < used; ++j) Rm[i][j] = SY[ph(i) * m + ph(j)];
+        for (int i = used - 1; i >= 0; --i) {
+            double t = sums[ph(i)];
+            for (int j = i + 1; j < used; ++j) t -= Rm[i][j] * u[j];
+            u[i] = t / Rm[i][i];
+        }
+        for (int i = 0; i < used; ++i) {
+            double t = 0;
+            for (int j = 0; j < used; ++j) t += Wsym(ph(i), ph(j)) * u[j];
+            w[i] = Rm[i][i] * u[i] + t - sums[m + ph(i)];
+        }
+        for (int i = 0; i < used; ++i) {
+            double t = w[i];
+            for (int j = 0; j < i; ++j) t -= Rm[j][i] * av[j];
+            av[i] = t / Rm[i][i];
+        }
+        const double hnorm = sqrt(hh);
+        for (int i = 0; i < used; ++i) {
+            const int s = ph(i);
+            const double a = av[i], b = -u[i];
+            coef[s] = a;
+            coef[m + s] = b;
+            U += fabs(a) * sqrt(SS[s]) + hnorm * fabs(b) * sqrt(YY[s * m + s]);
+            ok = ok && finite_d(a) && finite_d(b);
+        }
+        ok = ok && finite_d(hh);
+    }
+    ok = ok && finite_d(U);
+    coef[2 * m] = 1.0;
+    coef[2 * m + 1] = U;
+    coef[2 * m + 2] = n0;
+    int st = ST_ACCEPT;
+    if (A.check_nan) {
+        if (!ok) st = ST_REJECT_NONFINITE;
+        else if (used == 0) { if (U > A.limit) st = ST_REJECT_NONFINITE; }      // U is the exact norm here
+        else if (!(U <= 0.99 * A.limit)) st = ST_NEED_EXACT_NORM;
+    }
+    *status_dev = st;
+    *status_host = st;
+    info_host[0] = U;
+    info_host[1] = 1.0;
+    info_host[2] = n0;
+    __threadfence_system();
+}
+
+// KA3: adaQN combine + update:  h = g/sqrt(G+eps) ;  d = (used ? h*(g + sum b_j y_j) + sum a_j s_j : h)
+//      MODE_AVG: x -= step*d ; x_sum += x ; grad <- d      MODE_DIRONLY: grad <- d (+ exact norm partials)
+template <typename T, int MMAX, int MODE, int VEC>
+__global__ void __launch_bounds__(kThreads)
+ka3_combine(const T* g_in, T* grad_out, const T* __restrict__ G, const T* __restrict__ S, const T* __restrict__ Y,
+            size_t ld, int msize, int used, long long n, T* __restrict__ x, T* __restrict__ x_sum, T step,
+            T scal_reg, const double* __restrict__ coef, const int* __restrict__ status_dev, int force,
+            double* __restrict__ partials)
+{
+    if (!force && *status_dev != ST_ACCEPT) return;
+    T ca[MMAX], cb[MMAX];
+    #pragma unroll
+    for (int j = 0; j < MMAX; ++j) {
+        ca[j] = (j < used) ? (T) coef[j] : (T) 0;
+        cb[j] = (j < used) ? (T) coef[msize + j] : (T) 0;
+    }
+    const T nstep = -step;
+    double a_dd = 0, a_bad = 0;
+    auto one = [&](size_t off, auto vtag) {
+        constexpr int V = decltype(vtag)::value;
+        Pack<T, V> gv = ld_rw<T, V>(g_in + off);
+        Pack<T, V> Gv = ld_stream<T, V>(G + off);
+        Pack<T, V> d, t, acc;
+        #pragma unroll
+        for (int e = 0; e < V; ++e) { t.set(e, gv.get(e)); acc.set(e, (T) 0); }
+        #pragma unroll
+        for (int j = 0; j < MMAX; ++j) {
+            if (j < used) {
+                Pack<T, V> sv = ld_stream<T, V>(S + (size_t) j * ld + off);
+                Pack<T, V> yv = ld_stream<T, V>(Y + (size_t) j * ld + off);
+                #pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    t.set(e, fma(cb[j], yv.get(e), t.get(e)));
+                    acc.set(e, fma(ca[j], sv.get(e), acc.get(e)));
+                }
+            }
+        }
+        #pragma unroll
+        for (int e = 0; e < V; ++e) {
+            T h = gv.get(e) / sqrt(Gv.get(e) + scal_reg);
+            d.set(e, used > 0 ? fma(h, t.get(e), acc.get(e)) : h);
+        }
+        if constexpr (MODE == MODE_DIRONLY) {
+            #pragma unroll
+            for (int e = 0; e < V; ++e) {
+                double de = (double) d.get(e);
+                a_dd = fma(de, de, a_dd);
+                if (!isfinite(de)) a_bad += 1.0;
+            }
+            st_vec<T, V>(grad_out + off, d);
+        } else {
+            Pack<T, V> xv = ld_rw<T, V>(x + off);
+            #pragma unroll
+            for (int e = 0; e < V; ++e) xv.set(e, fma(nstep, d.get(e), xv.get(e)));
+            st_vec<T, V>(x + off, xv);
+            Pack<T, V> xs = ld_rw<T, V>(x_sum + off);
+            #pragma unroll
+            for (int e = 0; e < V; ++e) xs.set(e, xs.get(e) + xv.get(e));
+            st_vec<T, V>(x_sum + off, xs);
+            if (grad_out) st_vec<T, V>(grad_out + off, d);
+        }
+    };
+    const long long nchunks = n / VEC;
+    const long long stride = (long long) gridDim.x * kThreads;
+    for (long long c = (long long) blockIdx.x * kThreads + threadIdx.x; c < nchunks; c += stride)
+        one((size_t) c * VEC, std::integral_constant<int, VEC>{});
+    if (VEC > 1 && blockIdx.x == 0) {
+        const long long i = nchunks * VEC + threadIdx.x;
+        if (i < n) one((size_t) i, std::integral_constant<int, 1>{});
+    }
+    if constexpr (MODE == MODE_DIRONLY) {
+        double* out = partials + (size_t) blockIdx.x * 2;
+        block_reduce<2>(2, [&](int p) { return p == 0 ? a_dd : a_bad; }, [&](int p, double v) { out[p] = v; });
+    }
+}
+
+// =========================================================================================
+// Empirical-Fisher product (stochqn.c:936-952):  y = F' (F s) / k  over the first k ring rows.
+//   KF1: t_r = F_r's for rows r0..r0+RB   (record [k], entry r)
+//   KF2: y (+)= sum_r c_r F_r for rows r0..r0+RB, c_r = t_r / k read from device memory
+// Two sweeps of F (2k vector transfers): HBM-bound skinny GEMV pair.
+// =========================================================================================
+template <typename T, int RB, int VEC>
+__global__ void __launch_bounds__(kThreads)
+kf1_rowdots(const T* __restrict__ F, size_t ld, int r0, int rows, const T* __restrict__ s, long long n,
+            int rec, double* __restrict__ partials)
+{
+    double acc[RB];
+    #pragma unroll
+    for (int r = 0; r < RB; ++r) acc[r] = 0;
+    auto one = [&](size_t off, auto vtag) {
+        constexpr int V = decltype(vtag)::value;
+        Pack<T, V> sv = ld_stream<T, V>(s + off);
+        #pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            if (r < rows) {
+                Pack<T, V> fv = ld_stream<T, V>(F + (size_t) (r0 + r) * ld + off);
+                #pragma unroll
+                for (int e = 0; e < V; ++e) acc[r] = fma((double) fv.get(e), (double) sv.get(e), acc[r]);
+            }
+        }
+    };
+    const long long nchunks = n / VEC;
+    const long long stride = (long long) gridDim.x * kThreads;
+    for (long long c = (long long) blockIdx.x * kThreads + threadIdx.x; c < nchunks; c += stride)
+        one((size_t) c * VEC, std::integral_constant<int, VEC>{});
+    if (VEC > 1 && blockIdx.x == 0) {
+        const long long i = nchunks * VEC + threadIdx.x;
+        if (i < n) one((size_t) i, std::integral_constant<int, 1>{});
+    }
+    double* out = partials + (size_t) blockIdx.x * rec + r0;
+    block_reduce<RB>(RB, [&](int p) -> double { return acc[p < RB ? p : 0]; },
+                     [&](int p, double v) { if (p < rows) out[p] = v; });
+}
+
+template <typename T, int RB, int VEC>
+__global__ void __launch_bounds__(kThreads)
+kf2_combine(const T* __restrict__ F, size_t ld, int r0, int rows, const double* __restrict__ t, double inv_k,
+            T* __restrict__ y, int accumulate, long long n)
+{
+    T c[RB];
+    #pragma unroll
+    for (int r = 0; r < RB; ++r) c[r] = (r < rows) ? (T) t[r0 + r] : (T) 0;    // buffer_y in storage precision (stochqn.c:946-947)
+    const T alpha = (T) inv_k;
+    auto one = [&](size_t off, auto vtag) {
+        constexpr int V = decltype(vtag)::value;
+        Pack<T, V> acc;
+        #pragma unroll
+        for (int e = 0; e < V; ++e) acc.set(e, (T) 0);
+        #pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            if (r < rows) {
+                Pack<T, V> fv = ld_stream<T, V>(F + (size_t) (r0 + r) * ld + off);
+                #pragma unroll
+                for (int e = 0; e < V; ++e) acc.set(e, fma(c[r], fv.get(e), acc.get(e)));
+            }
+        }
+        Pack<T, V> yv;
+        if (accumulate) yv = ld_rw<T, V>(y + off);
+        #pragma unroll
+        for (int e = 0; e < V; ++e) yv.set(e, accumulate ? fma(alpha, acc.get(e), yv.get(e)) : alpha * acc.get(e));
+        st_vec<T, V>(y + off, yv);
+    };
+    const long long nchunks = n / VEC;
+    const long long stride = (long long) gridDim.x * kThreads;
+    for (long long c2 = (long long) blockIdx.x * kThreads + threadIdx.x; c2 < nchunks; c2 += stride)
+        one((size_t) c2 * VEC, std::integral_constant<int, VEC>{});
+    if (VEC > 1 && blockIdx.x == 0) {
+        const long long i = nchunks * VEC + threadIdx.x;
+        if (i < n) one((size_t) i, std::integral_constant<int, 1>{});
+    }
+}
+
+}  // namespace sqn

@@ -1,0 +1,54 @@
+"""Shared parity-case matrix: (name, optimizer kind, constructor kwargs, problem factory, calls, step).
+
+Used by the golden generator (reference library), the oracle tests (NumPy restatement) and the
+GPU parity tests (CUDA library), so that all three are compared on the same seeded inputs.
+The kwargs use the reference's argument names (include/stochqn.h:227-238).
+"""
+from oracle.problems import Logistic, Quadratic, Rosenbrock
+
+
+def _q():
+    return Quadratic(6)
+
+
+def _q24():
+    return Quadratic(24, seed=3, cond=50.0)
+
+
+def _r(n):
+    return lambda: Rosenbrock(n)
+
+
+def _l():
+    return Logistic()
+
+
+CASES = [
+    # --- oLBFGS ---------------------------------------------------------------------------------
+    ("olbfgs_quad", "oLBFGS", dict(mem_size=3, hess_init=0.0, y_reg=0.0, min_curvature=1e-4, check_nan=1), _q, 60, 1e-2),
+    ("olbfgs_quad_h0_yreg", "oLBFGS", dict(mem_size=3, hess_init=0.05, y_reg=1e-3, min_curvature=0.0, check_nan=1), _q, 60, 1e-2),
+    ("olbfgs_quad_nocheck", "oLBFGS", dict(mem_size=4, hess_init=0.0, y_reg=0.0, min_curvature=0.0, check_nan=0), _q24, 80, 5e-3),
+    ("olbfgs_rosen_1k", "oLBFGS", dict(mem_size=10, hess_init=0.0, y_reg=0.0, min_curvature=1e-4, check_nan=1), _r(1024), 220, 1e-4),
+    ("olbfgs_rosen_1001", "oLBFGS", dict(mem_size=10, hess_init=0.0, y_reg=0.0, min_curvature=1e-4, check_nan=1), _r(1001), 120, 1e-4),
+    ("olbfgs_rosen_m20", "oLBFGS", dict(mem_size=20, hess_init=0.0, y_reg=0.0, min_curvature=0.0, check_nan=1), _r(777), 120, 1e-4),
+    ("olbfgs_logistic", "oLBFGS", dict(mem_size=5, hess_init=0.0, y_reg=0.0, min_curvature=1e-4, check_nan=1), _l, 120, 1e-1),
+    # --- SQN -------------------------------------------------------------------------------------
+    ("sqn_hv_quad", "SQN", dict(mem_size=3, bfgs_upd_freq=3, min_curvature=1e-4, use_grad_diff=0, y_reg=0.0, check_nan=1), _q, 80, 1e-2),
+    ("sqn_gd_quad", "SQN", dict(mem_size=3, bfgs_upd_freq=3, min_curvature=1e-4, use_grad_diff=1, y_reg=0.0, check_nan=1), _q, 80, 1e-2),
+    ("sqn_hv_logistic", "SQN", dict(mem_size=5, bfgs_upd_freq=5, min_curvature=1e-4, use_grad_diff=0, y_reg=0.0, check_nan=1), _l, 150, 1e-1),
+    ("sqn_gd_logistic_yreg", "SQN", dict(mem_size=5, bfgs_upd_freq=5, min_curvature=0.0, use_grad_diff=1, y_reg=1e-4, check_nan=1), _l, 150, 1e-1),
+    ("sqn_hv_rosen_L1", "SQN", dict(mem_size=4, bfgs_upd_freq=1, min_curvature=0.0, use_grad_diff=0, y_reg=0.0, check_nan=1), _r(300), 90, 1e-4),
+    # --- adaQN -----------------------------------------------------------------------------------
+    ("adaqn_fisher_logistic", "adaQN", dict(mem_size=5, fisher_size=20, bfgs_upd_freq=5, max_incr=1.01, min_curvature=1e-4,
+                                            scal_reg=1e-4, rmsprop_weight=0.9, use_grad_diff=0, y_reg=0.0, check_nan=1), _l, 200, 1e-2),
+    ("adaqn_fisher_adagrad_logistic", "adaQN", dict(mem_size=5, fisher_size=20, bfgs_upd_freq=5, max_incr=0.0, min_curvature=1e-4,
+                                                    scal_reg=1e-4, rmsprop_weight=0.0, use_grad_diff=0, y_reg=0.0, check_nan=1), _l, 200, 1e-2),
+    ("adaqn_gd_logistic", "adaQN", dict(mem_size=5, fisher_size=20, bfgs_upd_freq=5, max_incr=1.01, min_curvature=1e-4,
+                                        scal_reg=1e-4, rmsprop_weight=0.9, use_grad_diff=1, y_reg=0.0, check_nan=1), _l, 200, 1e-2),
+    ("adaqn_gd_nomax_logistic", "adaQN", dict(mem_size=5, fisher_size=20, bfgs_upd_freq=5, max_incr=0.0, min_curvature=1e-4,
+                                              scal_reg=1e-4, rmsprop_weight=0.9, use_grad_diff=1, y_reg=0.0, check_nan=1), _l, 200, 1e-2),
+    ("adaqn_fisher_quad", "adaQN", dict(mem_size=3, fisher_size=5, bfgs_upd_freq=3, max_incr=1.01, min_curvature=1e-4,
+                                        scal_reg=1e-4, rmsprop_weight=0.9, use_grad_diff=0, y_reg=0.0, check_nan=1), _q, 90, 5e-3),
+]
+
+CASE_IDS = [c[0] for c in CASES]

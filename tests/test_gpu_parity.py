@@ -1,0 +1,99 @@
+"""GPU parity: the CUDA library, called through its C ABI, against the oracle on the same inputs.
+
+Bar (BASELINE.json north_star): task / return / counter sequences bit-exact; iterates within
+rel 1e-10 (fp64) or 1e-4 (fp32) of the reference algorithm.
+"""
+import numpy as np
+import pytest
+
+from cases import CASES, CASE_IDS
+from cuda_stepper import CudaStepper
+from oracle import stochqn_np as O
+from oracle.driver import HostStepper, discrete, run_trace
+
+pytestmark = pytest.mark.gpu
+
+ORACLE = {"oLBFGS": O.OracleOLBFGS, "SQN": O.OracleSQN, "adaQN": O.OracleAdaQN}
+RTOL = {np.float64: 1e-10, np.float32: 1e-4}
+
+
+def _run_pair(kind, kw, prob_f, calls, step, dtype, mode="device", **extra):
+    p1, p2 = prob_f(), prob_f()
+    x0 = p1.x0()
+    so = HostStepper(ORACLE[kind](len(x0), dtype=dtype, **kw), x0)
+    sc = CudaStepper(kind, x0, dtype=dtype, mode=mode, **kw, **extra)
+    to = run_trace(so, p1, calls, step, keep_x=True)
+    tc = run_trace(sc, p2, calls, step, keep_x=True)
+    sc.close()
+    return to, tc
+
+
+def _assert_parity(to, tc, rtol):
+    do, dc = discrete(to), discrete(tc)
+    for i, (a, b) in enumerate(zip(do, dc)):
+        assert a == b, "call %d: oracle %r != cuda %r" % (i, a, b)
+    worst = 0.0
+    for a, b in zip(to, tc):
+        scale = max(np.max(np.abs(a["x"])), 1e-300)
+        worst = max(worst, float(np.max(np.abs(a["x"] - b["x"])) / scale))
+    assert worst <= rtol, "iterates differ: rel-inf %.3e > %.1e" % (worst, rtol)
+
+
+@pytest.mark.parametrize("case", CASES, ids=CASE_IDS)
+def test_parity_fp64_device(case):
+    name, kind, kw, prob_f, calls, step = case
+    to, tc = _run_pair(kind, kw, prob_f, calls, step, np.float64)
+    _assert_parity(to, tc, RTOL[np.float64])
+
+
+@pytest.mark.parametrize("case", CASES, ids=CASE_IDS)
+def test_parity_fp32_device(case):
+    name, kind, kw, prob_f, calls, step = case
+    to, tc = _run_pair(kind, kw, prob_f, calls, step, np.float32)
+    # fp32: the oracle itself is only defined up to float rounding of its dots; branch decisions can
+    # legitimately flip on chaotic cases, so the discrete trace is required only while iterates agree
+    do, dc = discrete(to), discrete(tc)
+    worst = 0.0
+    for i, (a, b) in enumerate(zip(to, tc)):
+        scale = max(np.max(np.abs(a["x"])), 1e-30)
+        worst = max(worst, float(np.max(np.abs(a["x"] - b["x"])) / scale))
+        assert do[i] == dc[i], "call %d: oracle %r != cuda %r (rel err so far %.2e)" % (i, do[i], dc[i], worst)
+    assert worst <= RTOL[np.float32], "iterates differ: rel-inf %.3e" % worst
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c[0] in ("olbfgs_rosen_1001", "sqn_hv_logistic", "sqn_gd_quad",
+                                                                "adaqn_fisher_logistic", "adaqn_gd_logistic")],
+                         ids=lambda c: c[0])
+def test_parity_fp64_host_pointers(case):
+    """Drop-in compatibility mode: plain host arrays, exactly how example/c_rosen.c calls the ABI."""
+    name, kind, kw, prob_f, calls, step = case
+    to, tc = _run_pair(kind, kw, prob_f, calls, step, np.float64, mode="host")
+    _assert_parity(to, tc, RTOL[np.float64])
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c[0] in ("olbfgs_rosen_1k", "sqn_hv_logistic", "adaqn_fisher_logistic")],
+                         ids=lambda c: c[0])
+def test_grad_holds_direction_after_step(case):
+    """`grad` is overwritten as in the reference: the direction (stochqn.c:838), -step*direction for
+    oLBFGS (stochqn.c:1006).  Checked after every call that updated x."""
+    name, kind, kw, prob_f, calls, step = case
+    to, tc = _run_pair(kind, kw, prob_f, calls, step, np.float64)
+    checked = 0
+    for a, b in zip(to, tc):
+        if a["ret"] == 1 and a["info"] == 200:
+            scale = max(np.max(np.abs(a["grad"])), 1e-300)
+            assert np.max(np.abs(a["grad"] - b["grad"])) <= 1e-9 * scale
+            checked += 1
+    assert checked > 10
+
+
+def test_grad_writeback_off_leaves_grad_untouched():
+    name, kind, kw, prob_f, calls, step = CASES[3]
+    p = prob_f()
+    sc = CudaStepper(kind, p.x0(), grad_writeback=0, **kw)
+    tc = run_trace(sc, p, 40, step, keep_x=True)
+    p2 = prob_f()
+    so = HostStepper(O.OracleOLBFGS(len(p2.x0()), **kw), p2.x0())
+    to = run_trace(so, p2, 40, step, keep_x=True)
+    _assert_parity(to, tc, 1e-10)
+    sc.close()

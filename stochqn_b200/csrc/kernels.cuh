@@ -109,105 +109,118 @@ __device__ __forceinline__ void block_reduce(int count, Get get, Emit emit)
 // from slot 0 after every flush and all slots are valid once it is full).
 // Also writes grad_prev <- g when asked (the oLBFGS copy of stochqn.c:996 rides along).
 // Replaces: stochqn.c:671-679 and 702-707 (the 4m chained dots), 996.
+//
+// Work split: the CTA is kGroups row-groups x kLanes chunk-lanes.  The 2*cnt "virtual rows"
+// of a launch (S rows j0..j0+cnt-1, then Y rows j0..j0+cnt-1) are dealt RPG per group, so a
+// thread streams 2-3 probe chunks + RPG row chunks and keeps only 2*RPG+2 fp64 accumulators:
+// few registers, 3-4 CTAs per SM, every load of an iteration in flight at once.  The probe
+// chunks (g, y_c) are fetched by all groups of the CTA - one DRAM read, then L1/L2 hits.
 // =========================================================================================
-template <typename T, int MMAX, bool PENDING, int VEC>
+constexpr int kGroups = 4;
+constexpr int kLanes = kThreads / kGroups;     // 64: two warps per row-group
+
+template <typename T, int RPG, bool PENDING, int VEC>
 __global__ void __launch_bounds__(kThreads)
 k1_dots(const T* __restrict__ g, const T* __restrict__ S, const T* __restrict__ Y, size_t ld,
         int msize, int used, int j0, const T* __restrict__ sc_row, const T* __restrict__ yc_row, long long n,
         T* __restrict__ grad_prev, double* __restrict__ partials)
 {
-    // rows handled by this launch: physical slots j0 .. min(used, j0+MMAX)-1 (mem_size > MMAX takes several launches;
+    // slots handled by this launch: j0 .. j0+cnt-1 (mem_size > 2*RPG takes several launches;
     // g'g, s_c's_c and the grad_prev copy belong to the launch with j0 == 0)
-    S += (size_t) j0 * ld;
-    Y += (size_t) j0 * ld;
-    used -= j0;
-    if (j0 > 0) grad_prev = nullptr;
-    double a_sg[MMAX], a_yg[MMAX], a_sy[MMAX], a_yy[MMAX];
+    int cnt = used - j0;
+    if (cnt > 2 * RPG) cnt = 2 * RPG;               // kGroups*RPG = 4*RPG virtual rows = 2*RPG slots
+    if (cnt < 0) cnt = 0;
+    const int group = threadIdx.x / kLanes, lane = threadIdx.x % kLanes;
+    const bool lead = (group == 0) && (j0 == 0);    // owns g'g and s_c's_c
+    if (j0 > 0 || group != kGroups - 1) grad_prev = nullptr;
+    const int nv = 2 * cnt;
+    // row base pointers of this thread's RPG virtual rows (clamped: duplicates are dropped at the end)
+    const T* rows[RPG];
+    #pragma unroll
+    for (int r = 0; r < RPG; ++r) {
+        int v = group * RPG + r;
+        if (v >= nv) v = nv > 0 ? nv - 1 : 0;
+        rows[r] = (v < cnt || nv == 0) ? S + (size_t) (j0 + v) * ld : Y + (size_t) (j0 + v - cnt) * ld;
+    }
+    double a_g[RPG], a_c[RPG];
     double a_gg = 0, a_ss = 0;
     #pragma unroll
-    for (int j = 0; j < MMAX; ++j) { a_sg[j] = 0; a_yg[j] = 0; a_sy[j] = 0; a_yy[j] = 0; }
+    for (int r = 0; r < RPG; ++r) { a_g[r] = 0; a_c[r] = 0; }
 
-    const long long nchunks = n / VEC;
-    const long long stride = (long long) gridDim.x * kThreads;
-    for (long long c = (long long) blockIdx.x * kThreads + threadIdx.x; c < nchunks; c += stride) {
-        const size_t off = (size_t) c * VEC;
-        Pack<T, VEC> gv = ld_stream<T, VEC>(g + off);
-        if (grad_prev) st_vec<T, VEC>(grad_prev + off, gv);
-        Pack<T, VEC> yc, sc;
+    auto one = [&](size_t off, auto vtag) {
+        constexpr int V = decltype(vtag)::value;
+        Pack<T, V> gv = ld_stream<T, V>(g + off);
+        Pack<T, V> yc, sc, rv[RPG];
         if constexpr (PENDING) {
-            yc = ld_stream<T, VEC>(yc_row + off);
-            sc = ld_stream<T, VEC>(sc_row + off);
+            yc = ld_stream<T, V>(yc_row + off);
+            if (lead) sc = ld_stream<T, V>(sc_row + off);
         }
         #pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-            double ge = (double) gv.get(e);
-            a_gg = fma(ge, ge, a_gg);
-            if constexpr (PENDING) { double se = (double) sc.get(e); a_ss = fma(se, se, a_ss); }
-        }
-        #pragma unroll
-        for (int j = 0; j < MMAX; ++j) {
-            if (j < used) {
-                Pack<T, VEC> sv = ld_stream<T, VEC>(S + (size_t) j * ld + off);
-                Pack<T, VEC> yv = ld_stream<T, VEC>(Y + (size_t) j * ld + off);
-                #pragma unroll
-                for (int e = 0; e < VEC; ++e) {
-                    double ge = (double) gv.get(e), se = (double) sv.get(e), ye = (double) yv.get(e);
-                    a_sg[j] = fma(se, ge, a_sg[j]);
-                    a_yg[j] = fma(ye, ge, a_yg[j]);
-                    if constexpr (PENDING) {
-                        double yce = (double) yc.get(e);
-                        a_sy[j] = fma(se, yce, a_sy[j]);
-                        a_yy[j] = fma(ye, yce, a_yy[j]);
-                    }
-                }
-            }
-        }
-    }
-    // scalar tail (n not a multiple of VEC): the first CTA's leading threads take one element each
-    if (VEC > 1 && blockIdx.x == 0) {
-        const long long i = nchunks * VEC + threadIdx.x;
-        if (i < n) {
-            T gs = g[i];
-            if (grad_prev) grad_prev[i] = gs;
-            double ge = (double) gs;
-            a_gg = fma(ge, ge, a_gg);
-            double yce = 0;
-            if constexpr (PENDING) {
-                yce = (double) yc_row[i];
-                double se = (double) sc_row[i];
-                a_ss = fma(se, se, a_ss);
-            }
+        for (int r = 0; r < RPG; ++r) rv[r] = ld_stream<T, V>(rows[r] + off);
+        if (grad_prev) st_vec<T, V>(grad_prev + off, gv);
+        if (lead) {
             #pragma unroll
-            for (int j = 0; j < MMAX; ++j) {
-                if (j < used) {
-                    double se = (double) S[(size_t) j * ld + i], ye = (double) Y[(size_t) j * ld + i];
-                    a_sg[j] = fma(se, ge, a_sg[j]);
-                    a_yg[j] = fma(ye, ge, a_yg[j]);
-                    if constexpr (PENDING) { a_sy[j] = fma(se, yce, a_sy[j]); a_yy[j] = fma(ye, yce, a_yy[j]); }
-                }
+            for (int e = 0; e < V; ++e) {
+                double ge = (double) gv.get(e);
+                a_gg = fma(ge, ge, a_gg);
+                if constexpr (PENDING) { double se = (double) sc.get(e); a_ss = fma(se, se, a_ss); }
             }
         }
+        #pragma unroll
+        for (int r = 0; r < RPG; ++r) {
+            #pragma unroll
+            for (int e = 0; e < V; ++e) {
+                double re = (double) rv[r].get(e);
+                a_g[r] = fma(re, (double) gv.get(e), a_g[r]);
+                if constexpr (PENDING) a_c[r] = fma(re, (double) yc.get(e), a_c[r]);
+            }
+        }
+    };
+    const long long nchunks = n / VEC;
+    const long long stride = (long long) gridDim.x * kLanes;
+    for (long long c = (long long) blockIdx.x * kLanes + lane; c < nchunks; c += stride)
+        one((size_t) c * VEC, std::integral_constant<int, VEC>{});
+    if (VEC > 1 && blockIdx.x == 0) {               // scalar tail: n not a multiple of VEC
+        const long long i = nchunks * VEC + lane;
+        if (i < n) one((size_t) i, std::integral_constant<int, 1>{});
     }
 
+    // ---- CTA reduction: two warps per group, fixed order ----
+    constexpr int NA = 2 * RPG + 2;
+    __shared__ double red[kWarps][NA];
+    const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
+    #pragma unroll
+    for (int p = 0; p < NA; ++p) {
+        double v = p < RPG ? a_g[p < RPG ? p : 0] : p < 2 * RPG ? a_c[(p - RPG) < RPG ? (p - RPG) : 0] : p == 2 * RPG ? a_gg : a_ss;
+        v = warp_sum(v);
+        if (wl == 0) red[warp][p] = v;
+    }
+    __syncthreads();
     const int P = 4 * msize + 2;
     double* out = partials + (size_t) blockIdx.x * P;
-    constexpr int NK = PENDING ? 4 : 2;
-    // reduce the (k, j) accumulators, then the two scalars
-    block_reduce<NK * MMAX + 2>(NK * MMAX + 2,
-        [&](int p) -> double {
-            if (p < MMAX) return a_sg[p < MMAX ? p : 0];
-            if (p < 2 * MMAX) return a_yg[(p - MMAX) < MMAX ? (p - MMAX) : 0];
-            if (PENDING && p < 3 * MMAX) return a_sy[(p - 2 * MMAX) < MMAX ? (p - 2 * MMAX) : 0];
-            if (PENDING && p < 4 * MMAX) return a_yy[(p - 3 * MMAX) < MMAX ? (p - 3 * MMAX) : 0];
-            return (p == NK * MMAX) ? a_gg : a_ss;
-        },
-        [&](int p, double v) {
-            if (p >= NK * MMAX) { if (j0 == 0) out[4 * msize + (p - NK * MMAX)] = v; return; }
-            const int k = p / MMAX, j = p % MMAX;
-            if (j0 + j < msize) out[k * msize + j0 + j] = (j < used) ? v : 0.0;
-        });
-    if (!PENDING && j0 == 0) {   // keep the record fully defined
-        for (int p = threadIdx.x; p < 2 * msize; p += kThreads) out[2 * msize + p] = 0.0;
+    constexpr int WPG = kWarps / kGroups;            // warps per group
+    for (int t = threadIdx.x; t < kGroups * NA; t += kThreads) {
+        const int gi = t / NA, p = t % NA;
+        double v = 0;
+        #pragma unroll
+        for (int w = 0; w < WPG; ++w) v += red[gi * WPG + w][p];
+        if (p >= 2 * RPG) {                          // scalars: only the lead group's are meaningful
+            if (gi == 0 && j0 == 0) out[4 * msize + (p - 2 * RPG)] = v;
+            continue;
+        }
+        const int r = p % RPG, vrow = gi * RPG + r;
+        if (vrow >= nv) continue;                    // clamped duplicate
+        const bool is_s = vrow < cnt;
+        const int j = j0 + (is_s ? vrow : vrow - cnt);
+        const int k = (p < RPG) ? (is_s ? 0 : 1) : (is_s ? 2 : 3);
+        if (k < 2 || PENDING) out[k * msize + j] = v;
+    }
+    // entries this launch owns but did not compute: slots >= used (first launch) and the k=2,3 blocks without a pending pair
+    if (j0 == 0) {
+        for (int t = threadIdx.x; t < 4 * msize; t += kThreads) {
+            const int k = t / msize, j = t % msize;
+            if (j >= used || (!PENDING && k >= 2)) out[t] = 0.0;
+        }
     }
 }
 
@@ -332,16 +345,24 @@ k2_solve(SolveArgs A, const double* __restrict__ partials, double* __restrict__ 
 
 // =========================================================================================
 // K3: fused combine + update pass.
-//   d = gamma*g + sum_j a_j s_j + sum_j (gamma b_j) y_j            (T arithmetic, FMA chain)
+//   d = gamma*g + sum_j a_j s_j + sum_j (gamma b_j) y_j            (T arithmetic, FMA chains)
 //   MODE_OLBFGS : x -= step*d ; s_slot <- -step*d ; grad <- -step*d  (stochqn.c:838,1006-1007)
 //   MODE_AVG    : x -= step*d ; x_sum += x ; grad <- d               (stochqn.c:838,1067 / 1191)
 //   MODE_DIRONLY: grad <- d, and sum d^2 / non-finite count into partials (exact-norm route)
 // Does nothing unless *status_dev == ST_ACCEPT (or `force`), so a rejected direction never
 // touches x - the reference's check-before-update order (stochqn.c:825-838).
+//
+// Same work split as K1: kGroups row-groups x kLanes chunk-lanes.  Each group forms the partial
+// combination of its RPG virtual rows (S rows with a_j, Y rows with gamma*b_j; group 0 adds
+// gamma*g), the four partials meet in shared memory (double-buffered, one barrier per
+// iteration), every group adds them in the same order and then does ONE of the output jobs:
+// group 0 updates x (and x_sum), group 1 stores the new s, group 2 stores grad.
+// The barrier also orders the read of the slot that is about to be overwritten (it is still a
+// valid, oldest pair) and of `grad` before the stores that replace them.
 // =========================================================================================
 enum : int { MODE_OLBFGS = 0, MODE_AVG = 1, MODE_DIRONLY = 2 };
 
-template <typename T, int MMAX, int MODE, int VEC>
+template <typename T, int RPG, int MODE, int VEC>
 __global__ void __launch_bounds__(kThreads)
 k3_combine(const T* g_in, T* grad_out, const T* S_ro, const T* __restrict__ Y,
            T* S_rw, size_t ld, int msize, int used, int new_slot, long long n,
@@ -349,73 +370,110 @@ k3_combine(const T* g_in, T* grad_out, const T* S_ro, const T* __restrict__ Y,
            const int* __restrict__ status_dev, int force, double* __restrict__ partials)
 {
     if (!force && *status_dev != ST_ACCEPT) return;
-    T ca[MMAX], cb[MMAX];
+    const int group = threadIdx.x / kLanes, lane = threadIdx.x % kLanes;
+    const int nv = 2 * used;
+    const T* rows[RPG];
+    T cf[RPG];
     #pragma unroll
-    for (int j = 0; j < MMAX; ++j) {
-        ca[j] = (j < used) ? (T) coef[j] : (T) 0;
-        cb[j] = (j < used) ? (T) coef[msize + j] : (T) 0;
+    for (int r = 0; r < RPG; ++r) {
+        int v = group * RPG + r;
+        const bool live = v < nv;
+        if (!live) v = nv > 0 ? nv - 1 : 0;
+        const bool is_s = (v < used) || nv == 0;
+        const int j = is_s ? v : v - used;
+        rows[r] = is_s ? S_ro + (size_t) j * ld : Y + (size_t) j * ld;
+        cf[r] = live ? (T) coef[is_s ? j : msize + j] : (T) 0;
     }
-    const T gamma = (T) coef[2 * msize];
+    const T gamma = (group == 0) ? (T) coef[2 * msize] : (T) 0;
     const T nstep = -step;
     double a_dd = 0, a_bad = 0;
+    __shared__ __align__(16) T xchg[2][kGroups][kLanes * (VEC > 1 ? VEC : 1)];
+    int buf = 0;
 
-    auto one = [&](size_t off, auto vtag) {
+    auto one = [&](size_t off, bool valid, auto vtag) {
         constexpr int V = decltype(vtag)::value;
-        Pack<T, V> gv = ld_rw<T, V>(g_in + off);
-        Pack<T, V> d;
+        Pack<T, V> part;
         #pragma unroll
-        for (int e = 0; e < V; ++e) d.set(e, gamma * gv.get(e));
-        #pragma unroll
-        for (int j = 0; j < MMAX; ++j) {
-            if (j < used) {
-                // the slot about to be overwritten with the new s is still a valid (oldest) pair: read it first
-                Pack<T, V> sv = ld_rw<T, V>(S_ro + (size_t) j * ld + off);
-                Pack<T, V> yv = ld_stream<T, V>(Y + (size_t) j * ld + off);
+        for (int e = 0; e < V; ++e) part.set(e, (T) 0);
+        if (valid) {
+            Pack<T, V> rv[RPG], gv;
+            #pragma unroll
+            for (int r = 0; r < RPG; ++r) rv[r] = ld_rw<T, V>(rows[r] + off);
+            if (group == 0) {
+                gv = ld_rw<T, V>(g_in + off);
                 #pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    T t = d.get(e);
-                    t = fma(ca[j], sv.get(e), t);
-                    t = fma(cb[j], yv.get(e), t);
-                    d.set(e, t);
+                for (int e = 0; e < V; ++e) part.set(e, gamma * gv.get(e));
+            }
+            #pragma unroll
+            for (int r = 0; r < RPG; ++r) {
+                #pragma unroll
+                for (int e = 0; e < V; ++e) part.set(e, fma(cf[r], rv[r].get(e), part.get(e)));
+            }
+        }
+        T* slot = &xchg[buf][group][lane * V];
+        #pragma unroll
+        for (int e = 0; e < V; ++e) slot[e] = part.get(e);
+        __syncthreads();
+        if (valid) {
+            Pack<T, V> d;
+            #pragma unroll
+            for (int e = 0; e < V; ++e) {
+                T t = xchg[buf][0][lane * V + e];
+                #pragma unroll
+                for (int q = 1; q < kGroups; ++q) t += xchg[buf][q][lane * V + e];
+                d.set(e, t);
+            }
+            if constexpr (MODE == MODE_DIRONLY) {
+                if (group == 0) {
+                    #pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        double de = (double) d.get(e);
+                        a_dd = fma(de, de, a_dd);
+                        if (!isfinite(de)) a_bad += 1.0;
+                    }
+                } else if (group == 2) st_vec<T, V>(grad_out + off, d);
+            } else {
+                if (group == 0) {
+                    Pack<T, V> xv = ld_rw<T, V>(x + off);
+                    #pragma unroll
+                    for (int e = 0; e < V; ++e) xv.set(e, fma(nstep, d.get(e), xv.get(e)));
+                    st_vec<T, V>(x + off, xv);
+                    if constexpr (MODE == MODE_AVG) {
+                        Pack<T, V> xs = ld_rw<T, V>(x_sum + off);
+                        #pragma unroll
+                        for (int e = 0; e < V; ++e) xs.set(e, xs.get(e) + xv.get(e));
+                        st_vec<T, V>(x_sum + off, xs);
+                    }
+                } else if (group == 1) {
+                    if constexpr (MODE == MODE_OLBFGS) {
+                        Pack<T, V> sn;
+                        #pragma unroll
+                        for (int e = 0; e < V; ++e) sn.set(e, nstep * d.get(e));
+                        st_vec<T, V>(S_rw + (size_t) new_slot * ld + off, sn);
+                    }
+                } else if (group == 2) {
+                    if (grad_out) {
+                        if constexpr (MODE == MODE_OLBFGS) {
+                            #pragma unroll
+                            for (int e = 0; e < V; ++e) d.set(e, nstep * d.get(e));
+                        }
+                        st_vec<T, V>(grad_out + off, d);
+                    }
                 }
             }
         }
-        if constexpr (MODE == MODE_DIRONLY) {
-            #pragma unroll
-            for (int e = 0; e < V; ++e) {
-                double de = (double) d.get(e);
-                a_dd = fma(de, de, a_dd);
-                if (!isfinite(de)) a_bad += 1.0;
-            }
-            st_vec<T, V>(grad_out + off, d);
-        } else {
-            Pack<T, V> xv = ld_rw<T, V>(x + off);
-            #pragma unroll
-            for (int e = 0; e < V; ++e) xv.set(e, fma(nstep, d.get(e), xv.get(e)));
-            st_vec<T, V>(x + off, xv);
-            if constexpr (MODE == MODE_OLBFGS) {
-                Pack<T, V> sn;
-                #pragma unroll
-                for (int e = 0; e < V; ++e) sn.set(e, nstep * d.get(e));
-                st_vec<T, V>(S_rw + (size_t) new_slot * ld + off, sn);
-                if (grad_out) st_vec<T, V>(grad_out + off, sn);
-            } else {
-                Pack<T, V> xs = ld_rw<T, V>(x_sum + off);
-                #pragma unroll
-                for (int e = 0; e < V; ++e) xs.set(e, xs.get(e) + xv.get(e));
-                st_vec<T, V>(x_sum + off, xs);
-                if (grad_out) st_vec<T, V>(grad_out + off, d);
-            }
-        }
+        buf ^= 1;
     };
 
     const long long nchunks = n / VEC;
-    const long long stride = (long long) gridDim.x * kThreads;
-    for (long long c = (long long) blockIdx.x * kThreads + threadIdx.x; c < nchunks; c += stride)
-        one((size_t) c * VEC, std::integral_constant<int, VEC>{});
-    if (VEC > 1 && blockIdx.x == 0) {
-        const long long i = nchunks * VEC + threadIdx.x;
-        if (i < n) one((size_t) i, std::integral_constant<int, 1>{});
+    const long long stride = (long long) gridDim.x * kLanes;
+    for (long long base = (long long) blockIdx.x * kLanes; base < nchunks; base += stride) {   // block-uniform trip count
+        const long long c = base + lane;
+        one((size_t) c * VEC, c < nchunks, std::integral_constant<int, VEC>{});
+    }
+    if (VEC > 1 && blockIdx.x == 0 && nchunks * VEC < n) {
+        const long long i = nchunks * VEC + lane;
+        one((size_t) i, i < n, std::integral_constant<int, 1>{});
     }
     if constexpr (MODE == MODE_DIRONLY) {
         double* out = partials + (size_t) blockIdx.x * 2;

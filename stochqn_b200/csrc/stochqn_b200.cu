@@ -205,28 +205,55 @@ bool aligned16(const void* p) { return (((uintptr_t) p) & 15u) == 0; }
 
 int bucket(int used)
 {
-    return used <= 4 ? 4 : used <= 8 ? 8 : used <= 12 ? 12 : 16;
+    return used <= 4 ? 4 : used <= 8 ? 8 : used <= 10 ? 10 : used <= 12 ? 12 : 16;
 }
 
-template <int MMAX, bool PENDING, int VEC>
-void launch_k1_t(Ctx* c, const real_t* g, const real_t* S, const real_t* Y, int used, int j0,
-                 const real_t* sc, const real_t* yc, real_t* grad_prev)
+int k1_grid(Ctx* c, const void* func, long long chunks)
 {
-    const int grid = grid_for(c, c->n / VEC);
-    k1_dots<real_t, MMAX, PENDING, VEC><<<grid, kThreads, 0, c->stream>>>(
-        g, S, Y, c->ld, c->msize, used, j0, sc, yc, c->n, grad_prev, c->partials);
+    // persistent-style launch: as many CTAs as are resident at once (occupancy x SMs), grid-stride inside
+    static std::mutex mu;
+    static std::unordered_map<const void*, int> occ;
+    int per_sm = 0;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = occ.find(func);
+        if (it == occ.end()) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+            occ[func] = per_sm;
+        } else per_sm = it->second;
+    }
+    long long g = (chunks + kLanes - 1) / kLanes;
+    const long long cap = (long long) c->sm_count * per_sm;
+    if (g > cap) g = cap;
+    if (g > c->max_grid) g = c->max_grid;
+    if (g < 1) g = 1;
+    return (int) g;
+}
+
+template <int RPG, bool PENDING, int VEC>
+int launch_k1_t(Ctx* c, const real_t* g, const real_t* S, const real_t* Y, int used, int j0,
+                const real_t* sc, const real_t* yc, real_t* grad_prev)
+{
+    auto kern = k1_dots<real_t, RPG, PENDING, VEC>;
+    const int grid = k1_grid(c, (const void*) kern, c->n / VEC);
+    kern<<<grid, kThreads, 0, c->stream>>>(g, S, Y, c->ld, c->msize, used, j0, sc, yc, c->n, grad_prev, c->partials);
     COUNT_LAUNCH();
+    return grid;
 }
 
 template <bool PENDING, int VEC>
-void launch_k1_m(Ctx* c, int mm, const real_t* g, const real_t* S, const real_t* Y, int used, int j0,
-                 const real_t* sc, const real_t* yc, real_t* gp)
+int launch_k1_m(Ctx* c, int rpg, const real_t* g, const real_t* S, const real_t* Y, int used, int j0,
+                const real_t* sc, const real_t* yc, real_t* gp)
 {
-    switch (mm) {
-        case 4:  launch_k1_t<4, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp); break;
-        case 8:  launch_k1_t<8, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp); break;
-        case 12: launch_k1_t<12, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp); break;
-        default: launch_k1_t<16, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp); break;
+    switch (rpg) {
+        case 1:  return launch_k1_t<1, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp);
+        case 2:  return launch_k1_t<2, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp);
+        case 3:  return launch_k1_t<3, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp);
+        case 4:  return launch_k1_t<4, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp);
+        case 5:  return launch_k1_t<5, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp);
+        case 6:  return launch_k1_t<6, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp);
+        case 7:  return launch_k1_t<7, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp);
+        default: return launch_k1_t<8, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp);
     }
 }
 
@@ -236,62 +263,72 @@ int launch_k1(Ctx* c, const real_t* g, const real_t* S, const real_t* Y, int use
     const bool vec = aligned16(g) && aligned16(grad_prev);
     const real_t* sc = pend >= 0 ? S + (size_t) pend * c->ld : nullptr;
     const real_t* yc = pend >= 0 ? Y + (size_t) pend * c->ld : nullptr;
-    int j0 = 0;
+    // RPG rows per group x 4 groups = 2*slots virtual rows -> up to 16 slots per launch; all launches of one
+    // step use the same RPG (hence the same grid) so that they fill the same partial records
+    const int per_launch = used > 16 ? 16 : used;
+    int rpg = (2 * per_launch + kGroups - 1) / kGroups;
+    if (rpg < 1) rpg = 1;
+    int j0 = 0, grid = 1;
     do {
-        const int rows = used - j0 > 16 ? 16 : used - j0;
-        const int mm = bucket(rows);
         if (pend >= 0) {
-            if (vec) launch_k1_m<true, VECW>(c, mm, g, S, Y, used, j0, sc, yc, grad_prev);
-            else     launch_k1_m<true, 1>(c, mm, g, S, Y, used, j0, sc, yc, grad_prev);
+            grid = vec ? launch_k1_m<true, VECW>(c, rpg, g, S, Y, used, j0, sc, yc, grad_prev)
+                       : launch_k1_m<true, 1>(c, rpg, g, S, Y, used, j0, sc, yc, grad_prev);
         } else {
-            if (vec) launch_k1_m<false, VECW>(c, mm, g, S, Y, used, j0, sc, yc, grad_prev);
-            else     launch_k1_m<false, 1>(c, mm, g, S, Y, used, j0, sc, yc, grad_prev);
+            grid = vec ? launch_k1_m<false, VECW>(c, rpg, g, S, Y, used, j0, sc, yc, grad_prev)
+                       : launch_k1_m<false, 1>(c, rpg, g, S, Y, used, j0, sc, yc, grad_prev);
         }
-        j0 += 16;
+        j0 += 2 * rpg;
     } while (j0 < used);
-    return grid_for(c, c->n / (vec ? VECW : 1));
+    return grid;
 }
 
-template <int MMAX, int MODE, int VEC>
-void launch_k3_t(Ctx* c, const real_t* g, real_t* gout, real_t* S, const real_t* Y, int used, int new_slot,
-                 real_t* x, real_t* x_sum, real_t step, int force)
+template <int RPG, int MODE, int VEC>
+int launch_k3_t(Ctx* c, const real_t* g, real_t* gout, real_t* S, const real_t* Y, int used, int new_slot,
+                real_t* x, real_t* x_sum, real_t step, int force)
 {
-    const int grid = grid_for(c, c->n / VEC);
-    k3_combine<real_t, MMAX, MODE, VEC><<<grid, kThreads, 0, c->stream>>>(
-        g, gout, S, Y, S, c->ld, c->msize, used, new_slot, c->n, x, x_sum, step, c->coef, c->status_dev, force,
-        c->partials);
+    auto kern = k3_combine<real_t, RPG, MODE, VEC>;
+    const int grid = k1_grid(c, (const void*) kern, c->n / VEC);
+    kern<<<grid, kThreads, 0, c->stream>>>(g, gout, S, Y, S, c->ld, c->msize, used, new_slot, c->n, x, x_sum, step,
+                                           c->coef, c->status_dev, force, c->partials);
     COUNT_LAUNCH();
+    return grid;
 }
 
 template <int MODE, int VEC>
-void launch_k3_m(Ctx* c, int mm, const real_t* g, real_t* gout, real_t* S, const real_t* Y, int used, int new_slot,
-                 real_t* x, real_t* x_sum, real_t step, int force)
+int launch_k3_m(Ctx* c, int rpg, const real_t* g, real_t* gout, real_t* S, const real_t* Y, int used, int new_slot,
+                real_t* x, real_t* x_sum, real_t step, int force)
 {
-    switch (mm) {
-        case 4:  launch_k3_t<4, MODE, VEC>(c, g, gout, S, Y, used, new_slot, x, x_sum, step, force); break;
-        case 8:  launch_k3_t<8, MODE, VEC>(c, g, gout, S, Y, used, new_slot, x, x_sum, step, force); break;
-        case 12: launch_k3_t<12, MODE, VEC>(c, g, gout, S, Y, used, new_slot, x, x_sum, step, force); break;
-        case 16: launch_k3_t<16, MODE, VEC>(c, g, gout, S, Y, used, new_slot, x, x_sum, step, force); break;
-        case 32: launch_k3_t<32, MODE, VEC>(c, g, gout, S, Y, used, new_slot, x, x_sum, step, force); break;
-        default: launch_k3_t<64, MODE, VEC>(c, g, gout, S, Y, used, new_slot, x, x_sum, step, force); break;
+#define K3_RPG(R) case R: return launch_k3_t<R, MODE, VEC>(c, g, gout, S, Y, used, new_slot, x, x_sum, step, force)
+    switch (rpg) {
+        K3_RPG(1); K3_RPG(2); K3_RPG(3); K3_RPG(4); K3_RPG(5); K3_RPG(6); K3_RPG(7); K3_RPG(8);
+        K3_RPG(12); K3_RPG(16); K3_RPG(24);
+        default: return launch_k3_t<32, MODE, VEC>(c, g, gout, S, Y, used, new_slot, x, x_sum, step, force);
     }
+#undef K3_RPG
 }
 
-int bucket3(int used) { return used <= 16 ? bucket(used) : used <= 32 ? 32 : 64; }
+int bucket3(int used) { return used <= 16 ? bucket(used) : used <= 32 ? 32 : 64; }    // MMAX buckets of the adaQN combine
+
+int rpg_for_k3(int used)
+{
+    int rpg = (2 * used + kGroups - 1) / kGroups;
+    if (rpg < 1) rpg = 1;
+    if (rpg <= 8) return rpg;
+    return rpg <= 12 ? 12 : rpg <= 16 ? 16 : rpg <= 24 ? 24 : 32;
+}
 
 int launch_k3(Ctx* c, int mode, const real_t* g, real_t* gout, real_t* S, const real_t* Y, int used, int new_slot,
               real_t* x, real_t* x_sum, real_t step, int force)
 {
     const bool vec = aligned16(g) && aligned16(gout) && aligned16(x) && aligned16(x_sum);
-    const int mm = bucket3(used);
-#define K3_CASE(M)                                                                                         \
-    if (vec) launch_k3_m<M, VECW>(c, mm, g, gout, S, Y, used, new_slot, x, x_sum, step, force);            \
-    else     launch_k3_m<M, 1>(c, mm, g, gout, S, Y, used, new_slot, x, x_sum, step, force)
+    const int rpg = rpg_for_k3(used);
+#define K3_CASE(M)                                                                                               \
+    return vec ? launch_k3_m<M, VECW>(c, rpg, g, gout, S, Y, used, new_slot, x, x_sum, step, force)             \
+               : launch_k3_m<M, 1>(c, rpg, g, gout, S, Y, used, new_slot, x, x_sum, step, force)
     if (mode == MODE_OLBFGS) { K3_CASE(MODE_OLBFGS); }
     else if (mode == MODE_AVG) { K3_CASE(MODE_AVG); }
     else { K3_CASE(MODE_DIRONLY); }
 #undef K3_CASE
-    return grid_for(c, c->n / (vec ? VECW : 1));
 }
 
 void launch_k3_apply(Ctx* c, int mode, real_t* grad, real_t* S, int new_slot, real_t* x, real_t* x_sum, real_t step)

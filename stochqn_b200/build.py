@@ -73,6 +73,12 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
             subprocess.run(cmd, check=True)
     out = {t: lib_path(t) for t in tags}
     out["_ptxas"] = logs
+    # host-side helper for the end-to-end bench leg (CPU gradient callback, plain C + OpenMP)
+    hsrc = os.path.join(REPO, "tools", "host_callbacks.c")
+    hout = os.path.join(LIBDIR, "libhostcb_f64.so")
+    if force or not os.path.exists(hout) or os.path.getmtime(hout) < os.path.getmtime(hsrc):
+        subprocess.run(["gcc", "-O2", "-fopenmp", "-march=x86-64-v3", "-fPIC", "-shared", hsrc, "-o", hout], check=True)
+    out["hostcb_f64"] = hout
     return out
 
 

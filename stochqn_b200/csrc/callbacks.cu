@@ -73,6 +73,19 @@ rosen_grad_kernel(const real_t* __restrict__ x, real_t* __restrict__ g, long lon
     }
 }
 
+// halo exchange for sharded Rosenbrock: every rank contributes its first and last element to a zero-padded
+// [2*world] record, one sum all-reduce turns it into an all-gather, then each rank picks its neighbours' values
+__global__ void rosen_halo_pack(const real_t* __restrict__ x, long long n, int rank, int world, double* __restrict__ rec)
+{
+    const int t = threadIdx.x;
+    if (t < 2 * world) rec[t] = (t == 2 * rank) ? (double) x[0] : (t == 2 * rank + 1) ? (double) x[n - 1] : 0.0;
+}
+__global__ void rosen_halo_unpack(const double* __restrict__ rec, int rank, int world, real_t* __restrict__ halo)
+{
+    if (threadIdx.x == 0) halo[0] = rank > 0 ? (real_t) rec[2 * (rank - 1) + 1] : (real_t) 0;
+    if (threadIdx.x == 1) halo[1] = rank < world - 1 ? (real_t) rec[2 * (rank + 1)] : (real_t) 0;
+}
+
 __device__ double g_fun_partials[2048];
 __device__ unsigned int g_fun_ticket = 0;
 
@@ -242,6 +255,16 @@ int stochqn_b200_rosenbrock_fun(const real_t* x, long long n_local, long long of
 {
     rosen_fun_kernel<<<grid_1d(n_local, 1024), kT, 0, (cudaStream_t) stream>>>(x, n_local, offset, n_global, halo, f_dev);
     return check_launch("rosenbrock_fun");
+}
+
+int stochqn_b200_rosenbrock_halo(const real_t* x, long long n_local, int rank, int world_size, void* comm,
+                                 real_t* halo, double* scratch, void* stream)
+{
+    if (world_size > 512) return -1;
+    rosen_halo_pack<<<1, 1024, 0, (cudaStream_t) stream>>>(x, n_local, rank, world_size, scratch);
+    if (int r = stochqn_b200_allreduce_f64(comm, scratch, (size_t) 2 * world_size, stream)) return r;
+    rosen_halo_unpack<<<1, 32, 0, (cudaStream_t) stream>>>(scratch, rank, world_size, halo);
+    return check_launch("rosenbrock_halo", 2);
 }
 
 size_t stochqn_b200_logistic_work_size(long long nrows, long long ncols)

@@ -1,0 +1,41 @@
+/* Host-side (CPU, OpenMP) gradient callback used by bench.py's end-to-end leg: the caller of the
+ * drop-in C ABI keeps x and grad in HOST memory and evaluates the chained Rosenbrock gradient itself,
+ * exactly what a user of the reference does (example/c_rosen.c:26-41, formulas only).
+ * Shard-aware: x[0..n_local) starts at global index `offset` of a vector of length n_global;
+ * halo_left / halo_right are x[offset-1] and x[offset+n_local] (ignored at the global ends). */
+#include <stddef.h>
+#ifdef USE_FLOAT
+typedef float real_t;
+#else
+typedef double real_t;
+#endif
+
+void host_rosenbrock_grad(const real_t *x, real_t *g, long long n_local, long long offset, long long n_global,
+                          double halo_left, double halo_right)
+{
+    #pragma omp parallel for schedule(static)
+    for (long long i = 0; i < n_local; i++) {
+        const long long gi = i + offset;
+        const double xc = (double) x[i];
+        double out = 0.0;
+        if (gi > 0) {
+            const double xm = (i > 0) ? (double) x[i - 1] : halo_left;
+            out += 200.0 * (xc - xm * xm);
+        }
+        if (gi < n_global - 1) {
+            const double xp = (i < n_local - 1) ? (double) x[i + 1] : halo_right;
+            out -= 400.0 * (xp - xc * xc) * xc;
+            out -= 2.0 * (1.0 - xc);
+        }
+        g[i] = (real_t) out;
+    }
+}
+
+void host_rosenbrock_x0(real_t *x, long long n_local, long long offset)
+{
+    #pragma omp parallel for schedule(static)
+    for (long long i = 0; i < n_local; i++) {
+        unsigned int h = (unsigned int) ((unsigned long long) (i + offset) * 2654435761ull);
+        x[i] = (real_t) (0.95 + 1e-4 * (double) (h % 1000u));
+    }
+}

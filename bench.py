@@ -331,6 +331,8 @@ def run_e2e(args, lib, abi, rank, world, local_rank, n, offset, n_local, comm, d
     hostcb = C.CDLL(hostcb_path)
     hostcb.host_rosenbrock_grad.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_double, C.c_double]
     hostcb.host_rosenbrock_x0.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong]
+    host_threads = max(1, (os.cpu_count() or 1) // max(world, 1))
+    hostcb.host_set_threads(host_threads)
     steps = min(args.steps, args.e2e_steps)
     warmup = max(3, min(args.warmup, 12))
     xh = torch.empty(n_local, dtype=torch.float64).pin_memory()
@@ -384,7 +386,7 @@ def run_e2e(args, lib, abi, rank, world, local_rank, n, offset, n_local, comm, d
     # per iteration and rank: step call uploads x and grad, downloads x and grad (write-back on); pair call uploads grad
     return {"value": steps / dt, "unit": "steps/s", "h2d_bytes_per_step": 3 * vec * world, "d2h_bytes_per_step": 2 * vec * world,
             "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * dt / steps,
-            "path": "run_oLBFGS with host pointers (pinned), host C+OpenMP gradient callback, %d host threads" % (os.cpu_count() or 1)}
+            "path": "run_oLBFGS with host pointers (pinned), host C+OpenMP gradient callback, %d host threads per rank" % host_threads}
 
 
 def main():

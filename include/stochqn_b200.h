@@ -58,7 +58,8 @@ enum stochqn_b200_stat {
     STOCHQN_B200_STAT_K1_MS = 1, STOCHQN_B200_STAT_K1_COUNT = 2,     /* accumulated device ms / launches (profile mode) */
     STOCHQN_B200_STAT_K3_MS = 3, STOCHQN_B200_STAT_K3_COUNT = 4,
     STOCHQN_B200_STAT_K4_MS = 5, STOCHQN_B200_STAT_K4_COUNT = 6,
-    STOCHQN_B200_STAT_LAST_BOUND = 7                                  /* bound on ||direction|| of the last step */
+    STOCHQN_B200_STAT_LAST_BOUND = 7,                                 /* bound on ||direction|| of the last step */
+    STOCHQN_B200_STAT_EXACT_NORM_STEPS = 8                            /* steps that needed the exact-norm (two-pass) route */
 };
 int stochqn_b200_get_stat(void *ws, int what, double *out);
 

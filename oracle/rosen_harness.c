@@ -28,6 +28,14 @@
 #endif
 #include "stochqn.h"
 
+/* 0.95 + 1e-4*(h mod 1000) with the product rounded before the sum (no FMA contraction), so that the
+   start point is bit-identical in C, NumPy and CUDA */
+static double x0_value(unsigned int h)
+{
+    volatile double prod = 1e-4 * (double) (h % 1000u);
+    return 0.95 + prod;
+}
+
 static double now_s(void)
 {
     struct timespec ts;
@@ -72,7 +80,7 @@ int main(int argc, char **argv)
     #pragma omp parallel for schedule(static)
     for (long i = 0; i < n; i++) {
         uint32_t h = (uint32_t)((uint64_t) i * 2654435761ull);
-        x[i] = (real_t)(0.95 + 1e-4 * (double)(h % 1000u));
+        x[i] = (real_t) x0_value(h);
         g[i] = 0;
     }
 

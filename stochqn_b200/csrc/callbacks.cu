@@ -10,6 +10,7 @@
 
 #include "stochqn.h"
 #include "stochqn_b200.h"
+#include "vecio.cuh"
 
 // kernels launched by the callbacks; added to stochqn_b200_launch_count() by stochqn_b200.cu
 std::atomic<unsigned long long> stochqn_b200_cb_launches{0};
@@ -44,32 +45,53 @@ __global__ void rosen_x0_kernel(real_t* __restrict__ x, long long n, long long o
     const long long stride = (long long) gridDim.x * blockDim.x;
     for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint32_t h = (uint32_t) ((uint64_t) (i + offset) * 2654435761ull);
-        x[i] = (real_t) (0.95 + 1e-4 * (double) (h % 1000u));
+        x[i] = (real_t) __dadd_rn(0.95, __dmul_rn(1e-4, (double) (h % 1000u)));     // no FMA contraction: bit-identical to C / NumPy
     }
 }
 
 // interior: 200(x_i - x_{i-1}^2) - 400(x_{i+1} - x_i^2) x_i - 2(1 - x_i)      (c_rosen.c:35-40)
 // first   : -400 x_0 (x_1 - x_0^2) - 2(1 - x_0)                                (c_rosen.c:28)
 // last    : 200 (x_{n-1} - x_{n-2}^2)                                          (c_rosen.c:29)
+__device__ __forceinline__ double rosen_g(double xm, double xc, double xp, bool has_left, bool has_right)
+{
+    double out = 0.0;
+    if (has_left) out += 200.0 * (xc - xm * xm);
+    if (has_right) { out -= 400.0 * (xp - xc * xc) * xc; out -= 2.0 * (1.0 - xc); }
+    return out;
+}
+
+// One 16-byte chunk per thread and iteration: the chunk is loaded as a vector, the two neighbours as
+// scalars (they are the edge elements of the adjacent threads' chunks: L1 hits), the result stored as a vector.
+template <int VEC>
 __global__ void __launch_bounds__(kT)
 rosen_grad_kernel(const real_t* __restrict__ x, real_t* __restrict__ g, long long n, long long offset,
                   long long n_global, const real_t* __restrict__ halo)
 {
+    const long long nchunks = n / VEC;
     const long long stride = (long long) gridDim.x * blockDim.x;
-    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const long long gi = i + offset;
-        const double xc = (double) x[i];
-        double out = 0.0;
-        if (gi > 0) {
-            const double xm = (i > 0) ? (double) x[i - 1] : (double) halo[0];
-            out += 200.0 * (xc - xm * xm);
+    for (long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += stride) {
+        const long long i0 = c * VEC;
+        sqn::Pack<real_t, VEC> xv = sqn::ld_stream<real_t, VEC>(x + i0), gv;
+        double v[VEC + 2];
+        v[0] = (i0 > 0) ? (double) __ldg(x + i0 - 1) : (offset > 0 ? (double) halo[0] : 0.0);
+        #pragma unroll
+        for (int e = 0; e < VEC; ++e) v[e + 1] = (double) xv.get(e);
+        v[VEC + 1] = (i0 + VEC < n) ? (double) __ldg(x + i0 + VEC) : (offset + n < n_global ? (double) halo[1] : 0.0);
+        #pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const long long gi = i0 + e + offset;
+            gv.set(e, (real_t) rosen_g(v[e], v[e + 1], v[e + 2], gi > 0, gi < n_global - 1));
         }
-        if (gi < n_global - 1) {
-            const double xp = (i < n - 1) ? (double) x[i + 1] : (double) halo[1];
-            out -= 400.0 * (xp - xc * xc) * xc;
-            out -= 2.0 * (1.0 - xc);
+        sqn::st_vec<real_t, VEC>(g + i0, gv);
+    }
+    if (VEC > 1 && blockIdx.x == 0) {                  // scalar tail
+        const long long i = nchunks * VEC + threadIdx.x;
+        if (i < n) {
+            const long long gi = i + offset;
+            const double xm = (i > 0) ? (double) x[i - 1] : (offset > 0 ? (double) halo[0] : 0.0);
+            const double xp = (i < n - 1) ? (double) x[i + 1] : (offset + n < n_global ? (double) halo[1] : 0.0);
+            g[i] = (real_t) rosen_g(xm, (double) x[i], xp, gi > 0, gi < n_global - 1);
         }
-        g[i] = (real_t) out;
     }
 }
 
@@ -246,7 +268,11 @@ int stochqn_b200_rosenbrock_x0(real_t* x, long long n_local, long long offset, v
 int stochqn_b200_rosenbrock_grad(const real_t* x, real_t* grad, long long n_local, long long offset,
                                  long long n_global, const real_t* halo, void* stream)
 {
-    rosen_grad_kernel<<<grid_1d(n_local), kT, 0, (cudaStream_t) stream>>>(x, grad, n_local, offset, n_global, halo);
+    constexpr int V = 16 / sizeof(real_t);
+    if (((((uintptr_t) x) | ((uintptr_t) grad)) & 15u) == 0)
+        rosen_grad_kernel<V><<<grid_1d(n_local / V), kT, 0, (cudaStream_t) stream>>>(x, grad, n_local, offset, n_global, halo);
+    else
+        rosen_grad_kernel<1><<<grid_1d(n_local), kT, 0, (cudaStream_t) stream>>>(x, grad, n_local, offset, n_global, halo);
     return check_launch("rosenbrock_grad");
 }
 

@@ -22,51 +22,16 @@
 #include <stdint.h>
 #include <math.h>
 #include <type_traits>
+#include "vecio.cuh"
 
 namespace sqn {
 
 constexpr int kThreads = 256;          // threads per CTA for the streaming kernels
 constexpr int kWarps = kThreads / 32;
-constexpr int kMaxMem = 64;            // largest mem_size handled by the compact solve
+constexpr int kMaxMem = 32;            // largest mem_size handled by the compact solve
 
 // status word written by K2 (device + mapped host copy)
 enum : int { ST_ACCEPT = 0, ST_REJECT_NONFINITE = 1, ST_NEED_EXACT_NORM = 2 };
-
-// ---- 16-byte vector access -------------------------------------------------------------
-template <typename T, int VEC> struct Pack;
-template <> struct Pack<double, 2> { double2 v; __device__ __forceinline__ double get(int i) const { return i == 0 ? v.x : v.y; }
-                                     __device__ __forceinline__ void set(int i, double a) { if (i == 0) v.x = a; else v.y = a; } };
-template <> struct Pack<float, 4>  { float4 v;  __device__ __forceinline__ float get(int i) const { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
-                                     __device__ __forceinline__ void set(int i, float a) { if (i == 0) v.x = a; else if (i == 1) v.y = a; else if (i == 2) v.z = a; else v.w = a; } };
-template <typename T> struct Pack<T, 1> { T v; __device__ __forceinline__ T get(int) const { return v; }
-                                          __device__ __forceinline__ void set(int, T a) { v = a; } };
-
-template <typename T, int VEC>
-__device__ __forceinline__ Pack<T, VEC> ld_stream(const T* p)
-{
-    Pack<T, VEC> r;
-    if constexpr (VEC == 1) r.v = __ldg(p);
-    else if constexpr (sizeof(T) == 8) r.v = __ldg(reinterpret_cast<const double2*>(p));
-    else r.v = __ldg(reinterpret_cast<const float4*>(p));
-    return r;
-}
-// plain (coherent) load for buffers that the same kernel also writes
-template <typename T, int VEC>
-__device__ __forceinline__ Pack<T, VEC> ld_rw(const T* p)
-{
-    Pack<T, VEC> r;
-    if constexpr (VEC == 1) r.v = *p;
-    else if constexpr (sizeof(T) == 8) r.v = *reinterpret_cast<const double2*>(p);
-    else r.v = *reinterpret_cast<const float4*>(p);
-    return r;
-}
-template <typename T, int VEC>
-__device__ __forceinline__ void st_vec(T* p, const Pack<T, VEC>& r)
-{
-    if constexpr (VEC == 1) *p = r.v;
-    else if constexpr (sizeof(T) == 8) *reinterpret_cast<double2*>(p) = r.v;
-    else *reinterpret_cast<float4*>(p) = r.v;
-}
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -256,59 +221,68 @@ struct SolveArgs {
 
 __device__ __forceinline__ bool finite_d(double v) { return isfinite(v); }
 
+// Sum the CTA partial records into `sums` in a fixed order: one warp per entry, lanes stride over CTAs.
+__device__ __forceinline__ void reduce_partials(const double* __restrict__ partials, int nblocks, int P, double* __restrict__ sums)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int p = warp; p < P; p += kWarps) {
+        double v = 0;
+        for (int b = lane; b < nblocks; b += 32) v += partials[(size_t) b * P + p];
+        v = warp_sum(v);
+        if (lane == 0) sums[p] = v;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 k2_solve(SolveArgs A, const double* __restrict__ partials, double* __restrict__ sums,
          double* __restrict__ SY, double* __restrict__ YY, double* __restrict__ SS,
          double* __restrict__ coef, int* __restrict__ status_dev, volatile int* status_host,
          volatile double* info_host)
 {
-    const int m = A.msize;
+    const int m = A.msize, used = A.used;
     const int P = 4 * m + 2;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (A.nblocks > 0) {
-        // fixed-order sum over CTAs: lanes stride over records, then a shuffle tree
-        for (int p = warp; p < P; p += kWarps) {
-            double v = 0;
-            for (int b = lane; b < A.nblocks; b += 32) v += partials[(size_t) b * P + p];
-            v = warp_sum(v);
-            if (lane == 0) sums[p] = v;
-        }
-        __syncthreads();
-    }
-    if (!A.do_solve || threadIdx.x != 0) return;
+    if (A.nblocks > 0) { reduce_partials(partials, A.nblocks, P, sums); __syncthreads(); }
+    if (!A.do_solve) return;
 
-    __shared__ double Rm[kMaxMem][kMaxMem + 1];
-    __shared__ double u[kMaxMem], w[kMaxMem], av[kMaxMem];
-    const int used = A.used;
-    const double gg = sums[4 * m];
-    if (A.pend >= 0) {                       // fold the newest pair's Gram column in
+    auto ph = [&](int i) { int s = A.oldest + i; return s >= m ? s - m : s; };      // logical (oldest..newest) -> physical slot
+    if (A.pend >= 0) {                       // fold the newest pair's Gram column in (one thread per slot)
         const int c = A.pend;
-        for (int j = 0; j < used; ++j) {
+        for (int j = threadIdx.x; j < used; j += kThreads) {
             SY[j * m + c] = sums[2 * m + j];
             const double yy = sums[3 * m + j];
             YY[j * m + c] = yy;
             YY[c * m + j] = yy;
         }
-        SS[c] = sums[4 * m + 1];
+        if (threadIdx.x == 0) SS[c] = sums[4 * m + 1];
+        __syncthreads();
     }
+    // stage everything the serial solve touches in shared memory, in logical order
+    __shared__ double Rm[kMaxMem][kMaxMem + 1], Yl[kMaxMem][kMaxMem + 1];
+    __shared__ double pv[kMaxMem], qv[kMaxMem], ssv[kMaxMem], u[kMaxMem], w[kMaxMem], av[kMaxMem];
+    for (int t = threadIdx.x; t < used * used; t += kThreads) {
+        const int i = t / used, j = t % used;
+        Rm[i][j] = SY[ph(i) * m + ph(j)];
+        Yl[i][j] = YY[ph(i) * m + ph(j)];
+    }
+    for (int i = threadIdx.x; i < used; i += kThreads) { pv[i] = sums[ph(i)]; qv[i] = sums[m + ph(i)]; ssv[i] = SS[ph(i)]; }
+    for (int j = threadIdx.x; j < 2 * m; j += kThreads) coef[j] = 0.0;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+
+    const double gg = sums[4 * m];
     double gamma = 1.0, U = sqrt(gg);
     bool ok = finite_d(gg);
-    for (int j = 0; j < 2 * m; ++j) coef[j] = 0.0;
     if (used > 0) {
-        auto ph = [&](int i) { int s = A.oldest + i; return s >= m ? s - m : s; };
-        if (A.h0 > 0) gamma = A.h0;
-        else { const int l = ph(used - 1); gamma = SY[l * m + l] / YY[l * m + l]; }
-        for (int i = 0; i < used; ++i)
-            for (int j = i; j < used; ++j) Rm[i][j] = SY[ph(i) * m + ph(j)];
+        gamma = (A.h0 > 0) ? A.h0 : Rm[used - 1][used - 1] / Yl[used - 1][used - 1];
         for (int i = used - 1; i >= 0; --i) {          // u = R^-1 p
-            double t = sums[ph(i)];
+            double t = pv[i];
             for (int j = i + 1; j < used; ++j) t -= Rm[i][j] * u[j];
             u[i] = t / Rm[i][i];
         }
         for (int i = 0; i < used; ++i) {               // w = (D + gamma*YY) u - gamma*q0
             double t = 0;
-            for (int j = 0; j < used; ++j) t += YY[ph(i) * m + ph(j)] * u[j];
-            w[i] = Rm[i][i] * u[i] + gamma * t - gamma * sums[m + ph(i)];
+            for (int j = 0; j < used; ++j) t += Yl[i][j] * u[j];
+            w[i] = Rm[i][i] * u[i] + gamma * t - gamma * qv[i];
         }
         for (int i = 0; i < used; ++i) {               // a = R^-T w
             double t = w[i];
@@ -321,7 +295,7 @@ k2_solve(SolveArgs A, const double* __restrict__ partials, double* __restrict__ 
             const double a = av[i], gb = -gamma * u[i];
             coef[s] = a;
             coef[m + s] = gb;
-            U += fabs(a) * sqrt(SS[s]) + fabs(gb) * sqrt(YY[s * m + s]);
+            U += fabs(a) * sqrt(ssv[i]) + fabs(gb) * sqrt(Yl[i][i]);
             ok = ok && finite_d(a) && finite_d(gb);
         }
         ok = ok && finite_d(gamma);
@@ -333,6 +307,7 @@ k2_solve(SolveArgs A, const double* __restrict__ partials, double* __restrict__ 
     int st = ST_ACCEPT;
     if (A.check_nan) {
         if (!ok) st = ST_REJECT_NONFINITE;
+        else if (used == 0) { if (U > A.limit) st = ST_REJECT_NONFINITE; }      // d = g: U is the exact norm (stochqn.c:829)
         else if (!(U <= 0.99 * A.limit)) st = ST_NEED_EXACT_NORM;
     }
     *status_dev = st;
@@ -826,48 +801,47 @@ ka_solve(SolveArgs A, const double* __restrict__ partials, double* __restrict__ 
          double* __restrict__ coef, int* __restrict__ status_dev, volatile int* status_host,
          volatile double* info_host)
 {
-    const int m = A.msize;
+    const int m = A.msize, used = A.used;
     const int P = 3 * m + 4 + m * m;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (A.nblocks > 0) {
-        for (int p = warp; p < P; p += kWarps) {
-            double v = 0;
-            for (int b = lane; b < A.nblocks; b += 32) v += partials[(size_t) b * P + p];
-            v = warp_sum(v);
-            if (lane == 0) sums[p] = v;
-        }
-        __syncthreads();
-    }
-    if (!A.do_solve || threadIdx.x != 0) return;
-    __shared__ double Rm[kMaxMem][kMaxMem + 1];
-    __shared__ double u[kMaxMem], w[kMaxMem], av[kMaxMem];
-    const int used = A.used;
-    const double* W = sums + 3 * m + 4;
+    if (A.nblocks > 0) { reduce_partials(partials, A.nblocks, P, sums); __syncthreads(); }
+    if (!A.do_solve) return;
+    auto ph = [&](int i) { int s = A.oldest + i; return s >= m ? s - m : s; };
     if (A.pend >= 0) {
         const int c = A.pend;
-        for (int j = 0; j < used; ++j) SY[j * m + c] = sums[2 * m + j];
-        SS[c] = sums[3 * m + 2];
-        YY[c * m + c] = sums[3 * m + 3];
+        for (int j = threadIdx.x; j < used; j += kThreads) SY[j * m + c] = sums[2 * m + j];
+        if (threadIdx.x == 0) { SS[c] = sums[3 * m + 2]; YY[c * m + c] = sums[3 * m + 3]; }
+        __syncthreads();
     }
+    __shared__ double Rm[kMaxMem][kMaxMem + 1], Wl[kMaxMem][kMaxMem + 1];
+    __shared__ double pv[kMaxMem], qv[kMaxMem], ssv[kMaxMem], yyv[kMaxMem], u[kMaxMem], w[kMaxMem], av[kMaxMem];
+    const double* W = sums + 3 * m + 4;          // upper triangle (physical indices) is filled by KA2
+    for (int t = threadIdx.x; t < used * used; t += kThreads) {
+        const int i = t / used, j = t % used;
+        const int a = ph(i), b = ph(j);
+        Rm[i][j] = SY[a * m + b];
+        Wl[i][j] = a <= b ? W[a * m + b] : W[b * m + a];
+    }
+    for (int i = threadIdx.x; i < used; i += kThreads) {
+        pv[i] = sums[ph(i)]; qv[i] = sums[m + ph(i)]; ssv[i] = SS[ph(i)]; yyv[i] = YY[ph(i) * m + ph(i)];
+    }
+    for (int j = threadIdx.x; j < 2 * m; j += kThreads) coef[j] = 0.0;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+
     const double n0 = sums[3 * m];            // sum (h g)^2 with pairs, sum h^2 without
     const double hh = sums[3 * m + 1];
-    for (int j = 0; j < 2 * m; ++j) coef[j] = 0.0;
     double U = sqrt(n0);
     bool ok = finite_d(n0);
     if (used > 0) {
-        auto ph = [&](int i) { int s = A.oldest + i; return s >= m ? s - m : s; };
-        auto Wsym = [&](int a, int b) { return a <= b ? W[a * m + b] : W[b * m + a]; };
-        for (int i = 0; i < used; ++i)
-            for (int j = i; j < used; ++j) Rm[i][j] = SY[ph(i) * m + ph(j)];
         for (int i = used - 1; i >= 0; --i) {
-            double t = sums[ph(i)];
+            double t = pv[i];
             for (int j = i + 1; j < used; ++j) t -= Rm[i][j] * u[j];
             u[i] = t / Rm[i][i];
         }
         for (int i = 0; i < used; ++i) {
             double t = 0;
-            for (int j = 0; j < used; ++j) t += Wsym(ph(i), ph(j)) * u[j];
-            w[i] = Rm[i][i] * u[i] + t - sums[m + ph(i)];
+            for (int j = 0; j < used; ++j) t += Wl[i][j] * u[j];
+            w[i] = Rm[i][i] * u[i] + t - qv[i];
         }
         for (int i = 0; i < used; ++i) {
             double t = w[i];
@@ -880,7 +854,7 @@ ka_solve(SolveArgs A, const double* __restrict__ partials, double* __restrict__ 
             const double a = av[i], b = -u[i];
             coef[s] = a;
             coef[m + s] = b;
-            U += fabs(a) * sqrt(SS[s]) + hnorm * fabs(b) * sqrt(YY[s * m + s]);
+            U += fabs(a) * sqrt(ssv[i]) + hnorm * fabs(b) * sqrt(yyv[i]);
             ok = ok && finite_d(a) && finite_d(b);
         }
         ok = ok && finite_d(hh);

@@ -137,6 +137,7 @@ struct Ctx {
     double prof_ms[3] = {0, 0, 0};
     double prof_n[3] = {0, 0, 0};
     double last_bound = 0;
+    double exact_norm_steps = 0;        // steps that took the two-pass (exact ||d||) route
 };
 
 void prof_begin(Ctx* c, int k) { if (c->profile) cudaEventRecord(c->ev[2 * k], c->stream); }
@@ -301,20 +302,20 @@ int launch_k3_m(Ctx* c, int rpg, const real_t* g, real_t* gout, real_t* S, const
 #define K3_RPG(R) case R: return launch_k3_t<R, MODE, VEC>(c, g, gout, S, Y, used, new_slot, x, x_sum, step, force)
     switch (rpg) {
         K3_RPG(1); K3_RPG(2); K3_RPG(3); K3_RPG(4); K3_RPG(5); K3_RPG(6); K3_RPG(7); K3_RPG(8);
-        K3_RPG(12); K3_RPG(16); K3_RPG(24);
-        default: return launch_k3_t<32, MODE, VEC>(c, g, gout, S, Y, used, new_slot, x, x_sum, step, force);
+        K3_RPG(12);
+        default: return launch_k3_t<16, MODE, VEC>(c, g, gout, S, Y, used, new_slot, x, x_sum, step, force);
     }
 #undef K3_RPG
 }
 
-int bucket3(int used) { return used <= 16 ? bucket(used) : used <= 32 ? 32 : 64; }    // MMAX buckets of the adaQN combine
+int bucket3(int used) { return used <= 16 ? bucket(used) : 32; }    // MMAX buckets of the adaQN combine
 
 int rpg_for_k3(int used)
 {
     int rpg = (2 * used + kGroups - 1) / kGroups;
     if (rpg < 1) rpg = 1;
     if (rpg <= 8) return rpg;
-    return rpg <= 12 ? 12 : rpg <= 16 ? 16 : rpg <= 24 ? 24 : 32;
+    return rpg <= 12 ? 12 : 16;
 }
 
 int launch_k3(Ctx* c, int mode, const real_t* g, real_t* gout, real_t* S, const real_t* Y, int used, int new_slot,
@@ -584,6 +585,7 @@ int take_step_qn(Ctx* c, bfgs_mem* m, int mode, real_t step, real_t* x, real_t* 
     int status = c->hb->status;
     c->last_bound = c->hb->info[0];
     if (status == ST_NEED_EXACT_NORM) {
+        c->exact_norm_steps += 1;
         // rare: the cheap bound could not certify ||d|| <= 1e3*n.  Materialise d in `grad`, measure it
         // exactly, and only then touch x - the reference's order (stochqn.c:825-838).
         int nb2 = launch_k3(c, MODE_DIRONLY, g, g, m->s_mem, m->y_mem, used, st, x, x_sum, step, 1);

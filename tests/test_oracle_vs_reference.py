@@ -1,0 +1,70 @@
+"""CPU: the NumPy restatement against the reference C library itself (oracle/_ref, built from the
+unmodified reference sources).  Skipped where oracle/_ref has not been built."""
+import numpy as np
+import pytest
+
+from cases import CASES, CASE_IDS
+from oracle import ref_lib as R
+from oracle import stochqn_np as O
+from oracle.driver import HostStepper, discrete, run_trace
+from oracle.problems import Logistic, Quadratic
+
+pytestmark = pytest.mark.skipif(not (R.have_ref(np.float64) and R.have_ref(np.float32)),
+                                reason="oracle/_ref not built (needs /root/reference)")
+
+ORACLE = {"oLBFGS": O.OracleOLBFGS, "SQN": O.OracleSQN, "adaQN": O.OracleAdaQN}
+REF = {"oLBFGS": R.RefOLBFGS, "SQN": R.RefSQN, "adaQN": R.RefAdaQN}
+
+
+def _pair(kind, kw, prob_f, calls, step, dtype, hooks=None):
+    p1, p2 = prob_f(), prob_f()
+    so = HostStepper(ORACLE[kind](len(p1.x0()), dtype=dtype, **kw), p1.x0())
+    sr = HostStepper(REF[kind](len(p2.x0()), dtype=dtype, **kw), p2.x0())
+    return run_trace(so, p1, calls, step, hooks=hooks, keep_x=True), run_trace(sr, p2, calls, step, hooks=hooks, keep_x=True)
+
+
+def _err(ta, tb):
+    return max(float(np.max(np.abs(a["x"] - b["x"])) / max(np.max(np.abs(b["x"])), 1e-300)) for a, b in zip(ta, tb))
+
+
+@pytest.mark.parametrize("case", CASES, ids=CASE_IDS)
+def test_fp64(case):
+    name, kind, kw, prob_f, calls, step = case
+    to, tr = _pair(kind, kw, prob_f, calls, step, np.float64)
+    assert discrete(to) == discrete(tr)
+    assert _err(to, tr) <= 1e-6        # 1e-13 on the well-conditioned cases; chaotic adaQN cases amplify dot rounding
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c[0] not in ("sqn_gd_logistic_yreg", "adaqn_fisher_adagrad_logistic", "adaqn_fisher_quad")],
+                         ids=lambda c: c[0])
+def test_fp32(case):
+    name, kind, kw, prob_f, calls, step = case
+    to, tr = _pair(kind, kw, prob_f, calls, step, np.float32)
+    assert discrete(to) == discrete(tr)
+    assert _err(to, tr) <= 1e-4
+
+
+def test_nan_gradient_is_rejected_and_flushes():
+    def poison(stepper, task, payload):
+        payload["grad"] = payload["grad"].copy()
+        payload["grad"][3] = np.nan
+
+    kw = dict(mem_size=3, hess_init=0.0, y_reg=0.0, min_curvature=1e-4, check_nan=1)
+    to, tr = _pair("oLBFGS", kw, lambda: Quadratic(6), 12, 1e-2, np.float64, hooks={7: poison})
+    assert discrete(to) == discrete(tr)
+    assert tr[7]["info"] == 203 and tr[7]["ret"] == 0 and tr[7]["mem_used"] == 0
+    assert _err(to, tr) <= 1e-12
+
+
+def test_func_increased_reverts_x():
+    def blow(stepper, task, payload):
+        if "f" in payload:
+            payload["f"] = 1e30
+
+    kw = dict(mem_size=5, fisher_size=20, bfgs_upd_freq=5, max_incr=1.01, min_curvature=1e-4, scal_reg=1e-4,
+              rmsprop_weight=0.9, use_grad_diff=0, y_reg=0.0, check_nan=1)
+    hooks = {c: blow for c in range(20, 40)}
+    to, tr = _pair("adaQN", kw, Logistic, 60, 1e-2, np.float64, hooks=hooks)
+    assert discrete(to) == discrete(tr)
+    assert any(r["info"] == 201 for r in tr)
+    assert _err(to, tr) <= 1e-10

@@ -4,11 +4,22 @@
  * Shard-aware: x[0..n_local) starts at global index `offset` of a vector of length n_global;
  * halo_left / halo_right are x[offset-1] and x[offset+n_local] (ignored at the global ends). */
 #include <stddef.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #ifdef USE_FLOAT
 typedef float real_t;
 #else
 typedef double real_t;
 #endif
+
+/* 0.95 + 1e-4*(h mod 1000) with the product rounded before the sum (no FMA contraction), so that the
+   start point is bit-identical in C, NumPy and CUDA */
+static double x0_value(unsigned int h)
+{
+    volatile double prod = 1e-4 * (double) (h % 1000u);
+    return 0.95 + prod;
+}
 
 void host_rosenbrock_grad(const real_t *x, real_t *g, long long n_local, long long offset, long long n_global,
                           double halo_left, double halo_right)
@@ -36,6 +47,16 @@ void host_rosenbrock_x0(real_t *x, long long n_local, long long offset)
     #pragma omp parallel for schedule(static)
     for (long long i = 0; i < n_local; i++) {
         unsigned int h = (unsigned int) ((unsigned long long) (i + offset) * 2654435761ull);
-        x[i] = (real_t) (0.95 + 1e-4 * (double) (h % 1000u));
+        x[i] = (real_t) x0_value(h);
     }
+}
+
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the bench gives each rank its share of the host cores */
+void host_set_threads(int nthreads)
+{
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+    (void) nthreads;
+#endif
 }

@@ -59,6 +59,15 @@ def run(n, m=10, iters=30, warm=12, dtype=np.float64, writeback=1):
                k1_gbs=(2 * used + 2) * vec / k1 / 1e6, k3_gbs=(2 * used + 4) * vec / k3 / 1e6, k4_gbs=4 * vec / k4 / 1e6,
                e2e_gbs=(4 * used + 14) * vec / ms / 1e6, infos=infos, mem_used=int(used), niter=int(ws.contents.niter),
                U=st["U"], xnorm=float(torch.linalg.vector_norm(x).item()))
+    # stand-alone timing of the gradient callback and of an empty-ish call sequence
+    e0.record()
+    for _ in range(20):
+        lib.stochqn_b200_rosenbrock_grad(x.data_ptr(), g.data_ptr(), n, 0, n, None, None)
+    e1.record()
+    torch.cuda.synchronize()
+    out["grad_ms"] = e0.elapsed_time(e1) / 20
+    out["grad_gbs"] = 2 * vec / out["grad_ms"] / 1e6
+    out["overhead_ms"] = ms - (k1 + k3 + k4 + 2 * out["grad_ms"])
     lib.dealloc_oLBFGS(ws)
     del x, g
     torch.cuda.empty_cache()

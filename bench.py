@@ -286,7 +286,7 @@ def main_b200(args):
                          "frac_of_aggregate_peak": (4 * used + 14) * vec_bytes * world / (ms / args.steps) / 1e6 / (peak * world)}}
 
     # ---- end-to-end through the drop-in C ABI with HOST buffers --------------------------------------
-    e2e = run_e2e(args, lib, abi, rank, world, local_rank, n, offset, n_local, comm, dist, torch, np)
+    e2e = None if args.no_e2e else run_e2e(args, lib, abi, rank, world, local_rank, n, offset, n_local, comm, dist, torch, np)
 
     # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------------------------------
     cpu = None
@@ -398,6 +398,7 @@ def main():
     ap.add_argument("--n", type=int, default=N_DEFAULT)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-pointer end-to-end leg (profiling runs)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

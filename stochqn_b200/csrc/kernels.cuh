@@ -84,8 +84,10 @@ __device__ __forceinline__ void block_reduce(int count, Get get, Emit emit)
 constexpr int kGroups = 4;
 constexpr int kLanes = kThreads / kGroups;     // 64: two warps per row-group
 
+constexpr int kUnroll = 2;      // chunks per thread in flight (tools/kbench.cu: 2 x 8 loads x 512 threads/SM saturates HBM)
+
 template <typename T, int RPG, bool PENDING, int VEC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 k1_dots(const T* __restrict__ g, const T* __restrict__ S, const T* __restrict__ Y, size_t ld,
         int msize, int used, int j0, const T* __restrict__ sc_row, const T* __restrict__ yc_row, long long n,
         T* __restrict__ grad_prev, double* __restrict__ partials)
@@ -112,42 +114,62 @@ k1_dots(const T* __restrict__ g, const T* __restrict__ S, const T* __restrict__ 
     #pragma unroll
     for (int r = 0; r < RPG; ++r) { a_g[r] = 0; a_c[r] = 0; }
 
-    auto one = [&](size_t off, auto vtag) {
+    // U chunks per thread: all loads of the U chunks are issued before the first use
+    auto many = [&](const long long (&c)[kUnroll], auto vtag) {
         constexpr int V = decltype(vtag)::value;
-        Pack<T, V> gv = ld_stream<T, V>(g + off);
-        Pack<T, V> yc, sc, rv[RPG];
-        if constexpr (PENDING) {
-            yc = ld_stream<T, V>(yc_row + off);
-            if (lead) sc = ld_stream<T, V>(sc_row + off);
-        }
+        Pack<T, V> gv[kUnroll], yc[kUnroll], sc[kUnroll], rv[kUnroll][RPG];
         #pragma unroll
-        for (int r = 0; r < RPG; ++r) rv[r] = ld_stream<T, V>(rows[r] + off);
-        if (grad_prev) st_vec<T, V>(grad_prev + off, gv);
-        if (lead) {
-            #pragma unroll
-            for (int e = 0; e < V; ++e) {
-                double ge = (double) gv.get(e);
-                a_gg = fma(ge, ge, a_gg);
-                if constexpr (PENDING) { double se = (double) sc.get(e); a_ss = fma(se, se, a_ss); }
+        for (int u = 0; u < kUnroll; ++u) {
+            if (c[u] >= 0) {
+                const size_t off = (size_t) c[u] * V;
+                gv[u] = ld_stream<T, V>(g + off);
+                if constexpr (PENDING) {
+                    yc[u] = ld_stream<T, V>(yc_row + off);
+                    if (lead) sc[u] = ld_stream<T, V>(sc_row + off);
+                }
+                #pragma unroll
+                for (int r = 0; r < RPG; ++r) rv[u][r] = ld_row<T, V>(rows[r] + off);
             }
         }
         #pragma unroll
-        for (int r = 0; r < RPG; ++r) {
-            #pragma unroll
-            for (int e = 0; e < V; ++e) {
-                double re = (double) rv[r].get(e);
-                a_g[r] = fma(re, (double) gv.get(e), a_g[r]);
-                if constexpr (PENDING) a_c[r] = fma(re, (double) yc.get(e), a_c[r]);
+        for (int u = 0; u < kUnroll; ++u) {
+            if (c[u] >= 0) {
+                const size_t off = (size_t) c[u] * V;
+                if (grad_prev) st_vec<T, V>(grad_prev + off, gv[u]);
+                if (lead) {
+                    #pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        double ge = (double) gv[u].get(e);
+                        a_gg = fma(ge, ge, a_gg);
+                        if constexpr (PENDING) { double se = (double) sc[u].get(e); a_ss = fma(se, se, a_ss); }
+                    }
+                }
+                #pragma unroll
+                for (int r = 0; r < RPG; ++r) {
+                    #pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        double re = (double) rv[u][r].get(e);
+                        a_g[r] = fma(re, (double) gv[u].get(e), a_g[r]);
+                        if constexpr (PENDING) a_c[r] = fma(re, (double) yc[u].get(e), a_c[r]);
+                    }
+                }
             }
         }
     };
     const long long nchunks = n / VEC;
     const long long stride = (long long) gridDim.x * kLanes;
-    for (long long c = (long long) blockIdx.x * kLanes + lane; c < nchunks; c += stride)
-        one((size_t) c * VEC, std::integral_constant<int, VEC>{});
+    for (long long c0 = (long long) blockIdx.x * kLanes + lane; c0 < nchunks; c0 += stride * kUnroll) {
+        long long c[kUnroll];
+        #pragma unroll
+        for (int u = 0; u < kUnroll; ++u) { c[u] = c0 + u * stride; if (c[u] >= nchunks) c[u] = -1; }
+        many(c, std::integral_constant<int, VEC>{});
+    }
     if (VEC > 1 && blockIdx.x == 0) {               // scalar tail: n not a multiple of VEC
         const long long i = nchunks * VEC + lane;
-        if (i < n) one((size_t) i, std::integral_constant<int, 1>{});
+        long long c[kUnroll];
+        #pragma unroll
+        for (int u = 0; u < kUnroll; ++u) c[u] = -1;
+        if (i < n) { c[0] = i; many(c, std::integral_constant<int, 1>{}); }
     }
 
     // ---- CTA reduction: two warps per group, fixed order ----

@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from stochqn_b200 import _lib
 
 
-def run(n, m=10, iters=30, warm=12, dtype=np.float64, writeback=1):
+def run(n, m=10, iters=int(os.environ.get('PROBE_ITERS', 30)), warm=12, dtype=np.float64, writeback=1):
     abi = _lib.load(dtype)
     lib = abi.lib
     tdt = torch.float64 if dtype == np.float64 else torch.float32
@@ -77,6 +77,6 @@ def run(n, m=10, iters=30, warm=12, dtype=np.float64, writeback=1):
 if __name__ == "__main__":
     sizes = [int(a) for a in sys.argv[1:]] or [2 ** 20, 2 ** 24, 2 ** 27]
     for n in sizes:
-        for dt in (np.float64, np.float32):
+        for dt in [d for d, tag in ((np.float64, "f64"), (np.float32, "f32")) if tag in os.environ.get("PROBE_DTYPES", "f64,f32")]:
             r = run(n, dtype=dt)
             print(json.dumps(r), flush=True)

@@ -43,10 +43,11 @@ __device__ __forceinline__ double warp_sum(double v)
 // Deterministic CTA reduction of `count` per-thread accumulators: lane 0 of every warp
 // parks its warp sum in shared memory, then thread p adds the kWarps values in fixed order.
 // `emit(p, value)` is called once per accumulator by the thread that owns it.
-template <int COUNT_MAX, typename Get, typename Emit>
+template <int COUNT_MAX, int THREADS = kThreads, typename Get, typename Emit>
 __device__ __forceinline__ void block_reduce(int count, Get get, Emit emit)
 {
-    __shared__ double red[kWarps][COUNT_MAX];
+    constexpr int NW = THREADS / 32;
+    __shared__ double red[NW][COUNT_MAX];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     #pragma unroll
     for (int p = 0; p < COUNT_MAX; ++p) {
@@ -56,10 +57,10 @@ __device__ __forceinline__ void block_reduce(int count, Get get, Emit emit)
         }
     }
     __syncthreads();
-    for (int p = threadIdx.x; p < count; p += kThreads) {
+    for (int p = threadIdx.x; p < count; p += THREADS) {
         double v = 0;
         #pragma unroll
-        for (int w = 0; w < kWarps; ++w) v += red[w][p];
+        for (int w = 0; w < NW; ++w) v += red[w][p];
         emit(p, v);
     }
 }
@@ -349,55 +350,60 @@ k2_solve(SolveArgs A, const double* __restrict__ partials, double* __restrict__ 
 // Does nothing unless *status_dev == ST_ACCEPT (or `force`), so a rejected direction never
 // touches x - the reference's check-before-update order (stochqn.c:825-838).
 //
-// Same work split as K1: kGroups row-groups x kLanes chunk-lanes.  Each group forms the partial
-// combination of its RPG virtual rows (S rows with a_j, Y rows with gamma*b_j; group 0 adds
-// gamma*g), the four partials meet in shared memory (double-buffered, one barrier per
-// iteration), every group adds them in the same order and then does ONE of the output jobs:
-// group 0 updates x (and x_sum), group 1 stores the new s, group 2 stores grad.
+// Work split (picked with tools/kbench_k3.cu): 128-thread CTAs = 2 row-groups x 64 chunk-lanes, 4 CTAs per SM.
+// Group 0 forms gamma*g + sum_j a_j s_j, group 1 forms sum_j (gamma b_j) y_j for the same 64 chunks; every load
+// of an iteration (up to m rows + g + x [+ x_sum] per thread) is issued before the first use.  The two partials
+// meet in shared memory (double-buffered, one barrier per iteration) and each group then performs its output
+// job: group 0 updates x (and x_sum), group 1 stores the new s and grad.
 // The barrier also orders the read of the slot that is about to be overwritten (it is still a
 // valid, oldest pair) and of `grad` before the stores that replace them.
 // =========================================================================================
 enum : int { MODE_OLBFGS = 0, MODE_AVG = 1, MODE_DIRONLY = 2 };
 
+constexpr int k3Groups = 2;                    // group 0 streams the S rows (+ g, x), group 1 the Y rows
+constexpr int k3Lanes = 64;
+constexpr int k3Threads = k3Groups * k3Lanes;  // 128-thread CTAs, 4 resident per SM (tools/kbench_k3.cu)
+constexpr int k3_min_blocks(int rpg) { return rpg <= 10 ? 4 : rpg <= 16 ? 3 : 2; }
+
 template <typename T, int RPG, int MODE, int VEC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(k3Threads, k3_min_blocks(RPG))
 k3_combine(const T* g_in, T* grad_out, const T* S_ro, const T* __restrict__ Y,
            T* S_rw, size_t ld, int msize, int used, int new_slot, long long n,
            T* __restrict__ x, T* __restrict__ x_sum, T step, const double* __restrict__ coef,
            const int* __restrict__ status_dev, int force, double* __restrict__ partials)
 {
     if (!force && *status_dev != ST_ACCEPT) return;
-    const int group = threadIdx.x / kLanes, lane = threadIdx.x % kLanes;
-    const int nv = 2 * used;
+    const int group = threadIdx.x / k3Lanes, lane = threadIdx.x % k3Lanes;
     const T* rows[RPG];
     T cf[RPG];
     #pragma unroll
     for (int r = 0; r < RPG; ++r) {
-        int v = group * RPG + r;
-        const bool live = v < nv;
-        if (!live) v = nv > 0 ? nv - 1 : 0;
-        const bool is_s = (v < used) || nv == 0;
-        const int j = is_s ? v : v - used;
-        rows[r] = is_s ? S_ro + (size_t) j * ld : Y + (size_t) j * ld;
-        cf[r] = live ? (T) coef[is_s ? j : msize + j] : (T) 0;
+        const bool live = r < used;
+        const int j = live ? r : (used > 0 ? used - 1 : 0);
+        rows[r] = (group == 0 ? S_ro : Y) + (size_t) j * ld;
+        cf[r] = live ? (T) coef[group == 0 ? j : msize + j] : (T) 0;
     }
-    const T gamma = (group == 0) ? (T) coef[2 * msize] : (T) 0;
+    const T gamma = (T) coef[2 * msize];
     const T nstep = -step;
     double a_dd = 0, a_bad = 0;
-    __shared__ __align__(16) T xchg[2][kGroups][kLanes * (VEC > 1 ? VEC : 1)];
+    __shared__ __align__(16) T xchg[2][k3Groups][k3Lanes * (VEC > 1 ? VEC : 1)];
     int buf = 0;
 
     auto one = [&](size_t off, bool valid, auto vtag) {
         constexpr int V = decltype(vtag)::value;
-        Pack<T, V> part;
+        Pack<T, V> part, xv, xs;
         #pragma unroll
         for (int e = 0; e < V; ++e) part.set(e, (T) 0);
         if (valid) {
             Pack<T, V> rv[RPG], gv;
+            // every load of the iteration is issued before the first use; the rows are read through the coherent
+            // path because the slot that receives the new s is one of them
             #pragma unroll
             for (int r = 0; r < RPG; ++r) rv[r] = ld_rw<T, V>(rows[r] + off);
             if (group == 0) {
                 gv = ld_rw<T, V>(g_in + off);
+                if constexpr (MODE != MODE_DIRONLY) xv = ld_rw<T, V>(x + off);
+                if constexpr (MODE == MODE_AVG) xs = ld_rw<T, V>(x_sum + off);
                 #pragma unroll
                 for (int e = 0; e < V; ++e) part.set(e, gamma * gv.get(e));
             }
@@ -414,12 +420,7 @@ k3_combine(const T* g_in, T* grad_out, const T* S_ro, const T* __restrict__ Y,
         if (valid) {
             Pack<T, V> d;
             #pragma unroll
-            for (int e = 0; e < V; ++e) {
-                T t = xchg[buf][0][lane * V + e];
-                #pragma unroll
-                for (int q = 1; q < kGroups; ++q) t += xchg[buf][q][lane * V + e];
-                d.set(e, t);
-            }
+            for (int e = 0; e < V; ++e) d.set(e, xchg[buf][0][lane * V + e] + xchg[buf][1][lane * V + e]);
             if constexpr (MODE == MODE_DIRONLY) {
                 if (group == 0) {
                     #pragma unroll
@@ -428,34 +429,24 @@ k3_combine(const T* g_in, T* grad_out, const T* S_ro, const T* __restrict__ Y,
                         a_dd = fma(de, de, a_dd);
                         if (!isfinite(de)) a_bad += 1.0;
                     }
-                } else if (group == 2) st_vec<T, V>(grad_out + off, d);
+                } else st_vec<T, V>(grad_out + off, d);
             } else {
                 if (group == 0) {
-                    Pack<T, V> xv = ld_rw<T, V>(x + off);
                     #pragma unroll
                     for (int e = 0; e < V; ++e) xv.set(e, fma(nstep, d.get(e), xv.get(e)));
                     st_vec<T, V>(x + off, xv);
                     if constexpr (MODE == MODE_AVG) {
-                        Pack<T, V> xs = ld_rw<T, V>(x_sum + off);
                         #pragma unroll
                         for (int e = 0; e < V; ++e) xs.set(e, xs.get(e) + xv.get(e));
                         st_vec<T, V>(x_sum + off, xs);
                     }
-                } else if (group == 1) {
+                } else {
                     if constexpr (MODE == MODE_OLBFGS) {
-                        Pack<T, V> sn;
                         #pragma unroll
-                        for (int e = 0; e < V; ++e) sn.set(e, nstep * d.get(e));
-                        st_vec<T, V>(S_rw + (size_t) new_slot * ld + off, sn);
+                        for (int e = 0; e < V; ++e) d.set(e, nstep * d.get(e));
+                        st_vec<T, V>(S_rw + (size_t) new_slot * ld + off, d);
                     }
-                } else if (group == 2) {
-                    if (grad_out) {
-                        if constexpr (MODE == MODE_OLBFGS) {
-                            #pragma unroll
-                            for (int e = 0; e < V; ++e) d.set(e, nstep * d.get(e));
-                        }
-                        st_vec<T, V>(grad_out + off, d);
-                    }
+                    if (grad_out) st_vec<T, V>(grad_out + off, d);
                 }
             }
         }
@@ -463,8 +454,8 @@ k3_combine(const T* g_in, T* grad_out, const T* S_ro, const T* __restrict__ Y,
     };
 
     const long long nchunks = n / VEC;
-    const long long stride = (long long) gridDim.x * kLanes;
-    for (long long base = (long long) blockIdx.x * kLanes; base < nchunks; base += stride) {   // block-uniform trip count
+    const long long stride = (long long) gridDim.x * k3Lanes;
+    for (long long base = (long long) blockIdx.x * k3Lanes; base < nchunks; base += stride) {   // block-uniform trip count
         const long long c = base + lane;
         one((size_t) c * VEC, c < nchunks, std::integral_constant<int, VEC>{});
     }
@@ -474,7 +465,7 @@ k3_combine(const T* g_in, T* grad_out, const T* S_ro, const T* __restrict__ Y,
     }
     if constexpr (MODE == MODE_DIRONLY) {
         double* out = partials + (size_t) blockIdx.x * 2;
-        block_reduce<2>(2, [&](int p) { return p == 0 ? a_dd : a_bad; }, [&](int p, double v) { out[p] = v; });
+        block_reduce<2, k3Threads>(2, [&](int p) { return p == 0 ? a_dd : a_bad; }, [&](int p, double v) { out[p] = v; });
     }
 }
 

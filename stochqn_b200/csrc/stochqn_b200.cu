@@ -209,7 +209,7 @@ int bucket(int used)
     return used <= 4 ? 4 : used <= 8 ? 8 : used <= 10 ? 10 : used <= 12 ? 12 : 16;
 }
 
-int k1_grid(Ctx* c, const void* func, long long chunks)
+int k1_grid(Ctx* c, const void* func, long long chunks, int threads = kThreads, int lanes = kLanes)
 {
     // persistent-style launch: as many CTAs as are resident at once (occupancy x SMs), grid-stride inside
     static std::mutex mu;
@@ -219,11 +219,11 @@ int k1_grid(Ctx* c, const void* func, long long chunks)
         std::lock_guard<std::mutex> lk(mu);
         auto it = occ.find(func);
         if (it == occ.end()) {
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
             occ[func] = per_sm;
         } else per_sm = it->second;
     }
-    long long g = (chunks + kLanes - 1) / kLanes;
+    long long g = (chunks + lanes - 1) / lanes;
     const long long cap = (long long) c->sm_count * per_sm;
     if (g > cap) g = cap;
     if (g > c->max_grid) g = c->max_grid;
@@ -288,8 +288,8 @@ int launch_k3_t(Ctx* c, const real_t* g, real_t* gout, real_t* S, const real_t* 
                 real_t* x, real_t* x_sum, real_t step, int force)
 {
     auto kern = k3_combine<real_t, RPG, MODE, VEC>;
-    const int grid = k1_grid(c, (const void*) kern, c->n / VEC);
-    kern<<<grid, kThreads, 0, c->stream>>>(g, gout, S, Y, S, c->ld, c->msize, used, new_slot, c->n, x, x_sum, step,
+    const int grid = k1_grid(c, (const void*) kern, c->n / VEC, k3Threads, k3Lanes);
+    kern<<<grid, k3Threads, 0, c->stream>>>(g, gout, S, Y, S, c->ld, c->msize, used, new_slot, c->n, x, x_sum, step,
                                            c->coef, c->status_dev, force, c->partials);
     COUNT_LAUNCH();
     return grid;
@@ -302,20 +302,19 @@ int launch_k3_m(Ctx* c, int rpg, const real_t* g, real_t* gout, real_t* S, const
 #define K3_RPG(R) case R: return launch_k3_t<R, MODE, VEC>(c, g, gout, S, Y, used, new_slot, x, x_sum, step, force)
     switch (rpg) {
         K3_RPG(1); K3_RPG(2); K3_RPG(3); K3_RPG(4); K3_RPG(5); K3_RPG(6); K3_RPG(7); K3_RPG(8);
-        K3_RPG(12);
-        default: return launch_k3_t<16, MODE, VEC>(c, g, gout, S, Y, used, new_slot, x, x_sum, step, force);
+        K3_RPG(10); K3_RPG(12); K3_RPG(16); K3_RPG(24);
+        default: return launch_k3_t<32, MODE, VEC>(c, g, gout, S, Y, used, new_slot, x, x_sum, step, force);
     }
 #undef K3_RPG
 }
 
 int bucket3(int used) { return used <= 16 ? bucket(used) : 32; }    // MMAX buckets of the adaQN combine
 
-int rpg_for_k3(int used)
+int rpg_for_k3(int used)        // rows per group of K3 = pairs in memory, rounded up to an instantiated bucket
 {
-    int rpg = (2 * used + kGroups - 1) / kGroups;
-    if (rpg < 1) rpg = 1;
-    if (rpg <= 8) return rpg;
-    return rpg <= 12 ? 12 : 16;
+    if (used < 1) return 1;
+    if (used <= 8) return used;
+    return used <= 10 ? 10 : used <= 12 ? 12 : used <= 16 ? 16 : used <= 24 ? 24 : 32;
 }
 
 int launch_k3(Ctx* c, int mode, const real_t* g, real_t* gout, real_t* S, const real_t* Y, int used, int new_slot,

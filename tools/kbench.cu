@@ -330,19 +330,20 @@ int main(int argc, char** argv)
     CK(cudaGetDeviceProperties(&prop, 0));
     const int sms = prop.multiProcessorCount;
     Bufs B;
-    B.n = n; B.ld = (size_t) n;
+    const long long pad = argc > 2 ? atoll(argv[2]) : 0;       // extra elements per row (row stride experiments)
+    B.n = n; B.ld = (size_t) (n + pad);
     CK(cudaMalloc(&B.g, n * 8)); CK(cudaMalloc(&B.gp, n * 8));
-    CK(cudaMalloc(&B.S, (size_t) M * n * 8)); CK(cudaMalloc(&B.Y, (size_t) M * n * 8));
+    CK(cudaMalloc(&B.S, (size_t) M * B.ld * 8)); CK(cudaMalloc(&B.Y, (size_t) M * B.ld * 8));
     CK(cudaMalloc(&B.partials, (size_t) 4096 * NSUM * 8));
     fill_kernel<<<sms * 8, 256>>>(B.g, n, 1u);
-    fill_kernel<<<sms * 8, 256>>>(B.S, (long long) M * n, 2u);
-    fill_kernel<<<sms * 8, 256>>>(B.Y, (long long) M * n, 3u);
+    fill_kernel<<<sms * 8, 256>>>(B.S, (long long) M * B.ld, 2u);
+    fill_kernel<<<sms * 8, 256>>>(B.Y, (long long) M * B.ld, 3u);
     CK(cudaDeviceSynchronize());
-    printf("device %s, %d SMs, n = %lld (vec %.0f MiB)\n", prop.name, sms, n, n * 8 / 1048576.0);
+    printf("device %s, %d SMs, n = %lld (vec %.0f MiB), row stride n + %lld\n", prop.name, sms, n, n * 8 / 1048576.0, pad);
     {
         float ms = time_it([&] { copy_kernel<<<sms * 8, 256>>>((const double2*) B.S, (double2*) B.Y, (long long) 4 * n / 2); });
         printf("%-44s             %8.3f ms  %8.1f GB/s (read+write)\n", "copy 4 vec -> 4 vec (plain LDG/STG)", ms, 8.0 * n * 8 / ms / 1e6);
-        fill_kernel<<<sms * 8, 256>>>(B.Y, (long long) M * n, 3u);
+        fill_kernel<<<sms * 8, 256>>>(B.Y, (long long) M * B.ld, 3u);
         CK(cudaDeviceSynchronize());
     }
     run_ldg<4, 64, 5, 1, false, 3>("ldg g4 l64 rpg5 u1 minb3", B, sms);

@@ -32,8 +32,9 @@ unsigned long long stochqn_b200_launch_count(void);
 /* ---- device / stream ------------------------------------------------------------------- */
 /* initialize_*() allocates on the CUDA device that is current when it is called.  All work
    of a workspace is enqueued on one stream: the legacy default stream unless set here
-   (pass e.g. torch.cuda.current_stream().cuda_stream).  run_*() returns after that stream
-   has drained, so results are final on return, as with the reference. */
+   (pass e.g. torch.cuda.current_stream().cuda_stream).  With host pointers run_*() returns after
+   that stream has drained, so results are final on return, as with the reference; with device
+   pointers results are final in stream order (see STOCHQN_B200_OPT_SYNC_RETURN). */
 int stochqn_b200_set_stream(void *ws, void *stream);
 
 /* ---- per-workspace options --------------------------------------------------------------- */
@@ -50,7 +51,13 @@ enum stochqn_b200_option {
     /* 1: bracket the streaming kernels of each call (K1 multi-dot, K3 combine/update, K4 pair) with CUDA
        events on the workspace stream and accumulate their device times; setting it (to 0 or 1) resets the
        accumulators.  Read them with stochqn_b200_get_stat.  Default 0. */
-    STOCHQN_B200_OPT_PROFILE = 3
+    STOCHQN_B200_OPT_PROFILE = 3,
+    /* device-pointer calls only.  0 (default): run_*() returns as soon as the flags its control flow needs have
+       come back (accept / reject of the direction, the curvature dots); the streaming kernel that updates x may
+       still be running, and the results are final in the order of the workspace stream - enqueue the next
+       gradient evaluation on that stream (or synchronise it) as with any CUDA library.  1: drain the stream
+       before every return, the reference's contract.  Host-pointer calls always return with everything final. */
+    STOCHQN_B200_OPT_SYNC_RETURN = 4
 };
 int stochqn_b200_set_option(void *ws, int option, long long value);
 
@@ -71,12 +78,18 @@ size_t stochqn_b200_row_stride(void *ws);
 /* ---- sharding one optimizer over several GPUs (one process per GPU) ---------------------
    Every n-vector is split into contiguous blocks; each rank creates its workspace with
    n = its own block length and registers a communicator.  Inside a step the only exchange
-   is one small all-reduce (sum, fp64, <= 4*mem_size+2 values) per reduction phase.
+   is one small all-reduce (sum, fp64, <= 4*mem_size+2 values) per reduction phase, fused into
+   the kernel that sums the partial dots (peer-memory mailboxes over NVLink; the ranks must call
+   the library in the same order, and every rank must own its GPU).
    Bootstrap: rank 0 obtains a 128-byte id, the host program ships it to the other ranks
    (torch.distributed broadcast, MPI, a file ...), every rank calls comm_init. */
 int stochqn_b200_comm_unique_id(void *id128);
 int stochqn_b200_comm_init(const void *id128, int rank, int world_size, void **comm);
 int stochqn_b200_comm_destroy(void *comm);
+/* 1 when the small all-reduces of this communicator are done over NVLink peer memory inside the kernel that
+   produces the values (cudaIpc mailboxes, one rank per GPU), 0 when they go through ncclAllReduce
+   (no peer access between the devices, or STOCHQN_B200_NO_P2P=1 in the environment) */
+int stochqn_b200_comm_uses_p2p(void *comm);
 /* n_global = sum of all ranks' n: the reference's step-rejection limit is 1e3 * n
    (src/stochqn.c:829) and must use the length of the whole vector */
 int stochqn_b200_set_comm(void *ws, void *comm, long long n_global);

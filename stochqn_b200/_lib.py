@@ -18,7 +18,8 @@ _LIBS = {}
 EXT_SYMBOLS = (
     "stochqn_b200_version", "stochqn_b200_real_bytes", "stochqn_b200_last_error", "stochqn_b200_launch_count",
     "stochqn_b200_set_stream", "stochqn_b200_set_option", "stochqn_b200_get_stat", "stochqn_b200_row_stride",
-    "stochqn_b200_comm_unique_id", "stochqn_b200_comm_init", "stochqn_b200_comm_destroy", "stochqn_b200_set_comm",
+    "stochqn_b200_comm_unique_id", "stochqn_b200_comm_init", "stochqn_b200_comm_destroy", "stochqn_b200_comm_uses_p2p",
+    "stochqn_b200_set_comm",
     "stochqn_b200_allreduce_f64",
     "stochqn_b200_rosenbrock_x0", "stochqn_b200_rosenbrock_grad", "stochqn_b200_rosenbrock_fun", "stochqn_b200_rosenbrock_halo",
     "stochqn_b200_logistic_work_size", "stochqn_b200_logistic_grad", "stochqn_b200_logistic_hess_vec",
@@ -28,6 +29,7 @@ EXT_SYMBOLS = (
 OPT_GRAD_WRITEBACK = 1
 OPT_TRUST_X_MIRROR = 2
 OPT_PROFILE = 3
+OPT_SYNC_RETURN = 4
 STAT_K1_MS, STAT_K1_COUNT, STAT_K3_MS, STAT_K3_COUNT, STAT_K4_MS, STAT_K4_COUNT, STAT_LAST_BOUND = 1, 2, 3, 4, 5, 6, 7
 STAT_EXACT_NORM_STEPS = 8
 
@@ -69,6 +71,7 @@ def load(dtype=np.float64) -> StochqnABI:
     lib.stochqn_b200_comm_unique_id.argtypes = [vp]
     lib.stochqn_b200_comm_init.argtypes = [vp, ci, ci, C.POINTER(vp)]
     lib.stochqn_b200_comm_destroy.argtypes = [vp]
+    lib.stochqn_b200_comm_uses_p2p.argtypes = [vp]
     lib.stochqn_b200_set_comm.argtypes = [vp, vp, ll]
     lib.stochqn_b200_allreduce_f64.argtypes = [vp, vp, sz, vp]
     lib.stochqn_b200_rosenbrock_x0.argtypes = [vp, ll, ll, vp]

@@ -23,6 +23,7 @@
 #include <math.h>
 #include <type_traits>
 #include "vecio.cuh"
+#include "p2p.cuh"
 
 namespace sqn {
 
@@ -31,7 +32,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kMaxMem = 32;            // largest mem_size handled by the compact solve
 
 // status word written by K2 (device + mapped host copy)
-enum : int { ST_ACCEPT = 0, ST_REJECT_NONFINITE = 1, ST_NEED_EXACT_NORM = 2 };
+enum : int { ST_ACCEPT = 0, ST_REJECT_NONFINITE = 1, ST_NEED_EXACT_NORM = 2, ST_COMM_TIMEOUT = 3 };
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -240,7 +241,15 @@ struct SolveArgs {
     int check_nan;
     double h0;                          // hess_init (oLBFGS) or 0
     double limit;                       // 1e3 * n_global
+    unsigned long long seq;             // published to the host flag block after the status word (host polls it)
 };
+
+// what the host polls: payload first, then a system-scope fence, then the sequence number
+__device__ __forceinline__ void publish_seq(volatile unsigned long long* seq_host, unsigned long long seq)
+{
+    __threadfence_system();
+    *seq_host = seq;
+}
 
 __device__ __forceinline__ bool finite_d(double v) { return isfinite(v); }
 
@@ -257,14 +266,16 @@ __device__ __forceinline__ void reduce_partials(const double* __restrict__ parti
 }
 
 __global__ void __launch_bounds__(kThreads)
-k2_solve(SolveArgs A, const double* __restrict__ partials, double* __restrict__ sums,
+k2_solve(SolveArgs A, PeerArgs pa, const double* __restrict__ partials, double* sums,
          double* __restrict__ SY, double* __restrict__ YY, double* __restrict__ SS,
          double* __restrict__ coef, int* __restrict__ status_dev, volatile int* status_host,
-         volatile double* info_host)
+         volatile double* info_host, volatile unsigned long long* seq_host)
 {
     const int m = A.msize, used = A.used;
     const int P = 4 * m + 2;
     if (A.nblocks > 0) { reduce_partials(partials, A.nblocks, P, sums); __syncthreads(); }
+    bool comm_ok = true;
+    if (pa.world > 1) comm_ok = p2p_allreduce_cta(pa, sums, P);      // sharded: sum the records of all ranks (p2p.cuh)
     if (!A.do_solve) return;
 
     auto ph = [&](int i) { int s = A.oldest + i; return s >= m ? s - m : s; };      // logical (oldest..newest) -> physical slot
@@ -333,12 +344,13 @@ k2_solve(SolveArgs A, const double* __restrict__ partials, double* __restrict__ 
         else if (used == 0) { if (U > A.limit) st = ST_REJECT_NONFINITE; }      // d = g: U is the exact norm (stochqn.c:829)
         else if (!(U <= 0.99 * A.limit)) st = ST_NEED_EXACT_NORM;
     }
+    if (!comm_ok) st = ST_COMM_TIMEOUT;
     *status_dev = st;
     *status_host = st;
     info_host[0] = U;
     info_host[1] = gamma;
     info_host[2] = gg;
-    __threadfence_system();
+    publish_seq(seq_host, A.seq);
 }
 
 // =========================================================================================
@@ -561,27 +573,44 @@ k4_pair(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ 
     block_reduce<2>(2, [&](int p) { return p == 0 ? a_sy : a_ss; }, [&](int p, double v) { out[p] = v; });
 }
 
-// Sum `count`-wide partial records over CTAs into `sums` (device) and, when asked, into mapped
-// host memory.  One CTA.  Used for the 2-value records of K4 / MODE_DIRONLY.
+// Sum `count`-wide partial records over CTAs into `sums` (device), across ranks when sharded (p2p.cuh), and, when
+// asked, into mapped host memory followed by the sequence number the host polls.  One CTA.
+// Used for the 2-value records of K4 / MODE_DIRONLY and the k Fisher dots.
 __global__ void __launch_bounds__(kThreads)
-k_finalize(const double* __restrict__ partials, int nblocks, int count, double* __restrict__ sums,
-           volatile double* host_out)
+k_finalize(const double* __restrict__ partials, int nblocks, int count, double* sums, PeerArgs pa,
+           volatile double* host_out, volatile unsigned long long* seq_host, unsigned long long seq)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int p = warp; p < count; p += kWarps) {
         double v = 0;
         for (int b = lane; b < nblocks; b += 32) v += partials[(size_t) b * count + p];
         v = warp_sum(v);
-        if (lane == 0) { sums[p] = v; if (host_out) host_out[p] = v; }
+        if (lane == 0) sums[p] = v;
     }
-    if (host_out) __threadfence_system();
+    __syncthreads();
+    bool ok = true;
+    if (pa.world > 1) ok = p2p_allreduce_cta(pa, sums, count);
+    if (host_out) {
+        for (int p = threadIdx.x; p < count; p += kThreads) host_out[p] = ok ? sums[p] : __longlong_as_double(0x7ff8000000000000ll);
+        __syncthreads();
+        if (threadIdx.x == 0) publish_seq(seq_host, seq);
+    }
 }
 
-// device -> mapped-host copy of a few doubles (after an all-reduce landed them in `sums`)
-__global__ void k_publish(const double* __restrict__ sums, int count, volatile double* host_out)
+// device -> mapped-host copy of a few doubles (after a library all-reduce landed them in `sums`)
+__global__ void k_publish(const double* __restrict__ sums, int count, volatile double* host_out,
+                          volatile unsigned long long* seq_host, unsigned long long seq)
 {
     if (threadIdx.x < count) host_out[threadIdx.x] = sums[threadIdx.x];
-    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) publish_seq(seq_host, seq);
+}
+
+// stand-alone small all-reduce (sum, fp64, count <= kBoxCap) over peer memory: callbacks ride on it (halo exchange)
+__global__ void __launch_bounds__(kThreads)
+k_p2p_allreduce(double* buf, int count, PeerArgs pa, int* __restrict__ error_flag)
+{
+    if (!p2p_allreduce_cta(pa, buf, count) && threadIdx.x == 0 && error_flag) *error_flag = 1;
 }
 
 // Gram bookkeeping for a slot that was zeroed by a rejected pair (quirk Q1): the slot now holds
@@ -809,14 +838,16 @@ ka2_wgram(const T* __restrict__ g, const T* __restrict__ G, const T* __restrict_
 // KA-solve: adaQN flavour of K2 (same Gram bookkeeping, diagonal-H0 algebra).
 // coef layout: [0,m) a, [m,2m) b (NOT scaled), [2m] unused, [2m+1] U, [2m+2] first scalar of the record.
 __global__ void __launch_bounds__(kThreads)
-ka_solve(SolveArgs A, const double* __restrict__ partials, double* __restrict__ sums,
+ka_solve(SolveArgs A, PeerArgs pa, const double* __restrict__ partials, double* sums,
          double* __restrict__ SY, double* __restrict__ YY, double* __restrict__ SS,
          double* __restrict__ coef, int* __restrict__ status_dev, volatile int* status_host,
-         volatile double* info_host)
+         volatile double* info_host, volatile unsigned long long* seq_host)
 {
     const int m = A.msize, used = A.used;
     const int P = 3 * m + 4 + m * m;
     if (A.nblocks > 0) { reduce_partials(partials, A.nblocks, P, sums); __syncthreads(); }
+    bool comm_ok = true;
+    if (pa.world > 1) comm_ok = p2p_allreduce_cta(pa, sums, P);
     if (!A.do_solve) return;
     auto ph = [&](int i) { int s = A.oldest + i; return s >= m ? s - m : s; };
     if (A.pend >= 0) {
@@ -882,12 +913,13 @@ ka_solve(SolveArgs A, const double* __restrict__ partials, double* __restrict__ 
         else if (used == 0) { if (U > A.limit) st = ST_REJECT_NONFINITE; }      // U is the exact norm here
         else if (!(U <= 0.99 * A.limit)) st = ST_NEED_EXACT_NORM;
     }
+    if (!comm_ok) st = ST_COMM_TIMEOUT;
     *status_dev = st;
     *status_host = st;
     info_host[0] = U;
     info_host[1] = 1.0;
     info_host[2] = n0;
-    __threadfence_system();
+    publish_seq(seq_host, A.seq);
 }
 
 // KA3: adaQN combine + update:  h = g/sqrt(G+eps) ;  d = (used ? h*(g + sum b_j y_j) + sum a_j s_j : h)

@@ -20,6 +20,7 @@
 #include <atomic>
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 #include "stochqn.h"
 #include "stochqn_b200.h"
@@ -62,6 +63,7 @@ struct NcclApi {
     int (*CommInitRank)(void**, int, Id128, int) = nullptr;                // ncclCommInitRank(&comm, nranks, id, rank)
     int (*CommDestroy)(void*) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
 NcclApi g_nccl;
@@ -79,8 +81,9 @@ int load_nccl()
     g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank)) dlsym(h, "ncclCommInitRank");
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy)) dlsym(h, "ncclCommDestroy");
     g_nccl.AllReduce = (decltype(g_nccl.AllReduce)) dlsym(h, "ncclAllReduce");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather)) dlsym(h, "ncclAllGather");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString)) dlsym(h, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce)
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce || !g_nccl.AllGather)
         return fail(-3, "NCCL library lacks an expected symbol");
     g_nccl.handle = h;
     return 0;
@@ -89,7 +92,25 @@ int load_nccl()
 struct Comm {
     void* nccl = nullptr;
     int rank = 0, world = 1;
+    // peer-memory mailboxes for the fused small all-reduce (p2p.cuh); p2p == false -> library all-reduce
+    bool p2p = false;
+    unsigned char* box = nullptr;                 // this rank's mailbox (cudaMalloc, IPC-exported)
+    unsigned char* peer[kMaxWorld] = {};          // every rank's mailbox as mapped here (peer[rank] == box)
+    unsigned long long seq = 0;                   // exchanges issued so far (identical on every rank)
+    int* error_flag = nullptr;                    // device word set by a timed-out stand-alone exchange
 };
+
+// PeerArgs of the NEXT exchange on this communicator (world = 0 when there is nothing to exchange or no p2p)
+PeerArgs next_exchange(Comm* cm, size_t count)
+{
+    PeerArgs pa;
+    if (!cm || cm->world <= 1 || !cm->p2p || count > (size_t) kBoxCap) return pa;
+    pa.rank = cm->rank;
+    pa.world = cm->world;
+    pa.seq = ++cm->seq;
+    for (int r = 0; r < cm->world; ++r) pa.box[r] = cm->peer[r];
+    return pa;
+}
 
 // ------------------------------------------------------------------------------------------
 // private per-workspace state
@@ -100,7 +121,9 @@ struct HostBlock {              // pinned, mapped: written by kernels, read by t
     volatile double info[4];    // U bound, gamma, g'g
     volatile double pair[2];    // s'y, s's
     volatile double dir[2];     // sum d^2, number of non-finite entries
+    volatile unsigned long long seq[3];   // written LAST by the kernel that fills status+info / pair / dir
 };
+enum { FLAG_STATUS = 0, FLAG_PAIR = 1, FLAG_DIR = 2 };
 
 enum Kind { K_OLBFGS = 1, K_SQN = 2, K_ADAQN = 3 };
 
@@ -138,19 +161,23 @@ struct Ctx {
     double prof_n[3] = {0, 0, 0};
     double last_bound = 0;
     double exact_norm_steps = 0;        // steps that took the two-pass (exact ||d||) route
+    unsigned long long seq_want[3] = {0, 0, 0};   // sequence numbers the host is waiting for (HostBlock::seq)
+    int sync_return = 0;                // 1: drain the stream before every return, also for device-pointer calls
 };
 
-void prof_begin(Ctx* c, int k) { if (c->profile) cudaEventRecord(c->ev[2 * k], c->stream); }
-void prof_end(Ctx* c, int k) { if (c->profile) { cudaEventRecord(c->ev[2 * k + 1], c->stream); c->ev_armed[k] = true; } }
-void prof_collect(Ctx* c)      // after a stream synchronisation
+void prof_collect_one(Ctx* c, int k)      // waits for the closing event of kernel class k (long past when re-armed)
 {
-    if (!c->profile) return;
-    for (int k = 0; k < 3; ++k) {
-        if (!c->ev_armed[k]) continue;
-        float ms = 0;
-        if (cudaEventElapsedTime(&ms, c->ev[2 * k], c->ev[2 * k + 1]) == cudaSuccess) { c->prof_ms[k] += ms; c->prof_n[k] += 1; }
-        c->ev_armed[k] = false;
-    }
+    if (!c->ev_armed[k]) return;
+    float ms = 0;
+    if (cudaEventSynchronize(c->ev[2 * k + 1]) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, c->ev[2 * k], c->ev[2 * k + 1]) == cudaSuccess) { c->prof_ms[k] += ms; c->prof_n[k] += 1; }
+    c->ev_armed[k] = false;
+}
+void prof_begin(Ctx* c, int k) { if (c->profile) { prof_collect_one(c, k); cudaEventRecord(c->ev[2 * k], c->stream); } }
+void prof_end(Ctx* c, int k) { if (c->profile) { cudaEventRecord(c->ev[2 * k + 1], c->stream); c->ev_armed[k] = true; } }
+void prof_collect(Ctx* c)
+{
+    for (int k = 0; k < 3; ++k) prof_collect_one(c, k);
 }
 
 std::unordered_map<const void*, Ctx*> g_registry;
@@ -190,10 +217,19 @@ int grid_for(const Ctx* c, long long work_items)
 bool is_device_ptr(const void* p)
 {
     if (!p) return true;
+    // the same few arrays come back call after call: remember the answer (device and host address ranges are
+    // disjoint under unified addressing, so a remembered answer cannot go stale)
+    thread_local const void* seen[4] = {nullptr, nullptr, nullptr, nullptr};
+    thread_local bool kind[4] = {false, false, false, false};
+    thread_local int next = 0;
+    for (int i = 0; i < 4; ++i) if (seen[i] == p) return kind[i];
     cudaPointerAttributes a;
     cudaError_t e = cudaPointerGetAttributes(&a, p);
-    if (e != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+    bool dev = false;
+    if (e != cudaSuccess) cudaGetLastError();
+    else dev = a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+    seen[next] = p; kind[next] = dev; next = (next + 1) & 3;
+    return dev;
 }
 
 constexpr int VECW = 16 / sizeof(real_t);
@@ -377,51 +413,93 @@ int allreduce_sums(Ctx* c, double* buf, size_t count)
 
 double step_limit(const Ctx* c) { return 1e3 * (double) (c->n_global > 0 ? c->n_global : c->n); }
 
-// Reduce the K1 partials, (all-reduce,) solve.  One launch on one GPU, three steps when sharded.
+// Reduce the K1 partials, sum them over the ranks, solve.  ONE launch: on one GPU, and when sharded with
+// peer-memory mailboxes (the exchange happens inside the kernel, p2p.cuh); three steps with a library all-reduce.
 int launch_solve(Ctx* c, bool ada, int nblocks, int used, int oldest, int pend, int check_nan, double h0)
 {
     SolveArgs A;
     A.msize = c->msize; A.used = used; A.oldest = oldest; A.pend = pend;
     A.check_nan = check_nan; A.h0 = h0; A.limit = step_limit(c);
-    auto go = [&](const SolveArgs& a) {
-        if (ada) ka_solve<<<1, kThreads, 0, c->stream>>>(a, c->partials, c->sums, c->SY, c->YY, c->SS, c->coef,
-                                                         c->status_dev, &c->hb_dev->status, c->hb_dev->info);
-        else     k2_solve<<<1, kThreads, 0, c->stream>>>(a, c->partials, c->sums, c->SY, c->YY, c->SS, c->coef,
-                                                         c->status_dev, &c->hb_dev->status, c->hb_dev->info);
+    A.seq = ++c->seq_want[FLAG_STATUS];
+    auto go = [&](const SolveArgs& a, const PeerArgs& pa) {
+        if (ada) ka_solve<<<1, kThreads, 0, c->stream>>>(a, pa, c->partials, c->sums, c->SY, c->YY, c->SS, c->coef,
+                                                         c->status_dev, &c->hb_dev->status, c->hb_dev->info, &c->hb_dev->seq[FLAG_STATUS]);
+        else     k2_solve<<<1, kThreads, 0, c->stream>>>(a, pa, c->partials, c->sums, c->SY, c->YY, c->SS, c->coef,
+                                                         c->status_dev, &c->hb_dev->status, c->hb_dev->info, &c->hb_dev->seq[FLAG_STATUS]);
         COUNT_LAUNCH();
     };
-    if (c->comm && c->comm->world > 1) {
-        const size_t P = ada ? (size_t) (3 * c->msize + 4 + c->msize * c->msize) : (size_t) (4 * c->msize + 2);
-        A.nblocks = nblocks; A.do_solve = 0; go(A);
+    const size_t P = ada ? (size_t) (3 * c->msize + 4 + c->msize * c->msize) : (size_t) (4 * c->msize + 2);
+    const bool sharded = c->comm && c->comm->world > 1;
+    PeerArgs pa = sharded ? next_exchange(c->comm, P) : PeerArgs();
+    if (sharded && pa.world == 0) {
+        A.nblocks = nblocks; A.do_solve = 0; go(A, pa);
         if (int r = allreduce_sums(c, c->sums, P)) return r;
-        A.nblocks = 0; A.do_solve = 1; go(A);
+        A.nblocks = 0; A.do_solve = 1; go(A, pa);
     } else {
-        A.nblocks = nblocks; A.do_solve = 1; go(A);
+        A.nblocks = nblocks; A.do_solve = 1; go(A, pa);
     }
     return 0;
 }
 
-// Sum 2-wide partial records, (all-reduce,) publish into mapped host memory.
-int launch_pair_finalize(Ctx* c, int nblocks, volatile double* host_dst)
+// Sum `count`-wide partial records, over the ranks too, and publish them into mapped host memory (flag `which`).
+int launch_finalize(Ctx* c, int nblocks, int count, volatile double* host_dst, int which)
 {
-    if (c->comm && c->comm->world > 1) {
-        k_finalize<<<1, kThreads, 0, c->stream>>>(c->partials, nblocks, 2, c->sums, nullptr);
+    const unsigned long long seq = host_dst ? ++c->seq_want[which] : 0;
+    volatile unsigned long long* seq_dst = host_dst ? &c->hb_dev->seq[which] : nullptr;
+    const bool sharded = c->comm && c->comm->world > 1;
+    PeerArgs pa = sharded ? next_exchange(c->comm, (size_t) count) : PeerArgs();
+    if (sharded && pa.world == 0) {
+        k_finalize<<<1, kThreads, 0, c->stream>>>(c->partials, nblocks, count, c->sums, pa, nullptr, nullptr, 0);
         COUNT_LAUNCH();
-        if (int r = allreduce_sums(c, c->sums, 2)) return r;
-        k_publish<<<1, 32, 0, c->stream>>>(c->sums, 2, host_dst);
-        COUNT_LAUNCH();
+        if (int r = allreduce_sums(c, c->sums, (size_t) count)) return r;
+        if (host_dst) { k_publish<<<1, 32, 0, c->stream>>>(c->sums, count, host_dst, seq_dst, seq); COUNT_LAUNCH(); }
     } else {
-        k_finalize<<<1, kThreads, 0, c->stream>>>(c->partials, nblocks, 2, c->sums, host_dst);
+        k_finalize<<<1, kThreads, 0, c->stream>>>(c->partials, nblocks, count, c->sums, pa, host_dst, seq_dst, seq);
         COUNT_LAUNCH();
     }
     return 0;
+}
+int launch_pair_finalize(Ctx* c, int nblocks, volatile double* host_dst)
+{
+    return launch_finalize(c, nblocks, 2, host_dst, host_dst == c->hb_dev->pair ? FLAG_PAIR : FLAG_DIR);
 }
 
 int sync_stream(Ctx* c)
 {
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) return fail(-2, "device work failed: %s", cudaGetErrorString(e));
-    prof_collect(c);
+    return 0;
+}
+
+// Wait until the kernel that fills flag block `which` has published it.  The host spins on the mapped sequence
+// word instead of draining the stream: the answer is there the moment the small kernel retires, while the
+// streaming kernel queued behind it (K3) is still running - the call returns and the caller queues its next
+// kernel without a bubble on the GPU.
+int wait_flag(Ctx* c, int which)
+{
+    const unsigned long long want = c->seq_want[which];
+    volatile unsigned long long* p = &c->hb->seq[which];
+    for (unsigned long spins = 1;; ++spins) {
+        if (*p == want) return 0;
+        if ((spins & 0xfffu) == 0) {                     // every 4096 polls: has the stream died or drained?
+            cudaError_t e = cudaStreamQuery(c->stream);
+            if (e == cudaSuccess) {
+                if (*p == want) return 0;
+                return fail(-2, "device work finished without publishing its result (flag %d)", which);
+            }
+            if (e != cudaErrorNotReady) return fail(-2, "device work failed: %s", cudaGetErrorString(e));
+        }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+}
+
+// End of a call: host-pointer callers (and sync_return) get the reference's contract - everything final on
+// return; device-pointer callers get stream-ordered semantics (results are final in the workspace stream's order).
+int finish_call(Ctx* c, bool host_mode)
+{
+    if (host_mode || c->sync_return) return sync_stream(c);
     return 0;
 }
 
@@ -580,16 +658,17 @@ int take_step_qn(Ctx* c, bfgs_mem* m, int mode, real_t step, real_t* x, real_t* 
     prof_begin(c, 1);
     launch_k3(c, mode, g, gout, m->s_mem, m->y_mem, used, st, x, x_sum, step, 0);
     prof_end(c, 1);
-    if (int r = sync_stream(c)) return r;
+    if (int r = wait_flag(c, FLAG_STATUS)) return r;          // K2 has retired; K3 may still be running
     int status = c->hb->status;
     c->last_bound = c->hb->info[0];
+    if (status == ST_COMM_TIMEOUT) return fail(-4, "a peer rank did not join the all-reduce of this step");
     if (status == ST_NEED_EXACT_NORM) {
         c->exact_norm_steps += 1;
         // rare: the cheap bound could not certify ||d|| <= 1e3*n.  Materialise d in `grad`, measure it
         // exactly, and only then touch x - the reference's order (stochqn.c:825-838).
         int nb2 = launch_k3(c, MODE_DIRONLY, g, g, m->s_mem, m->y_mem, used, st, x, x_sum, step, 1);
         if (int r = launch_pair_finalize(c, nb2, c->hb_dev->dir)) return r;
-        if (int r = sync_stream(c)) return r;
+        if (int r = wait_flag(c, FLAG_DIR)) return r;
         const double dd = c->hb->dir[0], bad = c->hb->dir[1];
         if (bad > 0 || !(sqrt(dd) <= step_limit(c))) status = ST_REJECT_NONFINITE;
         else {
@@ -636,7 +715,7 @@ int update_y_grad_diff_dev(Ctx* c, bfgs_mem* m, const real_t* grad, const real_t
     int nb = launch_k4_k<PAIR_GRAD_DIFF>(c, grad, grad_prev, s, y, m->y_reg);
     prof_end(c, 2);
     if (int r = launch_pair_finalize(c, nb, c->hb_dev->pair)) return r;
-    if (int r = sync_stream(c)) return r;
+    if (int r = wait_flag(c, FLAG_PAIR)) return r;
     return curvature_decision(c, m, c->hb->pair[0], c->hb->pair[1], info);
 }
 
@@ -784,6 +863,7 @@ int run_oLBFGS(real_t step_size, real_t x[], real_t grad[], real_t** req, task_e
     if (!c || c->kind != K_OLBFGS) return invalid_ws("oLBFGS", task);
     if (enter(c)) return invalid_ws("oLBFGS", task);
     bfgs_mem* m = ws->bfgs_memory;
+    const bool host_mode = (x && !is_device_ptr(x)) || (grad && !is_device_ptr(grad));
 
     if (ws->section == 0) {                                     // stochqn.c:983-989
         *task = calc_grad;
@@ -806,10 +886,11 @@ int run_oLBFGS(real_t step_size, real_t x[], real_t grad[], real_t** req, task_e
         if (*iter_info == no_problems_encountered) {
             if (sx.host) { if (stage_out(c, sx)) return invalid_ws("oLBFGS", task); c->x_mirror_valid = true; }
             if (sg.host && c->grad_writeback) { if (stage_out(c, sg)) return invalid_ws("oLBFGS", task); }
-            if (sx.host || sg.host) { if (sync_stream(c)) return invalid_ws("oLBFGS", task); }
+            if (finish_call(c, host_mode)) return invalid_ws("oLBFGS", task);
             ws->section = 2;
             return 1;
         }
+        if (finish_call(c, host_mode)) return invalid_ws("oLBFGS", task);
         ws->section = 1;
         return 0;
     }
@@ -818,6 +899,7 @@ int run_oLBFGS(real_t step_size, real_t x[], real_t grad[], real_t** req, task_e
         Staged sg;
         if (stage_in(c, grad, &c->dg, &sg, true)) return invalid_ws("oLBFGS", task);
         if (update_y_grad_diff_dev(c, m, sg.dev, ws->grad_prev, iter_info) < 0) return invalid_ws("oLBFGS", task);
+        if (finish_call(c, host_mode)) return invalid_ws("oLBFGS", task);
         *task = calc_grad;
         *req = x;
         ws->section = 1;
@@ -894,18 +976,18 @@ int run_SQN(real_t step_size, real_t x[], real_t grad[], real_t hess_vec[], real
         if (sg.host && return_value && c->grad_writeback) { if (stage_out(c, sg)) SQN_FAIL(); }
 
         const size_t L = m->upd_freq;
-        if ((ws->niter % L) != 0) { if (sync_stream(c)) SQN_FAIL(); SQN_RESUME(); }
+        if ((ws->niter % L) != 0) { if (finish_call(c, host_mode)) SQN_FAIL(); SQN_RESUME(); }
         const real_t inv = (real_t) 1 / (real_t) L;             // average_from_sum, stochqn.c:286-291
         if (ws->niter == L) {                                   // 1078-1094
             launch_avg<AVG_ARCHIVE>(c, ws->x_sum, ws->x_avg_prev, nullptr, L > 1 ? inv : (real_t) 1);
             if (ws->use_grad_diff) {
                 *task = calc_grad_big_batch;
                 if (publish_req(c, host_mode, ws->x_avg_prev, &c->hreq, req)) SQN_FAIL();
-                if (sync_stream(c)) SQN_FAIL();
+                if (finish_call(c, host_mode)) SQN_FAIL();
                 ws->section = 2;
                 return return_value;
             }
-            if (sync_stream(c)) SQN_FAIL();
+            if (finish_call(c, host_mode)) SQN_FAIL();
             SQN_RESUME();
         }
         // update_s_vector (861-870): x_sum becomes the average, s = x_avg - x_avg_prev into the next slot
@@ -920,7 +1002,7 @@ int run_SQN(real_t step_size, real_t x[], real_t grad[], real_t hess_vec[], real
             ws->section = 4;
             if (publish_req(c, host_mode, s_slot, &c->hreq_vec, req_vec)) SQN_FAIL();
         }
-        if (sync_stream(c)) SQN_FAIL();
+        if (finish_call(c, host_mode)) SQN_FAIL();
         return return_value;
     }
 
@@ -928,7 +1010,7 @@ int run_SQN(real_t step_size, real_t x[], real_t grad[], real_t hess_vec[], real
         Staged sg;
         if (stage_in(c, grad, &c->dg, &sg, true)) SQN_FAIL();
         if (copy_vec_dev(c, ws->grad_prev, sg.dev)) SQN_FAIL();
-        if (sync_stream(c)) SQN_FAIL();
+        if (finish_call(c, host_mode)) SQN_FAIL();
         SQN_RESUME();
     }
 
@@ -941,7 +1023,7 @@ int run_SQN(real_t step_size, real_t x[], real_t grad[], real_t hess_vec[], real
             if (copy_vec_dev(c, ws->x_avg_prev, ws->x_sum)) SQN_FAIL();
         }
         if (cudaMemsetAsync(ws->x_sum, 0, (size_t) c->n * sizeof(real_t), c->stream) != cudaSuccess) SQN_FAIL();
-        if (sync_stream(c)) SQN_FAIL();
+        if (finish_call(c, host_mode)) SQN_FAIL();
         SQN_RESUME();
     }
 
@@ -952,9 +1034,9 @@ int run_SQN(real_t step_size, real_t x[], real_t grad[], real_t hess_vec[], real
         const size_t slot = m->mem_st_ix;
         int nb = launch_k4_k<PAIR_COPY>(c, shv.dev, shv.dev, m->s_mem + slot * c->ld, m->y_mem + slot * c->ld, (real_t) 0);
         if (launch_pair_finalize(c, nb, c->hb_dev->pair)) SQN_FAIL();
-        if (sync_stream(c)) SQN_FAIL();
+        if (wait_flag(c, FLAG_PAIR)) SQN_FAIL();
         if (curvature_decision(c, m, c->hb->pair[0], c->hb->pair[1], iter_info)) SQN_FAIL();
-        if (sync_stream(c)) SQN_FAIL();
+        if (finish_call(c, host_mode)) SQN_FAIL();
         SQN_RESUME();
     }
     return invalid_ws("SQN", task);                             // 1144-1146

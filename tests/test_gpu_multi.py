@@ -1,0 +1,48 @@
+"""Sharded optimisation on 2 GPUs (one process per GPU, torch.distributed.run) against the oracle on the whole
+vector: task / counter sequences identical on every rank and equal to the oracle's, iterates within 1e-10.
+Covers both exchange paths: peer-memory mailboxes fused into K2 / the pair finalisation (default) and the
+ncclAllReduce fallback (STOCHQN_B200_NO_P2P=1).  Skipped on boxes with one GPU."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("kind", ["oLBFGS", "SQN"])
+@pytest.mark.parametrize("no_p2p", [0, 1], ids=["p2p", "nccl"])
+def test_sharded_two_gpus_matches_oracle(tmp_path, kind, no_p2p):
+    out = str(tmp_path / "res.json")
+    env = dict(os.environ, STOCHQN_B200_NO_P2P=str(no_p2p))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(HERE, "multi_gpu_worker.py"), kind, "100003", "90", out]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    res = json.load(open(out))
+    assert res["uses_p2p"] == (0 if no_p2p else 1), res
+    assert res["same_on_all_ranks"] and res["matches_oracle"], res
+    assert res["pairs"] >= 4, res
+    assert res["rel_err"] <= 1e-10, res

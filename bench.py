@@ -203,9 +203,10 @@ def main_b200(args):
     events = {"info": 0}
 
     def serve_gradient():
-        if world > 1:
-            lib.stochqn_b200_rosenbrock_halo(req.value, n_local, rank, world, comm, hp, sp, stream)
-        lib.stochqn_b200_rosenbrock_grad(req.value, gp, n_local, offset, n, hp, stream)
+        if world > 1:       # halo exchange fused into the gradient kernel (peer memory), one launch
+            lib.stochqn_b200_rosenbrock_grad_sharded(req.value, gp, n_local, offset, n, rank, world, comm, hp, sp, stream)
+        else:
+            lib.stochqn_b200_rosenbrock_grad(req.value, gp, n_local, offset, n, hp, stream)
 
     def iteration():
         serve_gradient()                                                                          # calc_grad
@@ -358,16 +359,29 @@ def run_e2e(args, lib, abi, rank, world, local_rank, n, offset, n_local, comm, d
             hr = float(parts[rank + 1][0]) if rank < world - 1 else 0.0
         hostcb.host_rosenbrock_grad(req.value, gp, n_local, offset, n, hl, hr)
 
+    split = {"callback_s": 0.0, "step_call_s": 0.0, "pair_call_s": 0.0}
+
     def iteration():
+        t_a = time.perf_counter()
         serve()
+        t_b = time.perf_counter()
         lib.run_oLBFGS(STEP, xp, gp, C.byref(req), C.byref(task), ws, C.byref(info))
+        t_c = time.perf_counter()
+        split["callback_s"] += t_b - t_a
+        split["step_call_s"] += t_c - t_b
         if task.value == 102:
             serve()
+            t_d = time.perf_counter()
             lib.run_oLBFGS(STEP, xp, gp, C.byref(req), C.byref(task), ws, C.byref(info))
+            t_e = time.perf_counter()
+            split["callback_s"] += t_d - t_c
+            split["pair_call_s"] += t_e - t_d
 
     lib.run_oLBFGS(STEP, xp, gp, C.byref(req), C.byref(task), ws, C.byref(info))
     for _ in range(warmup):
         iteration()
+    for k in split:
+        split[k] = 0.0
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -386,6 +400,9 @@ def run_e2e(args, lib, abi, rank, world, local_rank, n, offset, n_local, comm, d
     # per iteration and rank: step call uploads x and grad, downloads x and grad (write-back on); pair call uploads grad
     return {"value": steps / dt, "unit": "steps/s", "h2d_bytes_per_step": 3 * vec * world, "d2h_bytes_per_step": 2 * vec * world,
             "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * dt / steps,
+            "ms_split_rank0": {"host_gradient_callbacks": 1e3 * split["callback_s"] / steps,
+                               "run_oLBFGS_step_call (H2D x, grad; K1-K3; D2H x, grad)": 1e3 * split["step_call_s"] / steps,
+                               "run_oLBFGS_pair_call (H2D grad; K4)": 1e3 * split["pair_call_s"] / steps},
             "path": "run_oLBFGS with host pointers (pinned), host C+OpenMP gradient callback, %d host threads per rank" % host_threads}
 
 

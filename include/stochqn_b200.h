@@ -48,7 +48,7 @@ enum stochqn_b200_option {
        the reference re-reads the caller's array each call.  1: trust the device mirror (the
        caller promises not to modify x between calls) - saves one host->device copy per step. */
     STOCHQN_B200_OPT_TRUST_X_MIRROR = 2,
-    /* 1: bracket the streaming kernels of each call (K1 multi-dot, K3 combine/update, K4 pair) with CUDA
+    /* 1: bracket the streaming kernels of each call (K1 multi-dot, K3 combine/update, K4 pair; adaQN: KA1, KA3, KA2) with CUDA
        events on the workspace stream and accumulate their device times; setting it (to 0 or 1) resets the
        accumulators.  Read them with stochqn_b200_get_stat.  Default 0. */
     STOCHQN_B200_OPT_PROFILE = 3,
@@ -66,7 +66,8 @@ enum stochqn_b200_stat {
     STOCHQN_B200_STAT_K3_MS = 3, STOCHQN_B200_STAT_K3_COUNT = 4,
     STOCHQN_B200_STAT_K4_MS = 5, STOCHQN_B200_STAT_K4_COUNT = 6,
     STOCHQN_B200_STAT_LAST_BOUND = 7,                                 /* bound on ||direction|| of the last step */
-    STOCHQN_B200_STAT_EXACT_NORM_STEPS = 8                            /* steps that needed the exact-norm (two-pass) route */
+    STOCHQN_B200_STAT_EXACT_NORM_STEPS = 8,                           /* steps that needed the exact-norm (two-pass) route */
+    STOCHQN_B200_STAT_KA2_MS = 9, STOCHQN_B200_STAT_KA2_COUNT = 10    /* adaQN: the second dot pass (K1/K3 slots hold KA1/KA3) */
 };
 int stochqn_b200_get_stat(void *ws, int what, double *out);
 
@@ -132,6 +133,14 @@ int stochqn_b200_logistic_hess_vec(const real_t *X, long long ldx, const real_t 
 int stochqn_b200_logistic_loss(const real_t *X, long long ldx, const real_t *y, const real_t *sw,
                                long long nrows, long long ncols, const real_t *w, real_t lambda,
                                double *loss_dev, void *work, void *stream);
+
+/* Sharded gradient in ONE launch: the halo exchange is fused into the gradient kernel (CTA 0 exchanges the shard
+   ends over the communicator's peer-memory mailboxes while the other CTAs stream; falls back to
+   stochqn_b200_rosenbrock_halo + stochqn_b200_rosenbrock_grad when the communicator has no peer-memory path).
+   `halo` (real_t[2]) and `scratch` (2*world_size doubles) are device scratch for the fallback. */
+int stochqn_b200_rosenbrock_grad_sharded(const real_t *x, real_t *grad, long long n_local, long long offset,
+                                         long long n_global, int rank, int world_size, void *comm,
+                                         real_t *halo, double *scratch, void *stream);
 
 /* ---- workspace export / import (checkpoint / resume) ----------------------------------------
    The reference keeps all state in host-language arrays, so saveRDS / pickle of the R / Python

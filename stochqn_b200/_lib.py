@@ -22,6 +22,7 @@ EXT_SYMBOLS = (
     "stochqn_b200_set_comm",
     "stochqn_b200_allreduce_f64",
     "stochqn_b200_rosenbrock_x0", "stochqn_b200_rosenbrock_grad", "stochqn_b200_rosenbrock_fun", "stochqn_b200_rosenbrock_halo",
+    "stochqn_b200_rosenbrock_grad_sharded",
     "stochqn_b200_logistic_work_size", "stochqn_b200_logistic_grad", "stochqn_b200_logistic_hess_vec",
     "stochqn_b200_logistic_loss", "stochqn_b200_export", "stochqn_b200_import",
 )
@@ -32,6 +33,7 @@ OPT_PROFILE = 3
 OPT_SYNC_RETURN = 4
 STAT_K1_MS, STAT_K1_COUNT, STAT_K3_MS, STAT_K3_COUNT, STAT_K4_MS, STAT_K4_COUNT, STAT_LAST_BOUND = 1, 2, 3, 4, 5, 6, 7
 STAT_EXACT_NORM_STEPS = 8
+STAT_KA2_MS, STAT_KA2_COUNT = 9, 10
 
 
 def lib_path(dtype) -> str:
@@ -78,6 +80,7 @@ def load(dtype=np.float64) -> StochqnABI:
     lib.stochqn_b200_rosenbrock_grad.argtypes = [vp, vp, ll, ll, ll, vp, vp]
     lib.stochqn_b200_rosenbrock_fun.argtypes = [vp, ll, ll, ll, vp, vp, vp]
     lib.stochqn_b200_rosenbrock_halo.argtypes = [vp, ll, ci, ci, vp, vp, vp, vp]
+    lib.stochqn_b200_rosenbrock_grad_sharded.argtypes = [vp, vp, ll, ll, ll, ci, ci, vp, vp, vp, vp]
     lib.stochqn_b200_logistic_work_size.argtypes = [ll, ll]
     lib.stochqn_b200_logistic_work_size.restype = sz
     lib.stochqn_b200_logistic_grad.argtypes = [vp, ll, vp, vp, ll, ll, vp, real, vp, vp, vp]

@@ -5,12 +5,17 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <math.h>
 #include <atomic>
 
 #include "stochqn.h"
 #include "stochqn_b200.h"
 #include "vecio.cuh"
+#include "p2p.cuh"
+
+// stochqn_b200.cu: PeerArgs of the next exchange on a communicator (world = 0 when the exchange must go through NCCL)
+sqn::PeerArgs stochqn_b200_internal_next_exchange(void* comm, size_t count, int** error_flag);
 
 // kernels launched by the callbacks; added to stochqn_b200_launch_count() by stochqn_b200.cu
 std::atomic<unsigned long long> stochqn_b200_cb_launches{0};
@@ -60,36 +65,95 @@ __device__ __forceinline__ double rosen_g(double xm, double xc, double xp, bool 
     return out;
 }
 
-// One 16-byte chunk per thread and iteration: the chunk is loaded as a vector, the two neighbours as
-// scalars (they are the edge elements of the adjacent threads' chunks: L1 hits), the result stored as a vector.
-template <int VEC>
+// One 16-byte chunk per thread and iteration: the chunk is loaded as a vector; its two neighbours are the edge
+// elements of the adjacent lanes' chunks and arrive by warp shuffle (only lanes 0 and 31 load a scalar), the
+// result is stored as a vector.
+// SHARDED: the halo exchange is fused into this kernel.  The chunks that touch the ends of the shard are left out
+// of the streaming loop; CTA 0 exchanges (first, last) of every rank over the peer-memory mailboxes (p2p.cuh)
+// while the other CTAs stream, then computes those few edge elements.
+template <int VEC, bool SHARDED, int U, bool SHUFFLE>
 __global__ void __launch_bounds__(kT)
 rosen_grad_kernel(const real_t* __restrict__ x, real_t* __restrict__ g, long long n, long long offset,
-                  long long n_global, const real_t* __restrict__ halo)
+                  long long n_global, const real_t* __restrict__ halo, sqn::PeerArgs pa, int* __restrict__ error_flag)
 {
     const long long nchunks = n / VEC;
     const long long stride = (long long) gridDim.x * blockDim.x;
-    for (long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += stride) {
-        const long long i0 = c * VEC;
-        sqn::Pack<real_t, VEC> xv = sqn::ld_stream<real_t, VEC>(x + i0), gv;
-        double v[VEC + 2];
-        v[0] = (i0 > 0) ? (double) __ldg(x + i0 - 1) : (offset > 0 ? (double) halo[0] : 0.0);
+    const int lane = threadIdx.x & 31;
+    for (long long base = (long long) blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < nchunks; base += U * stride) {   // warp-uniform
+        sqn::Pack<real_t, VEC> xv[U];
+        double le[U], re[U];
+        bool valid[U];
+        // all loads of the iteration first: the vector chunk, and for the two end lanes of the warp the scalar neighbour
         #pragma unroll
-        for (int e = 0; e < VEC; ++e) v[e + 1] = (double) xv.get(e);
-        v[VEC + 1] = (i0 + VEC < n) ? (double) __ldg(x + i0 + VEC) : (offset + n < n_global ? (double) halo[1] : 0.0);
-        #pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-            const long long gi = i0 + e + offset;
-            gv.set(e, (real_t) rosen_g(v[e], v[e + 1], v[e + 2], gi > 0, gi < n_global - 1));
+        for (int u = 0; u < U; ++u) {
+            const long long c = base + u * stride + lane;
+            const long long i0 = c * VEC;
+            valid[u] = c < nchunks;
+            le[u] = 0.0; re[u] = 0.0;
+            if (valid[u]) {
+                xv[u] = sqn::ld_stream<real_t, VEC>(x + i0);
+                if (!SHUFFLE || lane == 0) le[u] = (i0 > 0) ? (double) __ldg(x + i0 - 1) : ((halo && offset > 0) ? (double) halo[0] : 0.0);
+                if (!SHUFFLE || lane == 31 || c == nchunks - 1)
+                    re[u] = (i0 + VEC < n) ? (double) __ldg(x + i0 + VEC) : ((halo && offset + n < n_global) ? (double) halo[1] : 0.0);
+            } else {
+                #pragma unroll
+                for (int e = 0; e < VEC; ++e) xv[u].set(e, (real_t) 0);
+            }
         }
-        sqn::st_vec<real_t, VEC>(g + i0, gv);
+        #pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long c = base + u * stride + lane;
+            const long long i0 = c * VEC;
+            double v[VEC + 2];
+            #pragma unroll
+            for (int e = 0; e < VEC; ++e) v[e + 1] = (double) xv[u].get(e);
+            if (SHUFFLE) {
+                v[0] = __shfl_up_sync(0xffffffffu, v[VEC], 1);
+                v[VEC + 1] = __shfl_down_sync(0xffffffffu, v[1], 1);
+            }
+            if (!valid[u]) continue;
+            if (SHARDED && (c == 0 || c == nchunks - 1)) continue;          // shard ends: CTA 0, after the exchange
+            if (!SHUFFLE || lane == 0) v[0] = le[u];
+            if (!SHUFFLE || lane == 31 || c == nchunks - 1) v[VEC + 1] = re[u];
+            sqn::Pack<real_t, VEC> gv;
+            #pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const long long gi = i0 + e + offset;
+                gv.set(e, (real_t) rosen_g(v[e], v[e + 1], v[e + 2], gi > 0, gi < n_global - 1));
+            }
+            sqn::st_vec<real_t, VEC>(g + i0, gv);
+        }
     }
-    if (VEC > 1 && blockIdx.x == 0) {                  // scalar tail
-        const long long i = nchunks * VEC + threadIdx.x;
-        if (i < n) {
+    if (blockIdx.x != 0) return;
+    if (!SHARDED) {
+        if (VEC > 1) {                                  // scalar tail
+            const long long i = nchunks * VEC + threadIdx.x;
+            if (i < n) {
+                const long long gi = i + offset;
+                const double xm = (i > 0) ? (double) x[i - 1] : ((halo && offset > 0) ? (double) halo[0] : 0.0);
+                const double xp = (i < n - 1) ? (double) x[i + 1] : ((halo && offset + n < n_global) ? (double) halo[1] : 0.0);
+                g[i] = (real_t) rosen_g(xm, (double) x[i], xp, gi > 0, gi < n_global - 1);
+            }
+        }
+        return;
+    }
+    // ---- sharded: exchange (first, last) of every rank, then the edge elements ----
+    __shared__ double rec[2 * sqn::kMaxWorld];
+    const int t = threadIdx.x;
+    if (t < 2 * pa.world) rec[t] = (t == 2 * pa.rank) ? (double) x[0] : (t == 2 * pa.rank + 1) ? (double) x[n - 1] : 0.0;
+    if (!sqn::p2p_allreduce_cta(pa, rec, 2 * pa.world) && t == 0 && error_flag) *error_flag = 1;
+    const double hl = pa.rank > 0 ? rec[2 * (pa.rank - 1) + 1] : 0.0;
+    const double hr = pa.rank < pa.world - 1 ? rec[2 * (pa.rank + 1)] : 0.0;
+    const long long a_end = n < VEC ? n : VEC;                           // [0, a_end): first chunk
+    long long b_lo = (nchunks - 1) * VEC;                                // [b_lo, n): last chunk + scalar tail
+    if (b_lo < a_end) b_lo = a_end;
+    for (int pass = 0; pass < 2; ++pass) {
+        const long long i = pass == 0 ? (long long) t : b_lo + t;
+        const long long hi = pass == 0 ? a_end : n;
+        if (i < hi) {
             const long long gi = i + offset;
-            const double xm = (i > 0) ? (double) x[i - 1] : (offset > 0 ? (double) halo[0] : 0.0);
-            const double xp = (i < n - 1) ? (double) x[i + 1] : (offset + n < n_global ? (double) halo[1] : 0.0);
+            const double xm = (i > 0) ? (double) x[i - 1] : hl;
+            const double xp = (i < n - 1) ? (double) x[i + 1] : hr;
             g[i] = (real_t) rosen_g(xm, (double) x[i], xp, gi > 0, gi < n_global - 1);
         }
     }
@@ -148,7 +212,8 @@ rosen_fun_kernel(const real_t* __restrict__ x, long long n, long long offset, lo
     }
 }
 
-// ---- binary logistic regression (first version: two sweeps of the batch) ---------------------------
+// ---- binary logistic regression: loss, and the two-sweep gradient / Hessian-vector form kept for very wide
+// ---- matrices (ncols > 5120); the fused one-sweep kernel is further down ------------------------------------
 // pass A: one warp per row: z = x_row'w (and t = x_row'v), r_row written to scratch
 //         grad: r = (sigmoid(z) - y) * sw          hess_vec: r = p(1-p) * sw * t        loss: per-row loss * sw
 // pass B: one thread per column: out[col] = sum_rows r_row X[row][col] / sum(sw) + 2*lambda*u[col]
@@ -247,12 +312,204 @@ __global__ void logistic_loss_finish_kernel(const double* __restrict__ r, long l
     }
 }
 
+// ---- fused gradient / Hessian-vector kernel: ONE sweep of the batch --------------------------------------------
+// The first version above reads the batch twice (row pass for z = Xw, column pass for X'r).  Here a 256-thread CTA
+// owns a strided set of rows and keeps, spread over its threads' registers, a full-width fp64 column accumulator
+// (thread t owns columns t, t+256, ...: CPT of them).  Per iteration it loads R whole rows (thread t its CPT columns
+// of each: coalesced 8/4-byte loads, all issued before the first use), reduces the R dot products x_i'w (and x_i'v)
+// across the CTA (warp shuffles + one barrier, double-buffered), turns them into the row weights r_i and adds
+// r_i * x_i into the accumulator from the registers that still hold the row - X is read from HBM exactly once.
+// CTA partial columns (+ the CTA's sum of sample weights) go to `colpart`; logistic_fused_finish adds them in CTA
+// order (deterministic), divides by sum(sw) and adds 2*lambda*u   (R/logistic.R:12-21, 23-37).
+constexpr int LT = 256;
+__host__ __device__ constexpr int lg_rows(int cpt) { return cpt <= 4 ? 8 : cpt <= 8 ? 4 : 2; }
+constexpr int kLgMaxGrid = 320;          // CTA partial records (two CTAs per SM)
+constexpr int kLgMaxCpt = 20;            // columns per thread held in registers: ncols <= 5120 takes the fused path
+
+// products and the per-thread partial sums run in the storage type (fp64 for the double build - the reference's R
+// arithmetic; fp32 FMA for the float build, where an F2F conversion per element would be the bottleneck); everything
+// that crosses threads or rows of different CTAs is fp64.
+template <int CPT, int KIND, int R, int MINB>
+__global__ void __launch_bounds__(LT, MINB)
+logistic_fused_kernel(const real_t* __restrict__ X, long long ldx, const real_t* __restrict__ y,
+                      const real_t* __restrict__ sw, long long nrows, long long ncols,
+                      const real_t* __restrict__ w, const real_t* __restrict__ v, double* __restrict__ colpart)
+{
+    extern __shared__ __align__(16) unsigned char lg_smem[];
+    real_t* ws = reinterpret_cast<real_t*>(lg_smem);              // w (and v) staged once per CTA: [CPT*LT] each
+    real_t* vs = ws + CPT * LT;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    real_t acc[CPT];
+    #pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const long long c = tid + (long long) k * LT;
+        ws[tid + k * LT] = c < ncols ? w[c] : (real_t) 0;
+        if (KIND == LG_HVP) vs[tid + k * LT] = c < ncols ? v[c] : (real_t) 0;
+        acc[k] = (real_t) 0;
+    }
+    double sw_sum = 0.0;
+    __shared__ double red[2][2][LT / 32][R];
+    int par = 0;
+    // (each thread reads back only the w / v entries it wrote itself: no barrier needed before the loop)
+    for (long long row0 = (long long) blockIdx.x * R; row0 < nrows; row0 += (long long) gridDim.x * R) {
+        real_t xv[R][CPT];
+        #pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const long long row = row0 + r;
+            const real_t* xr = X + row * ldx;
+            #pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                const long long c = tid + (long long) k * LT;
+                xv[r][k] = (row < nrows && c < ncols) ? __ldg(xr + c) : (real_t) 0;
+            }
+        }
+        real_t zp[R], tp[R];
+        #pragma unroll
+        for (int r = 0; r < R; ++r) { zp[r] = (real_t) 0; tp[r] = (real_t) 0; }
+        #pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            const real_t wk = ws[tid + k * LT];
+            real_t vk = (real_t) 0;
+            if (KIND == LG_HVP) vk = vs[tid + k * LT];
+            #pragma unroll
+            for (int r = 0; r < R; ++r) {
+                zp[r] = fma(xv[r][k], wk, zp[r]);
+                if (KIND == LG_HVP) tp[r] = fma(xv[r][k], vk, tp[r]);
+            }
+        }
+        #pragma unroll
+        for (int r = 0; r < R; ++r) {
+            double z = (double) zp[r], t = (double) tp[r];
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                z += __shfl_down_sync(0xffffffffu, z, o);
+                if (KIND == LG_HVP) t += __shfl_down_sync(0xffffffffu, t, o);
+            }
+            if (lane == 0) { red[par][0][warp][r] = z; if (KIND == LG_HVP) red[par][1][warp][r] = t; }
+        }
+        __syncthreads();
+        #pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const long long row = row0 + r;
+            double z = 0, t = 0;
+            #pragma unroll
+            for (int q = 0; q < LT / 32; ++q) { z += red[par][0][q][r]; if (KIND == LG_HVP) t += red[par][1][q][r]; }
+            double rr = 0.0;
+            if (row < nrows) {
+                const double p = 1.0 / (1.0 + exp(-z));
+                const double wt = sw ? (double) sw[row] : 1.0;
+                rr = (KIND == LG_GRAD) ? (p - (double) y[row]) * wt : p * (1.0 - p) * wt * t;
+                if (tid == 0) sw_sum += wt;
+            }
+            const real_t rt = (real_t) rr;
+            #pragma unroll
+            for (int k = 0; k < CPT; ++k) acc[k] = fma(rt, xv[r][k], acc[k]);
+        }
+        par ^= 1;
+    }
+    double* out = colpart + (size_t) blockIdx.x * (size_t) (ncols + 1);
+    #pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const long long c = tid + (long long) k * LT;
+        if (c < ncols) out[c] = (double) acc[k];
+    }
+    if (tid == 0) out[ncols] = sw_sum;
+}
+
+__global__ void __launch_bounds__(kT)
+logistic_fused_finish(const double* __restrict__ colpart, int nparts, long long ncols, const real_t* __restrict__ u,
+                      real_t lambda, real_t* __restrict__ out)
+{
+    const long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    double acc = 0, swt = 0;
+    for (int b = 0; b < nparts; ++b) {
+        acc += colpart[(size_t) b * (size_t) (ncols + 1) + c];
+        swt += colpart[(size_t) b * (size_t) (ncols + 1) + ncols];
+    }
+    out[c] = (real_t) (acc / swt + 2.0 * (double) lambda * (double) u[c]);
+}
+
+template <int C, int KIND, int R, int MINB>
+void launch_logistic_fused_t(const real_t* X, long long ldx, const real_t* y, const real_t* sw, long long nrows, long long ncols,
+                             const real_t* w, const real_t* v, double* colpart, int* nparts, int sms, cudaStream_t st)
+{
+    auto kern = logistic_fused_kernel<C, KIND, R, MINB>;
+    const size_t smem = (size_t) (KIND == LG_HVP ? 2 : 1) * C * LT * sizeof(real_t);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); attr_set = true; }
+    long long g = (nrows + R - 1) / R;
+    const int cap = MINB * sms < kLgMaxGrid ? MINB * sms : kLgMaxGrid;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    kern<<<(unsigned) g, LT, smem, st>>>(X, ldx, y, sw, nrows, ncols, w, v, colpart);
+    *nparts = (int) g;
+}
+
+template <int KIND>
+bool launch_logistic_fused(const real_t* X, long long ldx, const real_t* y, const real_t* sw, long long nrows, long long ncols,
+                           const real_t* w, const real_t* v, double* colpart, int* nparts, cudaStream_t st)
+{
+    const int cpt = (int) ((ncols + LT - 1) / LT);
+    if (cpt > kLgMaxCpt) return false;
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms < 1) sms = 148; }
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("STOCHQN_B200_LG_VARIANT"); variant = e ? atoi(e) : 0; }
+#define LG_ARGS X, ldx, y, sw, nrows, ncols, w, v, colpart, nparts, sms, st
+#define LG_CASE(C) if (cpt <= C) { launch_logistic_fused_t<C, KIND, lg_rows(C), 2>(LG_ARGS); return true; }
+    // wide rows (measured on B200, tools/probe_logistic.py, STOCHQN_B200_LG_VARIANT is a dev switch):
+    //   fp64, big batches : two CTAs per SM with 2 rows in flight each (6.0 TB/s at 50000 x 4097; a few spilled bytes)
+    //   fp64, small batches: one CTA per SM with 4 rows in flight (fewer partial records to add up: 38 vs 49 us at 2000 x 4097)
+    //   fp32              : two CTAs per SM, 4 rows in flight each (4-byte loads need more of them in flight)
+#define LG_WIDE(C)                                                                                   \
+    if (cpt <= C) {                                                                                  \
+        if constexpr (sizeof(real_t) == 4) launch_logistic_fused_t<C, KIND, 4, 2>(LG_ARGS);          \
+        else if (variant == 1 || (variant == 0 && nrows >= 8192)) launch_logistic_fused_t<C, KIND, 2, 2>(LG_ARGS); \
+        else launch_logistic_fused_t<C, KIND, 4, 1>(LG_ARGS);                                        \
+        return true;                                                                                 \
+    }
+    LG_CASE(1) LG_CASE(2) LG_CASE(4) LG_CASE(8) LG_CASE(12) LG_WIDE(16) LG_WIDE(17) LG_WIDE(20)
+#undef LG_CASE
+#undef LG_WIDE
+#undef LG_ARGS
+    return false;
+}
+
 int row_slices(long long nrows)
 {
     long long s = nrows / 64;
     if (s < 1) s = 1;
     if (s > 64) s = 64;
     return (int) s;
+}
+
+template <bool SHARDED, int U, bool SHUFFLE>
+static void launch_rosen_grad(const real_t* x, real_t* grad, long long n_local, long long offset, long long n_global,
+                              const real_t* halo, const sqn::PeerArgs& pa, int* err, cudaStream_t st)
+{
+    constexpr int V = 16 / sizeof(real_t);
+    if (((((uintptr_t) x) | ((uintptr_t) grad)) & 15u) == 0)
+        rosen_grad_kernel<V, SHARDED, U, SHUFFLE><<<grid_1d(n_local / V), kT, 0, st>>>(x, grad, n_local, offset, n_global, halo, pa, err);
+    else
+        rosen_grad_kernel<1, SHARDED, U, SHUFFLE><<<grid_1d(n_local), kT, 0, st>>>(x, grad, n_local, offset, n_global, halo, pa, err);
+}
+
+template <bool SHARDED>
+static void launch_rosen_grad_variant(const real_t* x, real_t* grad, long long n_local, long long offset, long long n_global,
+                                      const real_t* halo, const sqn::PeerArgs& pa, int* err, cudaStream_t st)
+{
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("STOCHQN_B200_ROSEN_VARIANT"); variant = e ? atoi(e) : 0; }
+    // measured on B200, n = 2^27 fp64 (STOCHQN_B200_ROSEN_VARIANT, dev switch): neighbours by L1-hitting scalar loads
+    // with two chunks in flight 0.367 ms (5.85 TB/s); one chunk 0.445 ms; neighbours by warp shuffle 0.449-0.462 ms
+    switch (variant) {
+        case 1:  launch_rosen_grad<SHARDED, 1, true>(x, grad, n_local, offset, n_global, halo, pa, err, st); break;
+        case 2:  launch_rosen_grad<SHARDED, 2, true>(x, grad, n_local, offset, n_global, halo, pa, err, st); break;
+        case 3:  launch_rosen_grad<SHARDED, 1, false>(x, grad, n_local, offset, n_global, halo, pa, err, st); break;
+        case 4:  launch_rosen_grad<SHARDED, 4, false>(x, grad, n_local, offset, n_global, halo, pa, err, st); break;
+        default: launch_rosen_grad<SHARDED, 2, false>(x, grad, n_local, offset, n_global, halo, pa, err, st); break;
+    }
 }
 
 }  // namespace
@@ -268,12 +525,24 @@ int stochqn_b200_rosenbrock_x0(real_t* x, long long n_local, long long offset, v
 int stochqn_b200_rosenbrock_grad(const real_t* x, real_t* grad, long long n_local, long long offset,
                                  long long n_global, const real_t* halo, void* stream)
 {
-    constexpr int V = 16 / sizeof(real_t);
-    if (((((uintptr_t) x) | ((uintptr_t) grad)) & 15u) == 0)
-        rosen_grad_kernel<V><<<grid_1d(n_local / V), kT, 0, (cudaStream_t) stream>>>(x, grad, n_local, offset, n_global, halo);
-    else
-        rosen_grad_kernel<1><<<grid_1d(n_local), kT, 0, (cudaStream_t) stream>>>(x, grad, n_local, offset, n_global, halo);
+    sqn::PeerArgs none;
+    launch_rosen_grad_variant<false>(x, grad, n_local, offset, n_global, halo, none, nullptr, (cudaStream_t) stream);
     return check_launch("rosenbrock_grad");
+}
+
+int stochqn_b200_rosenbrock_grad_sharded(const real_t* x, real_t* grad, long long n_local, long long offset,
+                                         long long n_global, int rank, int world_size, void* comm,
+                                         real_t* halo, double* scratch, void* stream)
+{
+    if (world_size <= 1) return stochqn_b200_rosenbrock_grad(x, grad, n_local, offset, n_global, nullptr, stream);
+    int* err = nullptr;
+    sqn::PeerArgs pa = stochqn_b200_internal_next_exchange(comm, (size_t) 2 * world_size, &err);
+    if (pa.world <= 1) {                                 // no peer-memory path: library all-reduce, then the plain kernel
+        if (int r = stochqn_b200_rosenbrock_halo(x, n_local, rank, world_size, comm, halo, scratch, stream)) return r;
+        return stochqn_b200_rosenbrock_grad(x, grad, n_local, offset, n_global, halo, stream);
+    }
+    launch_rosen_grad_variant<true>(x, grad, n_local, offset, n_global, nullptr, pa, err, (cudaStream_t) stream);
+    return check_launch("rosenbrock_grad_sharded");
 }
 
 int stochqn_b200_rosenbrock_fun(const real_t* x, long long n_local, long long offset, long long n_global,
@@ -295,7 +564,9 @@ int stochqn_b200_rosenbrock_halo(const real_t* x, long long n_local, int rank, i
 
 size_t stochqn_b200_logistic_work_size(long long nrows, long long ncols)
 {
-    return sizeof(double) * (size_t) (nrows + 2 + (long long) row_slices(nrows) * ncols);
+    const long long two_sweep = (long long) row_slices(nrows) * ncols;
+    const long long fused = (long long) kLgMaxGrid * (ncols + 1);
+    return sizeof(double) * (size_t) (nrows + 2 + (two_sweep > fused ? two_sweep : fused));
 }
 
 static int logistic_common(int kind, const real_t* X, long long ldx, const real_t* y, const real_t* sw,
@@ -304,6 +575,15 @@ static int logistic_common(int kind, const real_t* X, long long ldx, const real_
 {
     double* r = (double*) work;
     double* colpart = r + nrows + 2;
+    if (kind != LG_LOSS && !getenv("STOCHQN_B200_LOGISTIC_TWO_SWEEP")) {      // one sweep of the batch (ncols <= 5120)
+        int nparts = 0;
+        const bool done = kind == LG_GRAD ? launch_logistic_fused<LG_GRAD>(X, ldx, y, sw, nrows, ncols, w, v, colpart, &nparts, st)
+                                          : launch_logistic_fused<LG_HVP>(X, ldx, y, sw, nrows, ncols, w, v, colpart, &nparts, st);
+        if (done) {
+            logistic_fused_finish<<<(unsigned) ((ncols + kT - 1) / kT), kT, 0, st>>>(colpart, nparts, ncols, kind == LG_HVP ? v : w, lambda, out);
+            return check_launch("logistic (fused)", 2);
+        }
+    }
     const int g_rows = grid_1d(nrows * 32);
     if (kind == LG_GRAD) logistic_rows_kernel<LG_GRAD><<<g_rows, kT, 0, st>>>(X, ldx, y, sw, nrows, ncols, w, v, r);
     else if (kind == LG_HVP) logistic_rows_kernel<LG_HVP><<<g_rows, kT, 0, st>>>(X, ldx, y, sw, nrows, ncols, w, v, r);

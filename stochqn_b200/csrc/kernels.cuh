@@ -672,333 +672,6 @@ k_avg(T* __restrict__ x_sum, T* __restrict__ other, T* __restrict__ s_slot, T in
 
 
 // =========================================================================================
-// adaQN kernels.
-//
-// The reference's take_step for adaQN (stochqn.c:808-822 with 720-783) first updates the
-// AdaGrad / RMSProp accumulator G, then
-//   no pairs : d = g / sqrt(G + eps)
-//   pairs    : "H0" = h = g / sqrt(G + eps) (the RESCALED GRADIENT, quirk Q2) and the two-loop
-//              multiplies by it elementwise, i.e. H0 = diag(h).
-// Compact form with a diagonal H0 = diag(h):   p = S'g,  q = Y'(h.g),  W = Y' diag(h) Y,
-//   u = R^-1 p ; b = -u ; a = R^-T [ (D + W) u - q ] ;  d = h.(g + Y b) + S a
-// h depends on the current gradient, so q and W are recomputed every step.
-// =========================================================================================
-
-template <typename T>
-__device__ __forceinline__ T ada_accumulate(T g, T G, T w_old, T w_new, bool rms)
-{
-    // stochqn.c:738 / 745
-    return rms ? (w_old * G + w_new * (g * g)) : (G + g * g);
-}
-
-// KA1: one pass over g, G (+ S, Y rows j0..): updates G (and the Fisher ring row) when j0 == 0,
-// accumulates  k=0: s_j'g   k=1: y_j'(h.g)   k=2: s_j'y_c (pending)   then scalars.
-// record layout (m = mem_size): [0,m) p  [m,2m) q  [2m,3m) s_j'y_c  [3m] sum (h g)^2 (pairs) or sum h^2 (no pairs)
-//                               [3m+1] sum h^2   [3m+2] s_c's_c   [3m+3] y_c'y_c   [3m+4 ...) W (m x m, row-major, upper filled)
-template <typename T, int MMAX, bool PENDING, int VEC>
-__global__ void __launch_bounds__(kThreads)
-ka1_dots(const T* __restrict__ g, T* __restrict__ G, const T* __restrict__ S, const T* __restrict__ Y, size_t ld,
-         int msize, int used, int j0, const T* __restrict__ sc_row, const T* __restrict__ yc_row, long long n,
-         T* __restrict__ fisher_row, T scal_reg, T rmsprop_weight, double* __restrict__ partials)
-{
-    S += (size_t) j0 * ld;
-    Y += (size_t) j0 * ld;
-    const int used_all = used;
-    used -= j0;
-    const bool first = (j0 == 0);
-    const bool rms = (rmsprop_weight > (T) 0 && rmsprop_weight < (T) 1);
-    const T w_new = (T) 1 - rmsprop_weight;
-    double a_p[MMAX], a_q[MMAX], a_sy[MMAX];
-    double a_hg = 0, a_hh = 0, a_ss = 0, a_yy = 0;
-    #pragma unroll
-    for (int j = 0; j < MMAX; ++j) { a_p[j] = 0; a_q[j] = 0; a_sy[j] = 0; }
-
-    auto one = [&](size_t off, auto vtag) {
-        constexpr int V = decltype(vtag)::value;
-        Pack<T, V> gv = ld_stream<T, V>(g + off);
-        Pack<T, V> Gv = ld_rw<T, V>(G + off);
-        Pack<T, V> hv;
-        if (first) {
-            #pragma unroll
-            for (int e = 0; e < V; ++e) Gv.set(e, ada_accumulate<T>(gv.get(e), Gv.get(e), rmsprop_weight, w_new, rms));
-            st_vec<T, V>(G + off, Gv);
-            if (fisher_row) st_vec<T, V>(fisher_row + off, gv);
-        }
-        #pragma unroll
-        for (int e = 0; e < V; ++e) hv.set(e, gv.get(e) / sqrt(Gv.get(e) + scal_reg));     // stochqn.c:778 / 781
-        Pack<T, V> yc, sc;
-        if constexpr (PENDING) { yc = ld_stream<T, V>(yc_row + off); sc = ld_stream<T, V>(sc_row + off); }
-        if (first) {
-            #pragma unroll
-            for (int e = 0; e < V; ++e) {
-                double he = (double) hv.get(e), ge = (double) gv.get(e);
-                a_hh = fma(he, he, a_hh);
-                if (used_all > 0) { double t = he * ge; a_hg = fma(t, t, a_hg); }
-                if constexpr (PENDING) {
-                    double se = (double) sc.get(e), ye = (double) yc.get(e);
-                    a_ss = fma(se, se, a_ss);
-                    a_yy = fma(ye, ye, a_yy);
-                }
-            }
-        }
-        #pragma unroll
-        for (int j = 0; j < MMAX; ++j) {
-            if (j < used) {
-                Pack<T, V> sv = ld_stream<T, V>(S + (size_t) j * ld + off);
-                Pack<T, V> yv = ld_stream<T, V>(Y + (size_t) j * ld + off);
-                #pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    double ge = (double) gv.get(e), he = (double) hv.get(e);
-                    double se = (double) sv.get(e), ye = (double) yv.get(e);
-                    a_p[j] = fma(se, ge, a_p[j]);
-                    a_q[j] = fma(ye, he * ge, a_q[j]);
-                    if constexpr (PENDING) a_sy[j] = fma(se, (double) yc.get(e), a_sy[j]);
-                }
-            }
-        }
-    };
-    const long long nchunks = n / VEC;
-    const long long stride = (long long) gridDim.x * kThreads;
-    for (long long c = (long long) blockIdx.x * kThreads + threadIdx.x; c < nchunks; c += stride)
-        one((size_t) c * VEC, std::integral_constant<int, VEC>{});
-    if (VEC > 1 && blockIdx.x == 0) {
-        const long long i = nchunks * VEC + threadIdx.x;
-        if (i < n) one((size_t) i, std::integral_constant<int, 1>{});
-    }
-    const int P = 3 * msize + 4 + msize * msize;
-    double* out = partials + (size_t) blockIdx.x * P;
-    block_reduce<3 * MMAX + 4>(3 * MMAX + 4,
-        [&](int p) -> double {
-            if (p < MMAX) return a_p[p < MMAX ? p : 0];
-            if (p < 2 * MMAX) return a_q[(p - MMAX) < MMAX ? (p - MMAX) : 0];
-            if (p < 3 * MMAX) return a_sy[(p - 2 * MMAX) < MMAX ? (p - 2 * MMAX) : 0];
-            const int r = p - 3 * MMAX;
-            return r == 0 ? (used_all > 0 ? a_hg : a_hh) : r == 1 ? a_hh : r == 2 ? a_ss : a_yy;
-        },
-        [&](int p, double v) {
-            if (p >= 3 * MMAX) { if (first) out[3 * msize + (p - 3 * MMAX)] = v; return; }
-            const int k = p / MMAX, j = p % MMAX;
-            if (j0 + j < msize) out[k * msize + j0 + j] = (j < used) ? v : 0.0;
-        });
-}
-
-// KA2: one block (JB x KB) of the weighted Gram matrix W[j][k] = sum_i y_j[i] h[i] y_k[i],
-// rows j in [ja, ja+JB), k in [ka, ka+KB), restricted to j <= k entries being meaningful.
-// Reads g and the ALREADY UPDATED G to rebuild h.  Writes into the same partial record as KA1.
-template <typename T, int JB, int KB, int VEC>
-__global__ void __launch_bounds__(kThreads)
-ka2_wgram(const T* __restrict__ g, const T* __restrict__ G, const T* __restrict__ Y, size_t ld,
-          int msize, int used, int ja, int ka, long long n, T scal_reg, double* __restrict__ partials)
-{
-    double acc[JB][KB];
-    #pragma unroll
-    for (int j = 0; j < JB; ++j)
-        #pragma unroll
-        for (int k = 0; k < KB; ++k) acc[j][k] = 0;
-    auto one = [&](size_t off, auto vtag) {
-        constexpr int V = decltype(vtag)::value;
-        Pack<T, V> gv = ld_stream<T, V>(g + off), Gv = ld_stream<T, V>(G + off);
-        double h[V];
-        #pragma unroll
-        for (int e = 0; e < V; ++e) h[e] = (double) (gv.get(e) / sqrt(Gv.get(e) + scal_reg));
-        Pack<T, V> yk[KB];
-        #pragma unroll
-        for (int k = 0; k < KB; ++k) if (ka + k < used) yk[k] = ld_stream<T, V>(Y + (size_t) (ka + k) * ld + off);
-        #pragma unroll
-        for (int j = 0; j < JB; ++j) {
-            if (ja + j < used) {
-                Pack<T, V> yj = ld_stream<T, V>(Y + (size_t) (ja + j) * ld + off);
-                #pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    double t = (double) yj.get(e) * h[e];
-                    #pragma unroll
-                    for (int k = 0; k < KB; ++k) if (ka + k < used) acc[j][k] = fma(t, (double) yk[k].get(e), acc[j][k]);
-                }
-            }
-        }
-    };
-    const long long nchunks = n / VEC;
-    const long long stride = (long long) gridDim.x * kThreads;
-    for (long long c = (long long) blockIdx.x * kThreads + threadIdx.x; c < nchunks; c += stride)
-        one((size_t) c * VEC, std::integral_constant<int, VEC>{});
-    if (VEC > 1 && blockIdx.x == 0) {
-        const long long i = nchunks * VEC + threadIdx.x;
-        if (i < n) one((size_t) i, std::integral_constant<int, 1>{});
-    }
-    const int P = 3 * msize + 4 + msize * msize;
-    double* out = partials + (size_t) blockIdx.x * P + 3 * msize + 4;
-    block_reduce<JB * KB>(JB * KB,
-        [&](int p) -> double { return acc[(p / KB) < JB ? (p / KB) : 0][p % KB]; },
-        [&](int p, double v) {
-            const int j = ja + p / KB, k = ka + p % KB;
-            if (j < msize && k < msize) out[j * msize + k] = (j < used && k < used) ? v : 0.0;
-        });
-}
-
-// KA-solve: adaQN flavour of K2 (same Gram bookkeeping, diagonal-H0 algebra).
-// coef layout: [0,m) a, [m,2m) b (NOT scaled), [2m] unused, [2m+1] U, [2m+2] first scalar of the record.
-__global__ void __launch_bounds__(kThreads)
-ka_solve(SolveArgs A, PeerArgs pa, const double* __restrict__ partials, double* sums,
-         double* __restrict__ SY, double* __restrict__ YY, double* __restrict__ SS,
-         double* __restrict__ coef, int* __restrict__ status_dev, volatile int* status_host,
-         volatile double* info_host, volatile unsigned long long* seq_host)
-{
-    const int m = A.msize, used = A.used;
-    const int P = 3 * m + 4 + m * m;
-    if (A.nblocks > 0) { reduce_partials(partials, A.nblocks, P, sums); __syncthreads(); }
-    bool comm_ok = true;
-    if (pa.world > 1) comm_ok = p2p_allreduce_cta(pa, sums, P);
-    if (!A.do_solve) return;
-    auto ph = [&](int i) { int s = A.oldest + i; return s >= m ? s - m : s; };
-    if (A.pend >= 0) {
-        const int c = A.pend;
-        for (int j = threadIdx.x; j < used; j += kThreads) SY[j * m + c] = sums[2 * m + j];
-        if (threadIdx.x == 0) { SS[c] = sums[3 * m + 2]; YY[c * m + c] = sums[3 * m + 3]; }
-        __syncthreads();
-    }
-    __shared__ double Rm[kMaxMem][kMaxMem + 1], Wl[kMaxMem][kMaxMem + 1];
-    __shared__ double pv[kMaxMem], qv[kMaxMem], ssv[kMaxMem], yyv[kMaxMem], u[kMaxMem], w[kMaxMem], av[kMaxMem];
-    const double* W = sums + 3 * m + 4;          // upper triangle (physical indices) is filled by KA2
-    for (int t = threadIdx.x; t < used * used; t += kThreads) {
-        const int i = t / used, j = t % used;
-        const int a = ph(i), b = ph(j);
-        Rm[i][j] = SY[a * m + b];
-        Wl[i][j] = a <= b ? W[a * m + b] : W[b * m + a];
-    }
-    for (int i = threadIdx.x; i < used; i += kThreads) {
-        pv[i] = sums[ph(i)]; qv[i] = sums[m + ph(i)]; ssv[i] = SS[ph(i)]; yyv[i] = YY[ph(i) * m + ph(i)];
-    }
-    for (int j = threadIdx.x; j < 2 * m; j += kThreads) coef[j] = 0.0;
-    __syncthreads();
-    if (threadIdx.x != 0) return;
-
-    const double n0 = sums[3 * m];            // sum (h g)^2 with pairs, sum h^2 without
-    const double hh = sums[3 * m + 1];
-    double U = sqrt(n0);
-    bool ok = finite_d(n0);
-    if (used > 0) {
-        for (int i = used - 1; i >= 0; --i) {
-            double t = pv[i];
-            for (int j = i + 1; j < used; ++j) t -= Rm[i][j] * u[j];
-            u[i] = t / Rm[i][i];
-        }
-        for (int i = 0; i < used; ++i) {
-            double t = 0;
-            for (int j = 0; j < used; ++j) t += Wl[i][j] * u[j];
-            w[i] = Rm[i][i] * u[i] + t - qv[i];
-        }
-        for (int i = 0; i < used; ++i) {
-            double t = w[i];
-            for (int j = 0; j < i; ++j) t -= Rm[j][i] * av[j];
-            av[i] = t / Rm[i][i];
-        }
-        const double hnorm = sqrt(hh);
-        for (int i = 0; i < used; ++i) {
-            const int s = ph(i);
-            const double a = av[i], b = -u[i];
-            coef[s] = a;
-            coef[m + s] = b;
-            U += fabs(a) * sqrt(ssv[i]) + hnorm * fabs(b) * sqrt(yyv[i]);
-            ok = ok && finite_d(a) && finite_d(b);
-        }
-        ok = ok && finite_d(hh);
-    }
-    ok = ok && finite_d(U);
-    coef[2 * m] = 1.0;
-    coef[2 * m + 1] = U;
-    coef[2 * m + 2] = n0;
-    int st = ST_ACCEPT;
-    if (A.check_nan) {
-        if (!ok) st = ST_REJECT_NONFINITE;
-        else if (used == 0) { if (U > A.limit) st = ST_REJECT_NONFINITE; }      // U is the exact norm here
-        else if (!(U <= 0.99 * A.limit)) st = ST_NEED_EXACT_NORM;
-    }
-    if (!comm_ok) st = ST_COMM_TIMEOUT;
-    *status_dev = st;
-    *status_host = st;
-    info_host[0] = U;
-    info_host[1] = 1.0;
-    info_host[2] = n0;
-    publish_seq(seq_host, A.seq);
-}
-
-// KA3: adaQN combine + update:  h = g/sqrt(G+eps) ;  d = (used ? h*(g + sum b_j y_j) + sum a_j s_j : h)
-//      MODE_AVG: x -= step*d ; x_sum += x ; grad <- d      MODE_DIRONLY: grad <- d (+ exact norm partials)
-template <typename T, int MMAX, int MODE, int VEC>
-__global__ void __launch_bounds__(kThreads)
-ka3_combine(const T* g_in, T* grad_out, const T* __restrict__ G, const T* __restrict__ S, const T* __restrict__ Y,
-            size_t ld, int msize, int used, long long n, T* __restrict__ x, T* __restrict__ x_sum, T step,
-            T scal_reg, const double* __restrict__ coef, const int* __restrict__ status_dev, int force,
-            double* __restrict__ partials)
-{
-    if (!force && *status_dev != ST_ACCEPT) return;
-    T ca[MMAX], cb[MMAX];
-    #pragma unroll
-    for (int j = 0; j < MMAX; ++j) {
-        ca[j] = (j < used) ? (T) coef[j] : (T) 0;
-        cb[j] = (j < used) ? (T) coef[msize + j] : (T) 0;
-    }
-    const T nstep = -step;
-    double a_dd = 0, a_bad = 0;
-    auto one = [&](size_t off, auto vtag) {
-        constexpr int V = decltype(vtag)::value;
-        Pack<T, V> gv = ld_rw<T, V>(g_in + off);
-        Pack<T, V> Gv = ld_stream<T, V>(G + off);
-        Pack<T, V> d, t, acc;
-        #pragma unroll
-        for (int e = 0; e < V; ++e) { t.set(e, gv.get(e)); acc.set(e, (T) 0); }
-        #pragma unroll
-        for (int j = 0; j < MMAX; ++j) {
-            if (j < used) {
-                Pack<T, V> sv = ld_stream<T, V>(S + (size_t) j * ld + off);
-                Pack<T, V> yv = ld_stream<T, V>(Y + (size_t) j * ld + off);
-                #pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    t.set(e, fma(cb[j], yv.get(e), t.get(e)));
-                    acc.set(e, fma(ca[j], sv.get(e), acc.get(e)));
-                }
-            }
-        }
-        #pragma unroll
-        for (int e = 0; e < V; ++e) {
-            T h = gv.get(e) / sqrt(Gv.get(e) + scal_reg);
-            d.set(e, used > 0 ? fma(h, t.get(e), acc.get(e)) : h);
-        }
-        if constexpr (MODE == MODE_DIRONLY) {
-            #pragma unroll
-            for (int e = 0; e < V; ++e) {
-                double de = (double) d.get(e);
-                a_dd = fma(de, de, a_dd);
-                if (!isfinite(de)) a_bad += 1.0;
-            }
-            st_vec<T, V>(grad_out + off, d);
-        } else {
-            Pack<T, V> xv = ld_rw<T, V>(x + off);
-            #pragma unroll
-            for (int e = 0; e < V; ++e) xv.set(e, fma(nstep, d.get(e), xv.get(e)));
-            st_vec<T, V>(x + off, xv);
-            Pack<T, V> xs = ld_rw<T, V>(x_sum + off);
-            #pragma unroll
-            for (int e = 0; e < V; ++e) xs.set(e, xs.get(e) + xv.get(e));
-            st_vec<T, V>(x_sum + off, xs);
-            if (grad_out) st_vec<T, V>(grad_out + off, d);
-        }
-    };
-    const long long nchunks = n / VEC;
-    const long long stride = (long long) gridDim.x * kThreads;
-    for (long long c = (long long) blockIdx.x * kThreads + threadIdx.x; c < nchunks; c += stride)
-        one((size_t) c * VEC, std::integral_constant<int, VEC>{});
-    if (VEC > 1 && blockIdx.x == 0) {
-        const long long i = nchunks * VEC + threadIdx.x;
-        if (i < n) one((size_t) i, std::integral_constant<int, 1>{});
-    }
-    if constexpr (MODE == MODE_DIRONLY) {
-        double* out = partials + (size_t) blockIdx.x * 2;
-        block_reduce<2>(2, [&](int p) { return p == 0 ? a_dd : a_bad; }, [&](int p, double v) { out[p] = v; });
-    }
-}
-
-// =========================================================================================
 // Empirical-Fisher product (stochqn.c:936-952):  y = F' (F s) / k  over the first k ring rows.
 //   KF1: t_r = F_r's for rows r0..r0+RB   (record [k], entry r)
 //   KF2: y (+)= sum_r c_r F_r for rows r0..r0+RB, c_r = t_r / k read from device memory
@@ -1076,3 +749,5 @@ kf2_combine(const T* __restrict__ F, size_t ld, int r0, int rows, const double* 
 }
 
 }  // namespace sqn
+
+#include "kernels_adaqn.cuh"

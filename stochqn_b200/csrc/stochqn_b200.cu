@@ -155,10 +155,11 @@ struct Ctx {
     void* pub = nullptr;
     // optional per-kernel timing (STOCHQN_B200_OPT_PROFILE): CUDA events around K1 / K3 / K4 on the stream
     int profile = 0;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    bool ev_armed[3] = {false, false, false};
-    double prof_ms[3] = {0, 0, 0};
-    double prof_n[3] = {0, 0, 0};
+    // kernel classes: 0 = K1 / KA1 (dots), 1 = K3 / KA3 (combine + update), 2 = K4 (pair), 3 = KA2 (adaQN second dots)
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_armed[4] = {false, false, false, false};
+    double prof_ms[4] = {0, 0, 0, 0};
+    double prof_n[4] = {0, 0, 0, 0};
     double last_bound = 0;
     double exact_norm_steps = 0;        // steps that took the two-pass (exact ||d||) route
     unsigned long long seq_want[3] = {0, 0, 0};   // sequence numbers the host is waiting for (HostBlock::seq)
@@ -177,7 +178,7 @@ void prof_begin(Ctx* c, int k) { if (c->profile) { prof_collect_one(c, k); cudaE
 void prof_end(Ctx* c, int k) { if (c->profile) { cudaEventRecord(c->ev[2 * k + 1], c->stream); c->ev_armed[k] = true; } }
 void prof_collect(Ctx* c)
 {
-    for (int k = 0; k < 3; ++k) prof_collect_one(c, k);
+    for (int k = 0; k < 4; ++k) prof_collect_one(c, k);
 }
 
 std::unordered_map<const void*, Ctx*> g_registry;
@@ -422,13 +423,12 @@ int launch_solve(Ctx* c, bool ada, int nblocks, int used, int oldest, int pend, 
     A.check_nan = check_nan; A.h0 = h0; A.limit = step_limit(c);
     A.seq = ++c->seq_want[FLAG_STATUS];
     auto go = [&](const SolveArgs& a, const PeerArgs& pa) {
-        if (ada) ka_solve<<<1, kThreads, 0, c->stream>>>(a, pa, c->partials, c->sums, c->SY, c->YY, c->SS, c->coef,
-                                                         c->status_dev, &c->hb_dev->status, c->hb_dev->info, &c->hb_dev->seq[FLAG_STATUS]);
-        else     k2_solve<<<1, kThreads, 0, c->stream>>>(a, pa, c->partials, c->sums, c->SY, c->YY, c->SS, c->coef,
-                                                         c->status_dev, &c->hb_dev->status, c->hb_dev->info, &c->hb_dev->seq[FLAG_STATUS]);
+        k2_solve<<<1, kThreads, 0, c->stream>>>(a, pa, c->partials, c->sums, c->SY, c->YY, c->SS, c->coef,
+                                                c->status_dev, &c->hb_dev->status, c->hb_dev->info, &c->hb_dev->seq[FLAG_STATUS]);
         COUNT_LAUNCH();
     };
-    const size_t P = ada ? (size_t) (3 * c->msize + 4 + c->msize * c->msize) : (size_t) (4 * c->msize + 2);
+    (void) ada;
+    const size_t P = (size_t) (4 * c->msize + 2);
     const bool sharded = c->comm && c->comm->world > 1;
     PeerArgs pa = sharded ? next_exchange(c->comm, P) : PeerArgs();
     if (sharded && pa.world == 0) {
@@ -515,7 +515,7 @@ void free_ctx(Ctx* c)
     cudaFree(c->dx); cudaFree(c->dg); cudaFree(c->dhv);
     if (c->hreq) cudaFreeHost(c->hreq);
     if (c->hreq_vec) cudaFreeHost(c->hreq_vec);
-    for (int k = 0; k < 6; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+    for (int k = 0; k < 8; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
     delete c;
 }
 
@@ -537,7 +537,7 @@ Ctx* make_ctx(Kind kind, long long n, int msize, int fisher_size)
     const size_t m = (size_t) msize;
     size_t rec = 4 * m + 2;
     if (kind == K_ADAQN) {
-        size_t r2 = 3 * m + 4 + m * m;
+        size_t r2 = (size_t) ka1_record((int) m) + (size_t) ka2_record((int) m);     // both sum records are live at once
         if (r2 > rec) rec = r2;
         if ((size_t) fisher_size > rec) rec = (size_t) fisher_size;
     }

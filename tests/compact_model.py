@@ -2,7 +2,8 @@
 with the same incremental Gram bookkeeping (physical-slot indexing, one column folded per
 accepted pair).  Host-logic test aid: lets the CPU suite check the compact form, the ring
 order and the pending-column protocol against the oracle's two-loop recursion without a GPU.
-Mirrors stochqn_b200/csrc/kernels.cuh (k1_dots / k2_solve / k3_combine / ka1_dots / ka_solve / ka3_combine).
+Mirrors stochqn_b200/csrc/kernels.cuh (k1_dots / k2_solve / k3_combine) and kernels_adaqn.cuh
+(ka1_dots / ka_solve_u / ka2_wdots / ka_solve_a / ka3_combine).
 """
 import numpy as np
 
@@ -60,30 +61,34 @@ class CompactModel:
         return d, U
 
     def direction_diag(self, g, h, S, Y, used, st):
-        """H*g for H0 = diag(h) (adaQN, quirk Q2: h = g / sqrt(G + eps))."""
+        """H*g for H0 = diag(h) (adaQN, quirk Q2: h = g / sqrt(G + eps)).  The weighted Gram matrix
+        W = Y' diag(h) Y is never formed: (W u - Y'(h.g)) = Y' [h . (Y u - g)]  (kernels_adaqn.cuh: KA1 -> KAu ->
+        KA2 -> KAa -> KA3)."""
         self.fold(S, Y, used)
         if used == 0:
             return h.copy(), np.sqrt(h @ h)
         ph = self._order(used, st)
-        p = np.array([S[s] @ g for s in ph])
-        q = np.array([Y[s] @ (h * g) for s in ph])
-        W = np.array([[Y[a] @ (h * Y[b]) for b in ph] for a in ph])
+        p = np.array([S[s] @ g for s in ph])                       # KA1
         R = np.triu(self.SY[np.ix_(ph, ph)])
         with np.errstate(all="ignore"):
-            u = np.zeros(used)
+            u = np.zeros(used)                                     # KAu
             for i in range(used - 1, -1, -1):
                 u[i] = (p[i] - R[i, i + 1:] @ u[i + 1:]) / R[i, i]
-            w = np.diag(R) * u + W @ u - q
+            t = -g.copy()                                          # KA2: t = Y u - g, w = Y'(h.t)
+            for i, s in enumerate(ph):
+                t = t + u[i] * Y[s]
+            ht = h * t
+            w2 = np.array([Y[s] @ ht for s in ph])
+            w = np.diag(R) * u + w2                                # KAa
             a = np.zeros(used)
             for i in range(used):
                 a[i] = (w[i] - R[:i, i] @ a[:i]) / R[i, i]
             b = -u
-            t = g.copy()
+            t3 = g.copy()                                          # KA3
             acc = np.zeros_like(g)
             for i, s in enumerate(ph):
-                t = t + b[i] * Y[s]
+                t3 = t3 + b[i] * Y[s]
                 acc = acc + a[i] * S[s]
-            d = h * t + acc
-            U = np.sqrt((h * g) @ (h * g)) + sum(abs(a[i]) * np.sqrt(self.SS[s]) + np.sqrt(h @ h) * abs(b[i]) * np.sqrt(self.YY[s, s])
-                                                 for i, s in enumerate(ph))
+            d = h * t3 + acc
+            U = np.sqrt(ht @ ht) + sum(abs(a[i]) * np.sqrt(self.SS[s]) for i, s in enumerate(ph))
         return d, U

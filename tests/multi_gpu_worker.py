@@ -64,8 +64,12 @@ def main():
     call()
     for _ in range(calls - 1):
         assert task.value in (101, 102, 103), task.value
-        lib.stochqn_b200_rosenbrock_halo(req.value, cnt, rank, world, comm, halo.data_ptr(), scratch.data_ptr(), None)
-        lib.stochqn_b200_rosenbrock_grad(req.value, g.data_ptr(), cnt, off, n, halo.data_ptr(), None)
+        if len(trace) % 2:      # alternate between the fused-halo gradient kernel and the two-step form
+            lib.stochqn_b200_rosenbrock_grad_sharded(req.value, g.data_ptr(), cnt, off, n, rank, world, comm, halo.data_ptr(),
+                                                     scratch.data_ptr(), None)
+        else:
+            lib.stochqn_b200_rosenbrock_halo(req.value, cnt, rank, world, comm, halo.data_ptr(), scratch.data_ptr(), None)
+            lib.stochqn_b200_rosenbrock_grad(req.value, g.data_ptr(), cnt, off, n, halo.data_ptr(), None)
         call()
     torch.cuda.synchronize()
     parts = [torch.empty(shard_bounds(n, r, world)[1], device="cuda", dtype=torch.float64) for r in range(world)]

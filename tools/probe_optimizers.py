@@ -1,0 +1,148 @@
+"""GPU probe: steps/s and per-kernel device times of SQN and adaQN (both pair constructions) at scale, objective =
+a separable convex quadratic f(x) = 0.5 sum a_i (x_i - c_i)^2, a_i in [1, 3], served on the device by torch
+elementwise kernels (dev tool; the headline bench is bench.py).
+
+    python tools/probe_optimizers.py [case ...]     cases: sqn_gd adaqn_gd_f32 adaqn_fisher adaqn_gd adaqn_fisher_big
+
+Per-step algorithmic n-vector counts (kernels_adaqn.cuh):
+    SQN   ordinary step   K1 2m+1 (no grad_prev write) + K3 2m+5 (+1 grad write-back)
+    adaQN ordinary step   KA1 m+3 reads + 1 write (+1 Fisher row) ; KA2 m+2 ; KA3 2m+4 reads + 2 writes (+1 write-back)
+"""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from stochqn_b200 import _lib
+
+CASES = {
+    # name: (kind, dtype, n, m, L, fisher, use_grad_diff, max_incr, rmsprop)
+    "sqn_gd": ("SQN", np.float64, 2 ** 26, 10, 10, 0, 1, 0.0, 0.0),
+    "adaqn_gd_f32": ("adaQN", np.float32, 33558528, 10, 10, 0, 1, 0.0, 0.9),        # BASELINE config 5 shape (8192 x 4096 + 4096)
+    "adaqn_gd": ("adaQN", np.float64, 2 ** 26, 10, 10, 0, 1, 0.0, 0.9),
+    "adaqn_fisher": ("adaQN", np.float64, 292083, 10, 20, 100, 0, 0.0, 0.0),         # BASELINE config 3 shape (1837 x 159)
+    "adaqn_fisher_big": ("adaQN", np.float64, 2 ** 24, 10, 20, 100, 0, 0.0, 0.0),
+}
+
+
+def run(name, iters=60, warm=None):
+    kind, dtype, n, m, L, fisher, gd, max_incr, rms = CASES[name]
+    abi = _lib.load(dtype)
+    lib = abi.lib
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    esz = 8 if dtype == np.float64 else 4
+    x = torch.empty(n, device="cuda", dtype=tdt)
+    g = torch.empty(n, device="cuda", dtype=tdt)
+    lib.stochqn_b200_rosenbrock_x0(x.data_ptr(), n, 0, None)
+    idx = torch.arange(n, device="cuda", dtype=torch.int64)
+    a = (1.0 + 2.0 * ((idx * 2654435761) % 1000).to(tdt) / 1000.0)
+    cc = (((idx * 40503) % 2000).to(tdt) / 1000.0 - 1.0)
+    del idx
+
+    class _Raw:
+        def __init__(self, ptr):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8" if esz == 8 else "<f4", "data": (int(ptr), False), "version": 2}
+
+    views = {}
+
+    def view(ptr):
+        if ptr not in views:
+            views[ptr] = torch.as_tensor(_Raw(ptr), device="cuda")
+        return views[ptr]
+
+    if kind == "SQN":
+        ws = lib.initialize_SQN(n, m, L, 1e-4, gd, 0.0, 1, 1)
+    else:
+        ws = lib.initialize_adaQN(n, m, max(fisher, 1), L, max_incr, 1e-4, 1e-4, rms, gd, 0.0, 1, 1)
+    assert ws, _lib.last_error(abi)
+    req, req_vec, task, info = C.c_void_p(), C.c_void_p(), C.c_int(), C.c_int()
+    step = float(os.environ.get("PROBE_STEP", 1e-3 if kind == "adaQN" else 1e-2))
+    infos = {}
+    tasks = {}
+
+    def call():
+        if kind == "SQN":
+            ret = lib.run_SQN(step, x.data_ptr(), g.data_ptr(), None, C.byref(req), C.byref(req_vec), C.byref(task), ws, C.byref(info))
+        else:
+            ret = lib.run_adaQN(step, x.data_ptr(), 0.0, g.data_ptr(), C.byref(req), C.byref(task), ws, C.byref(info))
+        infos[info.value] = infos.get(info.value, 0) + 1
+        tasks[task.value] = tasks.get(task.value, 0) + 1
+        return ret
+
+    def serve_and_call():
+        assert task.value in (101, 103), task.value
+        torch.sub(view(req.value), cc, out=g)
+        g.mul_(a)
+        return call()
+
+    call()
+    niter = lambda: int(ws.contents.niter)
+    if kind == "adaQN" and os.environ.get("PROBE_NATURAL", "0") == "0":
+        # steady state by construction: m synthetic pairs with positive curvature (y = a.s) written straight into the
+        # device ring buffers, Gram state rebuilt by stochqn_b200_import, and no pair update inside the timed region
+        # (the reference's adaQN iteration is fragile on smooth test objectives - quirk Q2 - and keeps flushing its memory)
+        bm = ws.contents.bfgs_memory.contents
+        ld = lib.stochqn_b200_row_stride(ws)
+        for j in range(m):
+            srow = view(C.cast(bm.s_mem, C.c_void_p).value + j * ld * esz)
+            yrow = view(C.cast(bm.y_mem, C.c_void_p).value + j * ld * esz)
+            srow.normal_(0.0, 0.01)
+            torch.mul(srow, a, out=yrow)
+        bm.mem_used = m
+        bm.mem_st_ix = 0
+        bm.upd_freq = 10 ** 9
+        hs = _lib.HostState()
+        assert lib.stochqn_b200_import(ws, C.byref(hs)) == 0, _lib.last_error(abi)
+        warm = 5
+    else:
+        warm = warm if warm is not None else (m + 2) * L
+    warm += niter()
+    while niter() < warm:
+        serve_and_call()
+    lib.stochqn_b200_set_option(ws, _lib.OPT_PROFILE, 1)
+    torch.cuda.synchronize()
+    infos.clear(); tasks.clear()
+    it0 = niter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    while niter() < it0 + iters:
+        serve_and_call()
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = e0.elapsed_time(e1) / iters
+    st = {k: _lib.get_stat(abi, ws, v) for k, v in dict(k1=1, k1n=2, k3=3, k3n=4, k4=5, k4n=6, ka2=9, ka2n=10).items()}
+    vec = n * esz
+    used = int(ws.contents.bfgs_memory.contents.mem_used)
+    out = dict(case=name, kind=kind, dtype=np.dtype(dtype).name, n=n, m=m, L=L, fisher=fisher, use_grad_diff=gd,
+               ms_per_step=ms, steps_per_s=1e3 / ms, wall_ms_per_step=1e3 * wall / iters, mem_used=used, infos=infos, tasks=tasks)
+    per = lambda a, b: st[a] / max(st[b], 1)
+    d1, d3, d4, d2 = per("k1", "k1n"), per("k3", "k3n"), per("k4", "k4n"), per("ka2", "ka2n")
+    if kind == "SQN":
+        v1, v3 = 2 * used + 1, 2 * used + 5
+        out.update(k1_ms=d1, k1_gbs=v1 * vec / d1 / 1e6, k3_ms=d3, k3_gbs=v3 * vec / d3 / 1e6, step_vec=v1 + v3)
+    else:
+        v1 = used + 3 + 1 + (1 if fisher and not gd else 0)
+        v2 = used + 2
+        v3 = 2 * used + 6
+        out.update(ka1_ms=d1, ka1_gbs=v1 * vec / d1 / 1e6, ka2_ms=d2, ka2_gbs=v2 * vec / max(d2, 1e-9) / 1e6, ka3_ms=d3,
+                   ka3_gbs=v3 * vec / d3 / 1e6, step_vec=v1 + v2 + v3)
+    out["k4_ms"] = d4
+    out["step_gbs_optimizer_only"] = out["step_vec"] * vec / max(d1 + d2 + d3, 1e-9) / 1e6
+    {"SQN": lib.dealloc_SQN, "adaQN": lib.dealloc_adaQN}[kind](ws)
+    del x, g, a, cc
+    views.clear()
+    torch.cuda.empty_cache()
+    return out
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or ["sqn_gd", "adaqn_gd_f32", "adaqn_gd", "adaqn_fisher", "adaqn_fisher_big"]
+    for nm in names:
+        print(json.dumps(run(nm)), flush=True)

@@ -142,6 +142,28 @@ int stochqn_b200_rosenbrock_grad_sharded(const real_t *x, real_t *grad, long lon
                                          long long n_global, int rank, int world_size, void *comm,
                                          real_t *halo, double *scratch, void *stream);
 
+/* Multinomial (softmax) logistic regression with the semantics of the scikit-learn (<= 1.0) private functions the
+   reference's Python layer calls (stochqn/_logistic.py:7-13: _multinomial_loss_grad, _multinomial_grad_hess):
+   w is (nclasses x (nfeat + fit_intercept)) row-major, intercept = last column; X row-major [nrows][nfeat] with leading
+   dimension ldx; the targets are either a dense indicator / probability matrix Y [nrows][nclasses] (leading dimension
+   ldy) or, with Y == NULL, int32 class labels; sample weights `sw` may be NULL.  SUMS over samples (not means):
+     loss     = -sum_i sw_i sum_k Y_ik log softmax(X w' + b)_ik + alpha/2 * ||w[:, :nfeat]||^2
+     grad     = (sw .* (P - Y))' X + alpha w ;  intercept column = column sums of sw .* (P - Y)
+     hess_vec = R' X + alpha v with R = sw .* P .* (X v' + vb - rowsum(P .* (X v' + vb))) ; intercept: column sums of R
+   `grad` or `loss_dev` (device double) may be NULL.  `work`: device scratch of stochqn_b200_multinomial_work_size bytes.
+   The two matrix products run on the tensor cores (tcgen05, tf32 inputs, fp32 accumulation: relative error <= 2^-10
+   per product) in the float build when they are large and 16-byte aligned; STOCHQN_B200_NO_TENSOR_CORES=1 in the
+   environment, or the double build, keeps them on the CUDA cores in full precision. */
+size_t stochqn_b200_multinomial_work_size(long long nrows, long long nfeat, long long nclasses);
+int stochqn_b200_multinomial_loss_grad(const real_t *X, long long ldx, const real_t *Y, long long ldy, const int *labels,
+                                       const real_t *sw, long long nrows, long long nfeat, long long nclasses,
+                                       int fit_intercept, const real_t *w, real_t alpha, real_t *grad, double *loss_dev,
+                                       void *work, void *stream);
+int stochqn_b200_multinomial_hess_vec(const real_t *X, long long ldx, const real_t *Y, long long ldy, const int *labels,
+                                      const real_t *sw, long long nrows, long long nfeat, long long nclasses,
+                                      int fit_intercept, const real_t *w, const real_t *v, real_t alpha, real_t *hess_vec,
+                                      void *work, void *stream);
+
 /* ---- workspace export / import (checkpoint / resume) ----------------------------------------
    The reference keeps all state in host-language arrays, so saveRDS / pickle of the R / Python
    object was a checkpoint (R/allocators.R, stochqn/_optimizers.py:791-879).  These copy the same

@@ -20,8 +20,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 
-SOURCES = ["stochqn_b200.cu", "callbacks.cu"]
-DEPS = ["kernels.cuh", "vecio.cuh", "adaqn_impl.inc", "ext_impl.inc",
+SOURCES = ["stochqn_b200.cu", "callbacks.cu", "multinomial.cu"]
+DEPS = ["kernels.cuh", "kernels_adaqn.cuh", "p2p.cuh", "gemm_tf32_sm100.cuh", "vecio.cuh", "adaqn_impl.inc", "ext_impl.inc",
         os.path.join(REPO, "include", "stochqn.h"), os.path.join(REPO, "include", "stochqn_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-I" + os.path.join(REPO, "include"), "-I" + CSRC]
@@ -61,7 +61,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     jobs = [(t, tags[t], s, verbose, extra) for t in todo for s in SOURCES]
     logs = {}
     if jobs:
-        with ThreadPoolExecutor(max_workers=min(4, len(jobs))) as ex:
+        with ThreadPoolExecutor(max_workers=min(6, len(jobs))) as ex:
             results = list(ex.map(_compile, jobs))
         for (t, _, s, _, _), (obj, log) in zip(jobs, results):
             logs[(t, s)] = log

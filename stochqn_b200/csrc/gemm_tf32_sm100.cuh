@@ -1,0 +1,283 @@
+// gemm_tf32_sm100.cuh - C[M x N] = A[M x K] * B[N x K]'  (fp32 storage, both operands K-contiguous, "TN") on the
+// 5th-generation tensor cores of sm_100a: tcgen05.mma kind::tf32, operands staged in shared memory by TMA
+// (cp.async.bulk.tensor, 128-byte swizzle), accumulators in tensor memory, epilogue through tcgen05.ld.
+//
+// This is the one compute-bound piece of the hot path: the two products of the multinomial-logistic gradient /
+// Hessian-vector callbacks (multinomial.cu: Z = X W' and G = D' X, 2*B*d*K flop each; BASELINE config 5: 8192 features x
+// 4096 classes, fp32).  Inputs are rounded to tf32 (10-bit mantissa) by the tensor core, products accumulate in fp32:
+// relative error of a dot product ~ 2^-11 / sqrt(K) typical, <= 2^-10 worst case (stated tolerance; the fp64 build and
+// STOCHQN_B200_NO_TENSOR_CORES=1 use the CUDA-core kernel).
+//
+// Structure (one persistent CTA per SM, 256 threads, warp-specialised; static round-robin over 128 x 128 output tiles):
+//   warp 0, one lane   TMA producer: for every k-block (32 tf32 = 128 bytes per row) waits for a free stage, arms the
+//                      stage's mbarrier with the byte count and issues two tensor copies (A: 128 rows, B: 128 rows)
+//   warp 1, one lane   MMA issuer: waits for the stage, issues 4 x tcgen05.mma (M 128, N 128, K 8) into the
+//                      accumulator stage in TMEM, tcgen05.commit -> frees the smem stage; after the last k-block
+//                      tcgen05.commit -> tells the epilogue the accumulator is complete
+//   warp 2             allocates / frees the 256 TMEM columns (2 accumulator stages x 128 fp32 columns)
+//   warps 4-7          epilogue: tcgen05.ld (32 lanes x 16 columns per instruction) -> registers -> global (row-major C,
+//                      any ldc, bounds-masked), then hand the accumulator stage back to the MMA warp
+// Rows / columns / k beyond the matrices are zero-filled by TMA (no padding required of the caller); A, B need 16-byte
+// aligned base pointers and leading dimensions that are multiples of 4 elements.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+#include <stdint.h>
+#include <mutex>
+
+namespace tf32gemm {
+
+constexpr int BM = 128, BN = 128, BK = 32;             // BK tf32 = 128 bytes = one swizzle atom
+constexpr int UMMA_K = 8;                              // 32 bytes of K per tcgen05.mma for tf32
+constexpr int STAGES = 6;
+constexpr int ACC_STAGES = 2;
+constexpr int THREADS = 256;
+constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr size_t SMEM_BYTES = (size_t) STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;        // 256: a power of two >= 32
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok = 0;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// shared-memory matrix descriptor, K-major operand, 128-byte swizzle: rows 128 bytes apart inside an 8-row group,
+// groups 1024 bytes apart (SBO), version 1 (sm_100), layout type 2 = SWIZZLE_128B  (cute/arch/mma_sm100_desc.hpp)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t) ((smem_addr >> 4) & 0x3fffu);                 // start address, bits [0,14)
+    d |= (uint64_t) 1 << 16;                                      // leading byte offset (unused for swizzled K-major), bits [16,30)
+    d |= (uint64_t) ((1024u >> 4) & 0x3fffu) << 32;               // stride byte offset, bits [32,46)
+    d |= (uint64_t) 1 << 46;                                      // version, bits [46,48)
+    d |= (uint64_t) 2 << 61;                                      // layout type, bits [61,64)
+    return d;
+}
+// instruction descriptor: D fp32, A / B tf32, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc()
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (BN >> 3) << 17) | ((uint32_t) (BM >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                 :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 float* __restrict__ C, long long ldc, int M, int N, int K)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
+    unsigned char* tiles = smem;                                              // [STAGES][A 16 KB | B 16 KB], 1024-aligned
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t) STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* acc_full = empty + STAGES;
+    uint64_t* acc_empty = acc_full + ACC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+    const int ntiles = tiles_m * tiles_n;
+    const int kblocks = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================= TMA producer =================
+            int s = 0; uint32_t ph = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    mbar_expect_tx(&full[s], STAGE_BYTES);
+                    unsigned char* a_dst = tiles + (size_t) s * STAGE_BYTES;
+                    tma_load_2d(a_dst, &map_a, &full[s], kb * BK, m0);
+                    tma_load_2d(a_dst + A_BYTES, &map_b, &full[s], kb * BK, n0);
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ================= MMA issuer =================
+            constexpr uint32_t idesc = make_idesc();
+            int s = 0; uint32_t ph = 0;
+            int as = 0; uint32_t aph = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                mbar_wait(&acc_empty[as], aph ^ 1u);                 // the epilogue has drained this accumulator stage
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t) (as * BN);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(tiles + (size_t) s * STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + A_BYTES;
+                    #pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t da = make_desc(a_addr + (uint32_t) (k * UMMA_K * 4));
+                        const uint64_t db = make_desc(b_addr + (uint32_t) (k * UMMA_K * 4));
+                        mma_tf32(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty[s]);                          // smem stage is free once these MMAs have read it
+                    if (kb == kblocks - 1) umma_commit(&acc_full[as]);
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
+                }
+                if (++as == ACC_STAGES) { as = 0; aph ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue: TMEM -> registers -> global =================
+        const int q = warp & 3;                                      // TMEM lane quadrant this warp may read
+        int as = 0; uint32_t aph = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+            mbar_wait(&acc_full[as], aph);
+            tc_fence_after();
+            const int row = m0 + q * 32 + lane;
+            float* crow = C + (long long) row * ldc + n0;
+            #pragma unroll 1
+            for (int c = 0; c < BN; c += 16) {
+                uint32_t v[16];
+                const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (as * BN + c);
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                             : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < M) {
+                    #pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (n0 + c + j < N) crow[c + j] = __uint_as_float(v[j]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+            if (++as == ACC_STAGES) { as = 0; aph ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+struct Host {
+    PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+    int sms = 0;
+    bool ok = false;
+    bool tried = false;
+};
+
+inline Host& host()
+{
+    static Host h;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (h.tried) return h;
+    h.tried = true;
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return h;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&h.sms, cudaDevAttrMultiProcessorCount, dev);
+    if (major != 10) return h;                                    // tcgen05 / TMEM: sm_100 family only
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) { cudaGetLastError(); return h; }
+    h.encode = (PFN_cuTensorMapEncodeTiled_v12000) fn;
+    if (cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); return h; }
+    h.ok = true;
+    return h;
+}
+
+inline bool make_map(Host& h, CUtensorMap* map, const float* base, long long ld, int rows, int cols, int box_rows)
+{
+    cuuint64_t dims[2] = {(cuuint64_t) cols, (cuuint64_t) rows};
+    cuuint64_t strides[1] = {(cuuint64_t) ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t) BK, (cuuint32_t) box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = h.encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+}  // namespace tf32gemm
+
+// worth it and legal for TMA? (16-byte aligned bases, leading dimensions multiples of 4 floats, a few tiles of work)
+inline bool sm100_gemm_tf32_usable(const float* A, long long lda, const float* B, long long ldb, const float* C, long long ldc,
+                                   int M, int N, int K)
+{
+    (void) C; (void) ldc;
+    if ((((uintptr_t) A) | ((uintptr_t) B)) & 15u) return false;
+    if ((lda & 3) || (ldb & 3)) return false;
+    if (M < 64 || N < 64 || K < 64) return false;
+    return (double) M * (double) N * (double) K >= 64.0 * 1024 * 1024;
+}
+
+// returns 0 = launched, 1 = tensor-core path not available here (caller falls back), < 0 = error
+inline int sm100_gemm_tf32(const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc,
+                           int M, int N, int K, cudaStream_t st)
+{
+    using namespace tf32gemm;
+    Host& h = host();
+    if (!h.ok) return 1;
+    CUtensorMap ma, mb;
+    if (!make_map(h, &ma, A, lda, M, K, BM) || !make_map(h, &mb, B, ldb, N, K, BN)) return 1;
+    const int ntiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int grid = ntiles < h.sms ? ntiles : h.sms;
+    gemm_tf32_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ma, mb, C, ldc, M, N, K);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}

@@ -15,8 +15,9 @@
 //                      accumulator stage in TMEM, tcgen05.commit -> frees the smem stage; after the last k-block
 //                      tcgen05.commit -> tells the epilogue the accumulator is complete
 //   warp 2             allocates / frees the 256 TMEM columns (2 accumulator stages x 128 fp32 columns)
-//   warps 4-7          epilogue: tcgen05.ld (32 lanes x 16 columns per instruction) -> registers -> global (row-major C,
-//                      any ldc, bounds-masked), then hand the accumulator stage back to the MMA warp
+//   warps 4-7          epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) -> registers -> per-warp 32 x 32 transpose in
+//                      shared memory -> global (row-major C, any ldc, bounds-masked, 128 contiguous bytes per store), then
+//                      hand the accumulator stage back to the MMA warp
 // Rows / columns / k beyond the matrices are zero-filled by TMA (no padding required of the caller); A, B need 16-byte
 // aligned base pointers and leading dimensions that are multiples of 4 elements.
 #pragma once
@@ -34,7 +35,9 @@ constexpr int STAGES = 6;
 constexpr int ACC_STAGES = 2;
 constexpr int THREADS = 256;
 constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr size_t SMEM_BYTES = (size_t) STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int EPI_LD = 33;                             // padded row of the epilogue staging tile (bank-conflict free)
+constexpr size_t EPI_BYTES = (size_t) 4 * 32 * EPI_LD * 4;        // one 32 x 32 fp32 tile per epilogue warp
+constexpr size_t SMEM_BYTES = (size_t) STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */ + EPI_BYTES;
 constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;        // 256: a power of two >= 32
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -106,6 +109,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint64_t* acc_full = empty + STAGES;
     uint64_t* acc_empty = acc_full + ACC_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+    float* epi = reinterpret_cast<float*>(smem + (size_t) STAGES * STAGE_BYTES + 256);      // [4 warps][32][EPI_LD]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
@@ -182,22 +186,33 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
             mbar_wait(&acc_full[as], aph);
             tc_fence_after();
-            const int row = m0 + q * 32 + lane;
-            float* crow = C + (long long) row * ldc + n0;
+            // A lane owns one accumulator row in TMEM; storing from there would scatter every store over 32 rows.
+            // Each warp transposes its 32 x 32 block through shared memory so that a store instruction writes 32
+            // consecutive floats of ONE row of C (128 contiguous bytes, whatever ldc is).
+            float* stage = epi + (size_t) q * 32 * EPI_LD;
             #pragma unroll 1
-            for (int c = 0; c < BN; c += 16) {
-                uint32_t v[16];
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (as * BN + c);
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
                              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                               "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                               "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                              : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < M) {
-                    #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (n0 + c + j < N) crow[c + j] = __uint_as_float(v[j]);
+                #pragma unroll
+                for (int j = 0; j < 32; ++j) stage[lane * EPI_LD + j] = __uint_as_float(v[j]);
+                __syncwarp();
+                const int col = n0 + c + lane;
+                #pragma unroll 4
+                for (int r = 0; r < 32; ++r) {
+                    const int row = m0 + q * 32 + r;
+                    if (row < M && col < N) C[(long long) row * ldc + col] = stage[r * EPI_LD + lane];
                 }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();

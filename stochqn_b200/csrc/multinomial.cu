@@ -209,15 +209,32 @@ mn_finish(T* __restrict__ G, long long ldg, const T* __restrict__ U, long long l
     }
 }
 
-// loss = sum_i terms[i] + alpha/2 * sum_{k, j<d} W[k][j]^2 ; one CTA, fixed order
+// wn[k] = sum_{j<d} W[k][j]^2 : one CTA per class (the penalty term of the loss, without the intercept column)
 template <typename T>
 __global__ void __launch_bounds__(256)
-mn_loss_finish(const double* __restrict__ terms, int B, const T* __restrict__ W, long long ldw, int K, int d, T alpha,
-               double* __restrict__ loss)
+mn_wnorm(const T* __restrict__ W, long long ldw, int d, double* __restrict__ wn)
+{
+    const T* row = W + (long long) blockIdx.x * ldw;
+    double b = 0.0;
+    for (int j = threadIdx.x; j < d; j += 256) { const double w = (double) row[j]; b = fma(w, w, b); }
+    __shared__ double rb[8];
+    for (int o = 16; o > 0; o >>= 1) b += __shfl_down_sync(0xffffffffu, b, o);
+    if ((threadIdx.x & 31) == 0) rb[threadIdx.x >> 5] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sb = 0;
+        for (int q = 0; q < 8; ++q) sb += rb[q];
+        wn[blockIdx.x] = sb;
+    }
+}
+
+// loss = sum_i terms[i] + alpha/2 * sum_k wn[k] ; one CTA, fixed order
+__global__ void __launch_bounds__(256)
+mn_loss_finish(const double* __restrict__ terms, int B, const double* __restrict__ wn, int K, double alpha, double* __restrict__ loss)
 {
     double a = 0.0, b = 0.0;
     for (int i = threadIdx.x; i < B; i += 256) a += terms[i];
-    for (long long t = threadIdx.x; t < (long long) K * d; t += 256) { const double w = (double) W[(t / d) * ldw + (t % d)]; b = fma(w, w, b); }
+    for (int k = threadIdx.x; k < K; k += 256) b += wn[k];
     __shared__ double ra[8], rb[8];
     for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); }
     if ((threadIdx.x & 31) == 0) { ra[threadIdx.x >> 5] = a; rb[threadIdx.x >> 5] = b; }
@@ -225,7 +242,7 @@ mn_loss_finish(const double* __restrict__ terms, int B, const T* __restrict__ W,
     if (threadIdx.x == 0) {
         double sa = 0, sb = 0;
         for (int q = 0; q < 8; ++q) { sa += ra[q]; sb += rb[q]; }
-        *loss = sa + 0.5 * (double) alpha * sb;
+        *loss = sa + 0.5 * alpha * sb;
     }
 }
 
@@ -267,7 +284,7 @@ MnPlan mn_plan(long long B, long long d, long long K)
     p.off_rp = off; off = al(off + sizeof(real_t) * (size_t) (s * B * K));
     p.off_dt = off; off = al(off + sizeof(real_t) * (size_t) (K * p.bpad));
     p.off_xt = off; off = al(off + sizeof(real_t) * (size_t) (d * p.bpad));
-    p.off_terms = off; off = al(off + sizeof(double) * (size_t) (B + 2));
+    p.off_terms = off; off = al(off + sizeof(double) * (size_t) (B + K + 2));       // per-sample loss terms, then per-class ||w_k||^2
     p.off_wp = off; p.off_vp = off;
 #ifdef USE_FLOAT
     p.off_wp = off; off = al(off + sizeof(real_t) * (size_t) (K * p.dpad));      // packed W / V for the tensor-core path
@@ -344,8 +361,9 @@ int mn_common(int kind, const real_t* X, long long ldx, const real_t* Y, long lo
                                                           DT, p.bpad, nullptr);
     int launched = 1;
     if (loss_dev && kind == MN_GRAD) {
-        mn_loss_finish<real_t><<<1, 256, 0, st>>>(terms, (int) B, w, ldw, (int) K, (int) d, alpha, loss_dev);
-        ++launched;
+        mn_wnorm<real_t><<<(unsigned) K, 256, 0, st>>>(w, ldw, (int) d, terms + B);
+        mn_loss_finish<<<1, 256, 0, st>>>(terms, (int) B, terms + B, (int) K, (double) alpha, loss_dev);
+        launched += 2;
     }
     if (need_out) {
         dim3 tb(32, 8), tg((unsigned) ((d + 31) / 32), (unsigned) ((B + 31) / 32));

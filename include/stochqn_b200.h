@@ -155,6 +155,10 @@ int stochqn_b200_rosenbrock_grad_sharded(const real_t *x, real_t *grad, long lon
    per product) in the float build when they are large and 16-byte aligned; STOCHQN_B200_NO_TENSOR_CORES=1 in the
    environment, or the double build, keeps them on the CUDA cores in full precision. */
 size_t stochqn_b200_multinomial_work_size(long long nrows, long long nfeat, long long nclasses);
+/* the product both callbacks are built on, exposed for tests and probes: C[M x N] (ldc) = A[M x K] (lda) * B[N x K]' (ldb),
+   row-major, device pointers; same tensor-core / CUDA-core selection as above */
+int stochqn_b200_gemm_tn(const real_t *A, long long lda, const real_t *B, long long ldb, real_t *C, long long ldc,
+                         int M, int N, int K, void *stream);
 int stochqn_b200_multinomial_loss_grad(const real_t *X, long long ldx, const real_t *Y, long long ldy, const int *labels,
                                        const real_t *sw, long long nrows, long long nfeat, long long nclasses,
                                        int fit_intercept, const real_t *w, real_t alpha, real_t *grad, double *loss_dev,

@@ -26,6 +26,7 @@ EXT_SYMBOLS = (
     "stochqn_b200_logistic_work_size", "stochqn_b200_logistic_grad", "stochqn_b200_logistic_hess_vec",
     "stochqn_b200_logistic_loss", "stochqn_b200_export", "stochqn_b200_import",
     "stochqn_b200_multinomial_work_size", "stochqn_b200_multinomial_loss_grad", "stochqn_b200_multinomial_hess_vec",
+    "stochqn_b200_gemm_tn",
 )
 
 OPT_GRAD_WRITEBACK = 1
@@ -91,6 +92,7 @@ def load(dtype=np.float64) -> StochqnABI:
     lib.stochqn_b200_multinomial_work_size.restype = sz
     lib.stochqn_b200_multinomial_loss_grad.argtypes = [vp, ll, vp, ll, vp, vp, ll, ll, ll, ci, vp, real, vp, vp, vp, vp]
     lib.stochqn_b200_multinomial_hess_vec.argtypes = [vp, ll, vp, ll, vp, vp, ll, ll, ll, ci, vp, vp, real, vp, vp, vp]
+    lib.stochqn_b200_gemm_tn.argtypes = [vp, ll, vp, ll, vp, ll, ci, ci, ci, vp]
     lib.stochqn_b200_export.argtypes = [vp, C.POINTER(HostState)]
     lib.stochqn_b200_import.argtypes = [vp, C.POINTER(HostState)]
     for name in EXT_SYMBOLS:

@@ -25,20 +25,26 @@
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <mutex>
 
 namespace tf32gemm {
 
-constexpr int BM = 128, BN = 128, BK = 32;             // BK tf32 = 128 bytes = one swizzle atom
+constexpr int BM = 128, BK = 32;                       // BK tf32 = 128 bytes = one swizzle atom
 constexpr int UMMA_K = 8;                              // 32 bytes of K per tcgen05.mma for tf32
-constexpr int STAGES = 6;
 constexpr int ACC_STAGES = 2;
 constexpr int THREADS = 256;
-constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr uint32_t A_BYTES = BM * BK * 4;
 constexpr int EPI_LD = 33;                             // padded row of the epilogue staging tile (bank-conflict free)
 constexpr size_t EPI_BYTES = (size_t) 4 * 32 * EPI_LD * 4;        // one 32 x 32 fp32 tile per epilogue warp
-constexpr size_t SMEM_BYTES = (size_t) STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */ + EPI_BYTES;
-constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;        // 256: a power of two >= 32
+// Tile width BN = 128 (6 stages of 32 KB, 256 TMEM columns) or 256 (4 stages of 48 KB, all 512 TMEM columns): the wide
+// tile moves 25 % fewer operand bytes from L2 per flop - the 128-wide kernel is L2-bound (ncu: 11 TB/s into the SMs).
+template <int BN> struct Cfg {
+    static constexpr int STAGES = BN == 128 ? 6 : 4;
+    static constexpr uint32_t B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr size_t SMEM_BYTES = (size_t) STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */ + EPI_BYTES;
+    static constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;        // a power of two >= 32
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
@@ -80,9 +86,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
     return d;
 }
 // instruction descriptor: D fp32, A / B tf32, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc()
+__host__ __device__ constexpr uint32_t make_idesc(int bn)
 {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (BN >> 3) << 17) | ((uint32_t) (BM >> 4) << 24);
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (bn >> 3) << 17) | ((uint32_t) (BM >> 4) << 24);
 }
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
 {
@@ -97,10 +103,13 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar)
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+template <int BN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  float* __restrict__ C, long long ldc, int M, int N, int K)
 {
+    constexpr int STAGES = Cfg<BN>::STAGES;
+    constexpr uint32_t STAGE_BYTES = Cfg<BN>::STAGE_BYTES, TMEM_COLS = Cfg<BN>::TMEM_COLS;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
     unsigned char* tiles = smem;                                              // [STAGES][A 16 KB | B 16 KB], 1024-aligned
@@ -153,7 +162,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     } else if (warp == 1) {
         if (lane == 0) {
             // ================= MMA issuer =================
-            constexpr uint32_t idesc = make_idesc();
+            constexpr uint32_t idesc = make_idesc(BN);
             int s = 0; uint32_t ph = 0;
             int as = 0; uint32_t aph = 0;
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -252,7 +261,8 @@ inline Host& host()
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) { cudaGetLastError(); return h; }
     h.encode = (PFN_cuTensorMapEncodeTiled_v12000) fn;
-    if (cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); return h; }
+    if (cudaFuncSetAttribute(gemm_tf32_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Cfg<128>::SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tf32_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Cfg<256>::SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); return h; }
     h.ok = true;
     return h;
 }
@@ -289,10 +299,16 @@ inline int sm100_gemm_tf32(const float* A, long long lda, const float* B, long l
     using namespace tf32gemm;
     Host& h = host();
     if (!h.ok) return 1;
+    static int force_bn = -1;
+    if (force_bn < 0) { const char* e = getenv("STOCHQN_B200_GEMM_BN"); force_bn = e ? atoi(e) : 0; }      // dev switch
+    const long long tiles_m = (M + BM - 1) / BM;
+    // wide tiles when they still give every SM work (the wide kernel makes the same makespan with less L2 traffic)
+    const bool wide = force_bn == 256 || (force_bn != 128 && N >= 256 && tiles_m * ((N + 255) / 256) >= (long long) h.sms * 3 / 4);
     CUtensorMap ma, mb;
-    if (!make_map(h, &ma, A, lda, M, K, BM) || !make_map(h, &mb, B, ldb, N, K, BN)) return 1;
-    const int ntiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-    const int grid = ntiles < h.sms ? ntiles : h.sms;
-    gemm_tf32_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ma, mb, C, ldc, M, N, K);
+    if (!make_map(h, &ma, A, lda, M, K, BM) || !make_map(h, &mb, B, ldb, N, K, wide ? 256 : 128)) return 1;
+    const long long ntiles = tiles_m * ((N + (wide ? 255 : 127)) / (wide ? 256 : 128));
+    const int grid = (int) (ntiles < h.sms ? ntiles : h.sms);
+    if (wide) gemm_tf32_kernel<256><<<grid, THREADS, Cfg<256>::SMEM_BYTES, st>>>(ma, mb, C, ldc, M, N, K);
+    else      gemm_tf32_kernel<128><<<grid, THREADS, Cfg<128>::SMEM_BYTES, st>>>(ma, mb, C, ldc, M, N, K);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

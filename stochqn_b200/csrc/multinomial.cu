@@ -382,6 +382,13 @@ int mn_common(int kind, const real_t* X, long long ldx, const real_t* Y, long lo
 
 extern "C" {
 
+int stochqn_b200_gemm_tn(const real_t* A, long long lda, const real_t* B, long long ldb, real_t* C, long long ldc,
+                         int M, int N, int K, void* stream)
+{
+    if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return -1;
+    return launch_gemm(A, lda, B, ldb, C, ldc, 0, M, N, K, 1, (cudaStream_t) stream);
+}
+
 size_t stochqn_b200_multinomial_work_size(long long nrows, long long nfeat, long long nclasses)
 {
     if (nrows <= 0 || nfeat <= 0 || nclasses <= 0) return 0;

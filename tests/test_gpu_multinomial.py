@@ -90,3 +90,36 @@ def test_multinomial_tensor_cores_fp32(shape, fit_intercept):
         os.environ.pop("STOCHQN_B200_NO_TENSOR_CORES", None)
     assert np.max(np.abs(g - g2)) <= 2e-3 * np.max(np.abs(g2))
     assert np.max(np.abs(g - g2)) > 0.0        # the two paths really are different arithmetic
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 64), (1024, 4096, 2048), (1000, 520, 1032), (130, 2050, 516), (4096, 300, 1024), (512, 256, 4100)])
+@pytest.mark.parametrize("bn", ["0", "128", "256"])
+def test_gemm_tn_tensor_cores_vs_fp64(shape, bn):
+    """C = A B' on the tcgen05 path (both tile widths, ragged edges, K not a multiple of the k-block) against an fp64
+    product of the same fp32 inputs: tf32 rounding only (|err| <= 2^-10 * sum |a||b| per entry, checked as 1.5e-3 of
+    the row-column magnitude bound)."""
+    import subprocess, sys, json
+    M, N, K = shape
+    code = """
+import os, sys, json, numpy as np, torch
+sys.path.insert(0, %r)
+from stochqn_b200 import _lib
+lib = _lib.load(np.float32).lib
+M, N, K = %d, %d, %d
+g = torch.Generator(device="cuda"); g.manual_seed(M + N + K)
+A = torch.randn(M, K, device="cuda", generator=g); B = torch.randn(N, K, device="cuda", generator=g)
+C = torch.full((M, N), float("nan"), device="cuda")
+assert lib.stochqn_b200_gemm_tn(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, M, N, K, None) == 0
+torch.cuda.synchronize()
+ref = A.double() @ B.double().T
+bound = A.abs().double() @ B.abs().double().T
+err = ((C.double() - ref).abs() / bound).max().item()
+exact = (C.double() - ref).abs().max().item()
+print(json.dumps(dict(err=err, finite=bool(torch.isfinite(C).all().item()), exact=exact)))
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), M, N, K)
+    env = dict(os.environ, STOCHQN_B200_GEMM_BN=bn)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert res["finite"], res
+    assert res["err"] <= 1.5e-3, res

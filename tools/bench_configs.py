@@ -1,0 +1,217 @@
+"""Device-resident request loops for the other BASELINE.json configurations (the headline one is bench.py):
+
+  cfg1  oLBFGS  + binary logistic      X 100k x (1000 + intercept), batch 1000, mem_size 10, fp64
+  cfg2  SQN (calc_hess_vec) + logistic X 1M x (4096 + intercept), batch 2000, bfgs_upd_freq 10, big batch 20k, fp64
+  cfg3  adaQN AdaGrad + Fisher(100)    multinomial 1836 features x 159 classes, batch 50, L 20, max_incr 1.01, fp64
+  cfg5  adaQN RMSProp(0.9) + grad-diff multinomial 8192 features x 4096 classes, batch 1024 per GPU, fp32 (tensor cores)
+
+Everything stays on the GPU: the optimizer's requests are served by the bundled device callbacks at `*req`.
+Synthetic data (no datasets in the image): X ~ N(0,1)/sqrt(d), labels drawn from a random ground-truth model.
+Prints one JSON line per configuration: optimizer steps/s (CUDA events), task / info histograms, final loss.
+
+    python tools/bench_configs.py [cfg1 cfg2 cfg3 cfg5] [--steps N] [--rows-cfg2 R]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from stochqn_b200 import _lib
+
+
+def _gen_rows(nrows, d, dtype, intercept_first, seed):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    cols = d + (1 if intercept_first else 0)
+    X = torch.empty(nrows, cols, device="cuda", dtype=dtype)
+    chunk = max(1, (1 << 28) // cols)
+    for r0 in range(0, nrows, chunk):
+        r1 = min(nrows, r0 + chunk)
+        X[r0:r1, (1 if intercept_first else 0):] = torch.randn(r1 - r0, d, device="cuda", dtype=dtype, generator=g) / d ** 0.5
+    if intercept_first:
+        X[:, 0] = 1.0                       # R prepends the intercept column (R/logistic.R:424)
+    return X
+
+
+def run_logistic(name, kind, nrows, d, batch, steps, L=10, big=20000):
+    dtype, tdt, esz = np.float64, torch.float64, 8
+    abi = _lib.load(dtype)
+    lib = abi.lib
+    n = d + 1
+    X = _gen_rows(nrows, d, tdt, True, 1)
+    wtrue = torch.randn(n, device="cuda", dtype=tdt, generator=torch.Generator(device="cuda").manual_seed(2))
+    y = (torch.rand(nrows, device="cuda", dtype=tdt) < torch.sigmoid(X @ wtrue * 3.0)).to(tdt)
+    x = torch.zeros(n, device="cuda", dtype=tdt)
+    g = torch.zeros(n, device="cuda", dtype=tdt)
+    hv = torch.zeros(n, device="cuda", dtype=tdt)
+    loss = torch.zeros(1, device="cuda", dtype=torch.float64)
+    work = torch.empty(lib.stochqn_b200_logistic_work_size(max(batch, big), n), device="cuda", dtype=torch.uint8)
+    lam = 1e-5                                  # the callbacks' default (R/logistic.R:1,12,23)
+    if kind == "oLBFGS":
+        ws = lib.initialize_oLBFGS(n, 10, 0.0, 0.0, 1e-4, 1, 1)
+    else:
+        ws = lib.initialize_SQN(n, 10, L, 1e-4, 0, 0.0, 1, 1)
+    assert ws, _lib.last_error(abi)
+    req, req_vec, task, info = C.c_void_p(), C.c_void_p(), C.c_int(), C.c_int()
+    tasks, infos = {}, {}
+    step = 1e-1
+    nb = nrows // batch
+    state = dict(b=0)
+
+    def call():
+        if kind == "oLBFGS":
+            lib.run_oLBFGS(step, x.data_ptr(), g.data_ptr(), C.byref(req), C.byref(task), ws, C.byref(info))
+        else:
+            lib.run_SQN(step, x.data_ptr(), g.data_ptr(), hv.data_ptr(), C.byref(req), C.byref(req_vec), C.byref(task), ws, C.byref(info))
+        tasks[task.value] = tasks.get(task.value, 0) + 1
+        infos[info.value] = infos.get(info.value, 0) + 1
+
+    def rows(b0, cnt):
+        return X.data_ptr() + b0 * n * esz, y.data_ptr() + b0 * esz
+
+    def serve():
+        t = task.value
+        b = state["b"]
+        if t == 101:                              # calc_grad: next batch
+            state["b"] = b = (b + 1) % nb
+            xp, yp = rows(b * batch, batch)
+            lib.stochqn_b200_logistic_grad(xp, n, yp, None, batch, n, req.value, lam, g.data_ptr(), work.data_ptr(), None)
+        elif t == 102:                            # calc_grad_same_batch
+            xp, yp = rows(b * batch, batch)
+            lib.stochqn_b200_logistic_grad(xp, n, yp, None, batch, n, req.value, lam, g.data_ptr(), work.data_ptr(), None)
+        elif t == 104:                            # calc_hess_vec on the big batch = the rows of the last L batches
+            cnt = min(big, (b + 1) * batch)
+            r0 = (b + 1) * batch - cnt
+            xp, yp = rows(r0, cnt)
+            lib.stochqn_b200_logistic_hess_vec(xp, n, yp, None, cnt, n, req.value, req_vec.value, lam, hv.data_ptr(), work.data_ptr(), None)
+        else:
+            raise RuntimeError("unexpected task %d" % t)
+
+    call()
+    niter = lambda: int(ws.contents.niter)
+    warm = 15 * (L if kind == "SQN" else 1)
+    while niter() < warm:
+        serve(); call()
+    torch.cuda.synchronize()
+    tasks.clear(); infos.clear()
+    launches0 = _lib.launch_count()
+    it0 = niter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    while niter() < it0 + steps:
+        serve(); call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    xp, yp = rows(0, min(nrows, 20000))
+    lib.stochqn_b200_logistic_loss(xp, n, yp, None, min(nrows, 20000), n, x.data_ptr(), lam, loss.data_ptr(), work.data_ptr(), None)
+    out = dict(config=name, optimizer=kind, dtype="f64", n=n, rows=nrows, batch=batch, steps=steps, ms_per_step=ms, steps_per_s=1e3 / ms,
+               tasks=tasks, infos=infos, mem_used=int(ws.contents.bfgs_memory.contents.mem_used),
+               launches_per_step=(_lib.launch_count() - launches0) / steps, loss_after=float(loss.item()), loss_at_zero=float(np.log(2.0)))
+    {"oLBFGS": lib.dealloc_oLBFGS, "SQN": lib.dealloc_SQN}[kind](ws)
+    print(json.dumps(out), flush=True)
+
+
+def run_multinomial(name, dtype, d, K, batch, nrows, steps, L, fisher, use_grad_diff, max_incr, rms, step):
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    esz = 8 if dtype == np.float64 else 4
+    abi = _lib.load(dtype)
+    lib = abi.lib
+    n = K * (d + 1)
+    X = _gen_rows(nrows, d, tdt, False, 3)
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    Wt = torch.randn(K, d, device="cuda", dtype=tdt, generator=gen)
+    lab = torch.empty(nrows, device="cuda", dtype=torch.int32)
+    for r0 in range(0, nrows, 4096):
+        r1 = min(nrows, r0 + 4096)
+        lab[r0:r1] = torch.argmax(X[r0:r1] @ Wt.T * 4.0 + torch.randn(r1 - r0, K, device="cuda", dtype=tdt, generator=gen), dim=1).to(torch.int32)
+    del Wt
+    nval = min(nrows, 740)
+    big = min(nrows, batch * L)
+    x = torch.zeros(n, device="cuda", dtype=tdt)
+    g = torch.zeros(n, device="cuda", dtype=tdt)
+    loss = torch.zeros(1, device="cuda", dtype=torch.float64)
+    work = torch.empty(lib.stochqn_b200_multinomial_work_size(max(batch, big, nval), d, K), device="cuda", dtype=torch.uint8)
+    sw = {c: torch.full((c,), 1.0 / c, device="cuda", dtype=tdt) for c in {batch, big, nval}}     # mean log-loss
+    alpha = 1e-3
+    ws = lib.initialize_adaQN(n, 10, max(fisher, 1), L, max_incr, 1e-4, 1e-4, rms, use_grad_diff, 0.0, 1, 1)
+    assert ws, _lib.last_error(abi)
+    req, task, info = C.c_void_p(), C.c_int(), C.c_int()
+    tasks, infos = {}, {}
+    nb = nrows // batch
+    state = dict(b=0, f=0.0)
+
+    def call():
+        lib.run_adaQN(step, x.data_ptr(), state["f"], g.data_ptr(), C.byref(req), C.byref(task), ws, C.byref(info))
+        tasks[task.value] = tasks.get(task.value, 0) + 1
+        infos[info.value] = infos.get(info.value, 0) + 1
+
+    def grad_on(r0, cnt, want_loss=False):
+        return lib.stochqn_b200_multinomial_loss_grad(X.data_ptr() + r0 * d * esz, d, None, K, lab.data_ptr() + r0 * 4, sw[cnt].data_ptr(), cnt, d, K, 1,
+                                                      req.value, alpha, None if want_loss else g.data_ptr(), loss.data_ptr() if want_loss else None,
+                                                      work.data_ptr(), None)
+
+    def serve():
+        t = task.value
+        b = state["b"]
+        if t == 101:
+            state["b"] = b = (b + 1) % nb
+            assert grad_on(b * batch, batch) == 0
+        elif t == 103:                            # calc_grad_big_batch: the rows of the last L batches
+            cnt = big
+            r0 = max(0, (b + 1) * batch - cnt)
+            assert grad_on(r0, cnt) == 0
+        elif t == 105:                            # calc_fun_val_batch: validation rows
+            assert grad_on(0, nval, want_loss=True) == 0
+            state["f"] = float(loss.item())
+        else:
+            raise RuntimeError("unexpected task %d" % t)
+
+    call()
+    niter = lambda: int(ws.contents.niter)
+    warm = 3 * L
+    while niter() < warm:
+        serve(); call()
+    torch.cuda.synchronize()
+    tasks.clear(); infos.clear()
+    launches0 = _lib.launch_count()
+    it0 = niter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    while niter() < it0 + steps:
+        serve(); call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    req.value = x.data_ptr()
+    grad_on(0, nval, want_loss=True)
+    out = dict(config=name, optimizer="adaQN", dtype="f64" if esz == 8 else "f32", n=n, features=d, classes=K, batch=batch, steps=steps,
+               ms_per_step=ms, steps_per_s=1e3 / ms, tasks=tasks, infos=infos, mem_used=int(ws.contents.bfgs_memory.contents.mem_used),
+               launches_per_step=(_lib.launch_count() - launches0) / steps, loss_after=float(loss.item()), loss_at_zero=float(np.log(K)))
+    lib.dealloc_adaQN(ws)
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("configs", nargs="*", default=["cfg1", "cfg2", "cfg3", "cfg5"])
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--rows-cfg2", type=int, default=1000000)
+    a = ap.parse_args()
+    if "cfg1" in a.configs:
+        run_logistic("cfg1", "oLBFGS", 100000, 1000, 1000, a.steps)
+    if "cfg2" in a.configs:
+        run_logistic("cfg2", "SQN", a.rows_cfg2, 4096, 2000, a.steps, L=10, big=20000)
+    if "cfg3" in a.configs:
+        run_multinomial("cfg3", np.float64, 1836, 159, 50, 6655, a.steps, 20, 100, 0, 1.01, 0.0, 1e-2)
+    if "cfg5" in a.configs:
+        run_multinomial("cfg5", np.float32, 8192, 4096, 1024, 16384, min(a.steps, 100), 10, 0, 1, 0.0, 0.9, 1e-3)
+
+
+if __name__ == "__main__":
+    main()

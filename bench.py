@@ -269,15 +269,18 @@ def main_b200(args):
     k3_bytes = (2 * used + 4) * vec_bytes              # read g, S, Y, x; write x, s_new  (SURVEY 8(d)); the grad write-back is not counted
     k1_bytes = (2 * used + 2) * vec_bytes              # read g, S, Y; write grad_prev
     k4_bytes = 4 * vec_bytes
-    traffic = None
+    traffic, traffic_note = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if int(tj.get("n_local", -1)) == n_local:
-            traffic = tj.get("k3_dram_bytes_per_launch")
+        # ncu --set full was taken at n = 2^24 (40 replays of a 20 GiB working set are not practical at 2^27); every byte
+        # of K3's traffic is streaming, so the per-launch figure scales with the vector length
+        traffic = float(tj["k3_dram_bytes_per_launch"]) * n_local / float(tj["n_local"])
+        traffic_note = "dram__bytes_read+write of one K3 launch captured at n_local=%d, scaled by n_local/%d (%s)" % (
+            int(tj["n_local"]), int(tj["n_local"]), tj.get("source", "profiles/"))
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "k3_combine (fused combine + x update + new s)", "achieved": k3_bytes / k3_ms / 1e6,
-                "peak": peak, "unit": "GB/s", "frac": k3_bytes / k3_ms / 1e6 / peak, "traffic": traffic,
+                "peak": peak, "unit": "GB/s", "frac": k3_bytes / k3_ms / 1e6 / peak, "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "per_launch_bytes": k3_bytes, "avg_launch_ms": k3_ms, "launches_timed": int(st["k3n"]),
                 "other_kernels": {

@@ -98,6 +98,14 @@ int stochqn_b200_set_comm(void *ws, void *comm, long long n_global);
    (exposed so that callbacks can ride on the same communicator) */
 int stochqn_b200_allreduce_f64(void *comm, double *dev_buf, size_t count, void *stream);
 
+/* n-vector collectives for row-sharded gradient / Hessian-vector callbacks (each rank evaluates the callback on its rows
+   of the batch; NCCL over NVLink, on `stream`).  all-reduce: every rank ends with the full sum (replicated optimizer).
+   reduce-scatter + all-gather: rank r receives block r (block_count elements; the vector is world_size * block_count
+   long) of the sum, steps its shard of the optimizer state (stochqn_b200_set_comm) and the updated x is gathered back. */
+int stochqn_b200_allreduce_real(void *comm, real_t *dev_buf, size_t count, void *stream);
+int stochqn_b200_reduce_scatter_real(void *comm, const real_t *send_full, real_t *recv_block, size_t block_count, void *stream);
+int stochqn_b200_all_gather_real(void *comm, const real_t *send_block, real_t *recv_full, size_t block_count, void *stream);
+
 /* ---- bundled device callbacks -------------------------------------------------------------
    Chained Rosenbrock, formulas of the reference's example (example/c_rosen.c:13-41), on a
    contiguous shard x[0..n_local) of a vector of length n_global that starts at global index

@@ -20,7 +20,7 @@ EXT_SYMBOLS = (
     "stochqn_b200_set_stream", "stochqn_b200_set_option", "stochqn_b200_get_stat", "stochqn_b200_row_stride",
     "stochqn_b200_comm_unique_id", "stochqn_b200_comm_init", "stochqn_b200_comm_destroy", "stochqn_b200_comm_uses_p2p",
     "stochqn_b200_set_comm",
-    "stochqn_b200_allreduce_f64",
+    "stochqn_b200_allreduce_f64", "stochqn_b200_allreduce_real", "stochqn_b200_reduce_scatter_real", "stochqn_b200_all_gather_real",
     "stochqn_b200_rosenbrock_x0", "stochqn_b200_rosenbrock_grad", "stochqn_b200_rosenbrock_fun", "stochqn_b200_rosenbrock_halo",
     "stochqn_b200_rosenbrock_grad_sharded",
     "stochqn_b200_logistic_work_size", "stochqn_b200_logistic_grad", "stochqn_b200_logistic_hess_vec",
@@ -78,6 +78,9 @@ def load(dtype=np.float64) -> StochqnABI:
     lib.stochqn_b200_comm_uses_p2p.argtypes = [vp]
     lib.stochqn_b200_set_comm.argtypes = [vp, vp, ll]
     lib.stochqn_b200_allreduce_f64.argtypes = [vp, vp, sz, vp]
+    lib.stochqn_b200_allreduce_real.argtypes = [vp, vp, sz, vp]
+    lib.stochqn_b200_reduce_scatter_real.argtypes = [vp, vp, vp, sz, vp]
+    lib.stochqn_b200_all_gather_real.argtypes = [vp, vp, vp, sz, vp]
     lib.stochqn_b200_rosenbrock_x0.argtypes = [vp, ll, ll, vp]
     lib.stochqn_b200_rosenbrock_grad.argtypes = [vp, vp, ll, ll, ll, vp, vp]
     lib.stochqn_b200_rosenbrock_fun.argtypes = [vp, ll, ll, ll, vp, vp, vp]

@@ -64,6 +64,7 @@ struct NcclApi {
     int (*CommDestroy)(void*) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*ReduceScatter)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
 NcclApi g_nccl;
@@ -82,8 +83,9 @@ int load_nccl()
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy)) dlsym(h, "ncclCommDestroy");
     g_nccl.AllReduce = (decltype(g_nccl.AllReduce)) dlsym(h, "ncclAllReduce");
     g_nccl.AllGather = (decltype(g_nccl.AllGather)) dlsym(h, "ncclAllGather");
+    g_nccl.ReduceScatter = (decltype(g_nccl.ReduceScatter)) dlsym(h, "ncclReduceScatter");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString)) dlsym(h, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce || !g_nccl.AllGather)
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce || !g_nccl.AllGather || !g_nccl.ReduceScatter)
         return fail(-3, "NCCL library lacks an expected symbol");
     g_nccl.handle = h;
     return 0;

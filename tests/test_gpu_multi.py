@@ -46,3 +46,21 @@ def test_sharded_two_gpus_matches_oracle(tmp_path, kind, no_p2p):
     assert res["same_on_all_ranks"] and res["matches_oracle"], res
     assert res["pairs"] >= 4, res
     assert res["rel_err"] <= 1e-10, res
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_row_sharded_multinomial_two_gpus(tmp_path):
+    """adaQN + multinomial gradient with the batch rows sharded over 2 GPUs: ncclAllReduce + replicated optimizer and
+    ncclReduceScatter + sharded optimizer + ncclAllGather give the same iterates (up to summation order), identical on
+    every rank, with identical task sequences."""
+    out = str(tmp_path / "res.json")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(HERE, "multi_gpu_rowshard_worker.py"), out]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    res = json.load(open(out))
+    assert res["ranks_identical"], res
+    assert res["moved"] > 1e-3, res
+    assert res["res"]["allreduce"]["tasks"] == res["res"]["zero1"]["tasks"], res
+    assert res["res"]["allreduce"]["infos"] == res["res"]["zero1"]["infos"], res
+    assert res["modes_rel_err"] <= 1e-9, res

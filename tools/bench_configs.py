@@ -197,12 +197,137 @@ def run_multinomial(name, dtype, d, K, batch, nrows, steps, L, fisher, use_grad_
     print(json.dumps(out), flush=True)
 
 
+def run_multinomial_sharded(name, dtype, d, K, batch_per_gpu, nrows_per_gpu, steps, L, rms, step, mode="zero1", warm_cycles=3,
+                            return_x=False, quiet=False):
+    """BASELINE config 5 over several GPUs (launch with torch.distributed.run, one rank per GPU): batch ROWS shard across
+    the ranks, each rank evaluates the multinomial gradient on its rows (weights 1/global batch), then either
+      mode "allreduce": ncclAllReduce of the n-vector, every rank runs the same (replicated) adaQN step, or
+      mode "zero1"    : ncclReduceScatter -> rank r steps block r of the optimizer state (the library's sharded optimizer:
+                        dot partials exchanged inside the solve kernels) -> ncclAllGather of the point the next request names.
+    adaQN with RMSProp + gradient differencing (calc_grad / calc_grad_big_batch), max_incr 0."""
+    import torch.distributed as dist
+    from stochqn_b200.distributed import init_comm
+
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    esz = 8 if dtype == np.float64 else 4
+    abi = _lib.load(dtype)
+    lib = abi.lib
+    comm = init_comm(abi, rank, world) if world > 1 else None
+    n = K * (d + 1)
+    assert n % world == 0, "n must divide by the number of ranks for reduce-scatter"
+    blk = n // world if mode == "zero1" else n
+    off = rank * blk if mode == "zero1" else 0
+    # this rank's rows of every global batch: global row = b * (world * batch_per_gpu) + rank * batch_per_gpu + i
+    nb = nrows_per_gpu // batch_per_gpu
+    gen = torch.Generator(device="cuda").manual_seed(100)
+    Wt = torch.randn(K, d, device="cuda", dtype=tdt, generator=gen)                    # same ground truth on every rank
+    gen_r = torch.Generator(device="cuda").manual_seed(200 + rank)
+    X = torch.randn(nrows_per_gpu, d, device="cuda", dtype=tdt, generator=gen_r) / d ** 0.5
+    lab = torch.empty(nrows_per_gpu, device="cuda", dtype=torch.int32)
+    for r0 in range(0, nrows_per_gpu, 4096):
+        r1 = min(nrows_per_gpu, r0 + 4096)
+        lab[r0:r1] = torch.argmax(X[r0:r1] @ Wt.T * 4.0, dim=1).to(torch.int32)
+    del Wt
+    big = min(nrows_per_gpu, batch_per_gpu * L)
+    x_full = torch.zeros(n, device="cuda", dtype=tdt)
+    xq = torch.zeros(n, device="cuda", dtype=tdt)              # the requested point, gathered
+    g_full = torch.zeros(n, device="cuda", dtype=tdt)
+    g_blk = torch.zeros(blk, device="cuda", dtype=tdt) if mode == "zero1" else g_full
+    work = torch.empty(lib.stochqn_b200_multinomial_work_size(max(batch_per_gpu, big), d, K), device="cuda", dtype=torch.uint8)
+    sw = {c: torch.full((c,), 1.0 / (c * world), device="cuda", dtype=tdt) for c in {batch_per_gpu, big}}
+    alpha = 1e-3
+    ws = lib.initialize_adaQN(blk, 10, 1, L, 0.0, 1e-4, 1e-4, rms, 1, 0.0, 1, 1)
+    assert ws, _lib.last_error(abi)
+    if mode == "zero1" and comm is not None:
+        assert lib.stochqn_b200_set_comm(ws, comm, n) == 0
+    x_ptr = x_full.data_ptr() + off * esz
+    req, task, info = C.c_void_p(), C.c_int(), C.c_int()
+    tasks, infos = {}, {}
+    state = dict(b=0)
+
+    def call():
+        lib.run_adaQN(step, x_ptr, 0.0, g_blk.data_ptr(), C.byref(req), C.byref(task), ws, C.byref(info))
+        tasks[task.value] = tasks.get(task.value, 0) + 1
+        infos[info.value] = infos.get(info.value, 0) + 1
+
+    def serve():
+        t = task.value
+        b = state["b"]
+        if t == 101:
+            state["b"] = b = (b + 1) % nb
+            r0, cnt = b * batch_per_gpu, batch_per_gpu
+        elif t == 103:
+            cnt = big
+            r0 = max(0, (b + 1) * batch_per_gpu - cnt)
+        else:
+            raise RuntimeError("unexpected task %d" % t)
+        if mode == "zero1":                                   # gather the point the request names (x, x_avg or x_avg_prev block)
+            lib.stochqn_b200_all_gather_real(comm, req.value, xq.data_ptr(), blk, None)
+            point = xq.data_ptr()
+        else:
+            point = req.value
+        # alpha / world per rank: the penalty term is added once in the sum over ranks
+        assert lib.stochqn_b200_multinomial_loss_grad(X.data_ptr() + r0 * d * esz, d, None, K, lab.data_ptr() + r0 * 4, sw[cnt].data_ptr(), cnt, d, K, 1,
+                                                      point, alpha / world, g_full.data_ptr(), None, work.data_ptr(), None) == 0
+        if mode == "zero1":
+            lib.stochqn_b200_reduce_scatter_real(comm, g_full.data_ptr(), g_blk.data_ptr(), blk, None)
+        else:
+            lib.stochqn_b200_allreduce_real(comm, g_full.data_ptr(), n, None)
+
+    call()
+    niter = lambda: int(ws.contents.niter)
+    while niter() < warm_cycles * L:
+        serve(); call()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    tasks.clear(); infos.clear()
+    it0 = niter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    while niter() < it0 + steps:
+        serve(); call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    if mode == "zero1":
+        lib.stochqn_b200_all_gather_real(comm, x_ptr, x_full.data_ptr(), blk, None)
+    torch.cuda.synchronize()
+    out = dict(config=name, optimizer="adaQN", mode=mode if world > 1 else "single", n_gpus=world, dtype="f64" if esz == 8 else "f32", n=n,
+               features=d, classes=K, batch_per_gpu=batch_per_gpu, global_batch=batch_per_gpu * world, steps=steps, ms_per_step=ms,
+               steps_per_s=1e3 / ms, samples_per_s=1e3 / ms * batch_per_gpu * world, tasks=tasks, infos=infos,
+               mem_used=int(ws.contents.bfgs_memory.contents.mem_used), x_norm=float(torch.linalg.vector_norm(x_full.double()).item()))
+    lib.dealloc_adaQN(ws)
+    if rank == 0 and not quiet:
+        print(json.dumps(out), flush=True)
+    xr = x_full.cpu().numpy().astype(np.float64) if return_x else None
+    if world > 1:
+        dist.barrier()
+        lib.stochqn_b200_comm_destroy(comm)
+    return out, xr
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("configs", nargs="*", default=["cfg1", "cfg2", "cfg3", "cfg5"])
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--rows-cfg2", type=int, default=1000000)
+    ap.add_argument("--mode", default="zero1", choices=["zero1", "allreduce"], help="cfg5s: how the row-sharded gradient is combined")
     a = ap.parse_args()
+    if "cfg5s" in a.configs:          # row-sharded config 5 (torch.distributed.run, one rank per GPU)
+        import torch.distributed as dist
+        run_multinomial_sharded("cfg5 row-sharded", np.float32, 8192, 4096, 1024, 16384, min(a.steps, 100), 10, 0.9, 1e-3, mode=a.mode)
+        if dist.is_initialized():
+            dist.destroy_process_group()
+        return
     if "cfg1" in a.configs:
         run_logistic("cfg1", "oLBFGS", 100000, 1000, 1000, a.steps)
     if "cfg2" in a.configs:

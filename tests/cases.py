@@ -31,12 +31,15 @@ CASES = [
     ("olbfgs_rosen_1k", "oLBFGS", dict(mem_size=10, hess_init=0.0, y_reg=0.0, min_curvature=1e-4, check_nan=1), _r(1024), 220, 1e-4),
     ("olbfgs_rosen_1001", "oLBFGS", dict(mem_size=10, hess_init=0.0, y_reg=0.0, min_curvature=1e-4, check_nan=1), _r(1001), 120, 1e-4),
     ("olbfgs_rosen_m20", "oLBFGS", dict(mem_size=20, hess_init=0.0, y_reg=0.0, min_curvature=0.0, check_nan=1), _r(777), 120, 1e-4),
+    ("olbfgs_rosen_m32", "oLBFGS", dict(mem_size=32, hess_init=0.0, y_reg=0.0, min_curvature=0.0, check_nan=1), _r(130), 150, 1e-4),
+    ("olbfgs_rosen_n2", "oLBFGS", dict(mem_size=3, hess_init=0.0, y_reg=0.0, min_curvature=1e-4, check_nan=1), _r(2), 60, 1e-4),
     ("olbfgs_logistic", "oLBFGS", dict(mem_size=5, hess_init=0.0, y_reg=0.0, min_curvature=1e-4, check_nan=1), _l, 120, 1e-1),
     # --- SQN -------------------------------------------------------------------------------------
     ("sqn_hv_quad", "SQN", dict(mem_size=3, bfgs_upd_freq=3, min_curvature=1e-4, use_grad_diff=0, y_reg=0.0, check_nan=1), _q, 80, 1e-2),
     ("sqn_gd_quad", "SQN", dict(mem_size=3, bfgs_upd_freq=3, min_curvature=1e-4, use_grad_diff=1, y_reg=0.0, check_nan=1), _q, 80, 1e-2),
     ("sqn_hv_logistic", "SQN", dict(mem_size=5, bfgs_upd_freq=5, min_curvature=1e-4, use_grad_diff=0, y_reg=0.0, check_nan=1), _l, 150, 1e-1),
     ("sqn_gd_logistic_yreg", "SQN", dict(mem_size=5, bfgs_upd_freq=5, min_curvature=0.0, use_grad_diff=1, y_reg=1e-4, check_nan=1), _l, 150, 1e-1),
+    ("sqn_gd_rosen_n3_m32", "SQN", dict(mem_size=32, bfgs_upd_freq=2, min_curvature=0.0, use_grad_diff=1, y_reg=0.0, check_nan=1), _r(3), 120, 1e-4),
     ("sqn_hv_rosen_L1", "SQN", dict(mem_size=4, bfgs_upd_freq=1, min_curvature=0.0, use_grad_diff=0, y_reg=0.0, check_nan=1), _r(300), 90, 1e-4),
     # --- adaQN -----------------------------------------------------------------------------------
     ("adaqn_fisher_logistic", "adaQN", dict(mem_size=5, fisher_size=20, bfgs_upd_freq=5, max_incr=1.01, min_curvature=1e-4,
@@ -47,8 +50,17 @@ CASES = [
                                         scal_reg=1e-4, rmsprop_weight=0.9, use_grad_diff=1, y_reg=0.0, check_nan=1), _l, 200, 1e-2),
     ("adaqn_gd_nomax_logistic", "adaQN", dict(mem_size=5, fisher_size=20, bfgs_upd_freq=5, max_incr=0.0, min_curvature=1e-4,
                                               scal_reg=1e-4, rmsprop_weight=0.9, use_grad_diff=1, y_reg=0.0, check_nan=1), _l, 200, 1e-2),
+    ("adaqn_fisher_rosen_m12", "adaQN", dict(mem_size=12, fisher_size=7, bfgs_upd_freq=2, max_incr=0.0, min_curvature=0.0,
+                                             scal_reg=1e-4, rmsprop_weight=0.5, use_grad_diff=0, y_reg=0.0, check_nan=1), _r(37), 120, 1e-5),
     ("adaqn_fisher_quad", "adaQN", dict(mem_size=3, fisher_size=5, bfgs_upd_freq=3, max_incr=1.01, min_curvature=1e-4,
                                         scal_reg=1e-4, rmsprop_weight=0.9, use_grad_diff=0, y_reg=0.0, check_nan=1), _q, 90, 5e-3),
 ]
 
 CASE_IDS = [c[0] for c in CASES]
+
+# Cases whose fp32 run is not comparable with anything: the REFERENCE's own fp32 build takes different branches
+# (different task / info sequence) from its fp64 build on them (checked with oracle/_ref: adaqn_fisher_rosen_m12
+# diverges discretely, 2e-2 apart in x).  They are exercised in fp64 only.
+FP64_ONLY = {"adaqn_fisher_rosen_m12"}
+CASES_FP32 = [c for c in CASES if c[0] not in FP64_ONLY]
+CASE_IDS_FP32 = [c[0] for c in CASES_FP32]

@@ -6,7 +6,7 @@ rel 1e-10 (fp64) or 1e-4 (fp32) of the reference algorithm.
 import numpy as np
 import pytest
 
-from cases import CASES, CASE_IDS
+from cases import CASES, CASE_IDS, CASES_FP32, CASE_IDS_FP32
 from cuda_stepper import CudaStepper
 from oracle import stochqn_np as O
 from oracle.driver import HostStepper, discrete, run_trace
@@ -87,7 +87,7 @@ def _rel_err(ta, tb):
     return worst
 
 
-@pytest.mark.parametrize("case", CASES, ids=CASE_IDS)
+@pytest.mark.parametrize("case", CASES_FP32, ids=CASE_IDS_FP32)
 def test_parity_fp32_device(case):
     """fp32 build against the fp64 oracle: rel 1e-4 (north_star).  A few cases amplify float rounding so
     much that the REFERENCE's own fp32 build is 1e-3..4e-2 away from its fp64 build (checked on CPU:

@@ -14,12 +14,14 @@ SHAPES = [("cfg1 batch 1000x1001", 1000, 1001), ("cfg2 batch 2000x4097", 2000, 4
           ("100000x1001", 100000, 1001), ("50000x4097", 50000, 4097)]
 
 
-def run(dtype):
+def run(dtype, only=None):
     abi = _lib.load(dtype)
     lib = abi.lib
     tdt = torch.float64 if dtype == np.float64 else torch.float32
     esz = 8 if dtype == np.float64 else 4
     for name, B, d in SHAPES:
+        if only and only not in name:
+            continue
         nbatches = max(2, min(64, int(3e9 // (B * d * esz))))        # rotate over > L2 worth of batches
         X = torch.randn(nbatches * B, d, device="cuda", dtype=tdt) / d ** 0.5
         y = (torch.rand(nbatches * B, device="cuda") < 0.5).to(tdt)
@@ -61,5 +63,7 @@ def run(dtype):
 
 
 if __name__ == "__main__":
-    for dt in (np.float64, np.float32):
-        run(dt)
+    only = sys.argv[1] if len(sys.argv) > 1 else None            # substring of a shape name
+    dts = [np.float64] if (len(sys.argv) > 2 and sys.argv[2] == "f64") else [np.float64, np.float32]
+    for dt in dts:
+        run(dt, only)

@@ -1,0 +1,108 @@
+"""Guided mode on the GPU: stochqn_b200.guided over the CUDA library, with the data, the variables and the
+callbacks on the device, against what the REFERENCE's guided classes produced on the same seeded data
+(tests/golden/guided_f64.json).  Task / info / return sequences must be identical, iterates within 1e-9."""
+import json
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+from guided_support import GUIDED_CASES, GUIDED_IDS, drive
+from stochqn_b200 import guided
+
+pytestmark = pytest.mark.gpu
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "guided_f64.json")))
+
+
+def _torch_callbacks():
+    import torch
+
+    def wts(X, sw):
+        return torch.ones(X.shape[0], dtype=X.dtype, device=X.device) if sw is None else sw.reshape(-1)
+
+    def grad(w, X, y, sample_weight=None, reg_param=0.0):
+        sw = wts(X, sample_weight)
+        return X.T @ ((torch.sigmoid(X @ w) - y) * sw) / sw.sum() + 2.0 * reg_param * w
+
+    def hess_vec(w, v, X, y, sample_weight=None, reg_param=0.0):
+        sw = wts(X, sample_weight)
+        p = torch.sigmoid(X @ w)
+        return X.T @ (p * (1.0 - p) * sw * (X @ v)) / sw.sum() + 2.0 * reg_param * v
+
+    def obj(w, X, y, sample_weight=None, reg_param=0.0):
+        sw = wts(X, sample_weight)
+        z = X @ w
+        ll = torch.logaddexp(torch.zeros_like(z), z) - y * z
+        return float(((ll * sw).sum() / sw.sum() + reg_param * (w @ w)).item())
+
+    return grad, hess_vec, obj
+
+
+class _Recorder:
+    """Wraps a free-mode optimizer to record (task, info, ret) of every call, as the golden file does."""
+
+    def __init__(self, inner):
+        self.__dict__["inner"] = inner
+        self.__dict__["trace"] = []
+
+    def __getattr__(self, k):
+        return getattr(self.inner, k)
+
+    def __setattr__(self, k, v):
+        setattr(self.inner, k, v)
+
+    def run_optimizer(self, x, step):
+        from guided_support import INFOS, TASKS
+        r = self.inner.run_optimizer(x, step)
+        t = {v: k for k, v in TASKS.items()}[r["task"]]
+        i = {v: k for k, v in INFOS.items()}[r["info"]["iteration_info"]]
+        self.trace.append([t, i, int(r["info"]["x_changed_in_run"])])
+        return r
+
+
+def _recorded(kind):
+    base = getattr(guided, kind)
+    free = base._free_class()
+    return type(kind, (base,), {"_free_class": staticmethod(lambda: (lambda *a, **k: _Recorder(free(*a, **k))))})
+
+
+@pytest.mark.parametrize("container", ["cuda", "numpy"])
+@pytest.mark.parametrize("name,kind,okw,how", GUIDED_CASES, ids=GUIDED_IDS)
+def test_guided_cuda_matches_reference(name, kind, okw, how, container):
+    import torch
+
+    if container == "cuda":
+        conv = lambda a: torch.tensor(a, device="cuda")
+        cbs = _torch_callbacks()
+    else:
+        conv, cbs = (lambda a: a), None        # the reference's own calling convention: NumPy in, NumPy callbacks
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        obj, snaps = drive(_recorded(kind), name, okw, how, to_array=conv, callbacks=cbs)
+    g = GOLD[name]
+    assert obj.optimizer.trace == g["calls"]
+    assert obj.niter == g["niter"] and obj.epoch == g["epoch"]
+    x = obj.x.cpu().numpy() if container == "cuda" else obj.x
+    scale = max(1.0, float(np.max(np.abs(g["x"]))))
+    assert len(snaps) == len(g["snaps"])
+    for a, b in zip(snaps, g["snaps"]):
+        assert np.max(np.abs(a - np.asarray(b))) / scale <= 1e-9
+    assert np.max(np.abs(x - np.asarray(g["x"]))) / scale <= 1e-9
+
+
+def test_long_batch_view_on_device():
+    import torch
+
+    X = torch.randn(400, 7, device="cuda", dtype=torch.float64)
+    y = torch.randn(400, device="cuda", dtype=torch.float64)
+    st = guided._RowStash()
+    for r0, r1 in ((40, 100), (100, 260), (260, 300)):
+        st.push(X[r0:r1], y[r0:r1], None)
+    Xl, yl, _ = st.pop_all()
+    assert Xl.data_ptr() == X[40:].data_ptr() and Xl.shape == (260, 7) and torch.equal(Xl, X[40:300])
+    assert yl.data_ptr() == y[40:].data_ptr() and torch.equal(yl, y[40:300])
+    st.push(X[0:10], y[0:10], None)
+    st.push(X[30:50], y[30:50], None)
+    Xl, _, _ = st.pop_all()
+    assert torch.equal(Xl, torch.cat([X[0:10], X[30:50]]))

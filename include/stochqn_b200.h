@@ -142,6 +142,25 @@ int stochqn_b200_logistic_loss(const real_t *X, long long ldx, const real_t *y, 
                                long long nrows, long long ncols, const real_t *w, real_t lambda,
                                double *loss_dev, void *work, void *stream);
 
+/* The same three closed forms in the conventions of the scikit-learn (<= 1.0) private functions the reference's Python
+   layer calls for two-class problems (stochqn/_logistic.py:23-30: _logistic_loss_and_grad, _logistic_grad_hess):
+   labels y in {-1,+1}; SUMS over samples (the caller pre-normalises sw, stochqn/_logistic.py:167); w has
+   ncols + fit_intercept entries, the intercept LAST and unpenalised; penalty alpha/2 * |w[:ncols]|^2.  With
+   z_i = x_i'w[:ncols] + intercept and q_i = sigmoid(y_i z_i):
+     loss     = -sum_i sw_i log q_i + alpha/2 |w[:ncols]|^2
+     grad     = [ X'r + alpha w[:ncols] ; sum(r) ]            r_i = sw_i (q_i - 1) y_i
+     hess_vec = [ X'r + alpha v[:ncols] ; sum(r) ]            r_i = sw_i q_i (1 - q_i) (x_i'v[:ncols] + v[ncols])
+   Same kernels, same `work` size as above (one sweep of the batch for ncols <= 5120). */
+int stochqn_b200_logistic_sk_grad(const real_t *X, long long ldx, const real_t *y, const real_t *sw,
+                                  long long nrows, long long ncols, int fit_intercept, const real_t *w,
+                                  real_t alpha, real_t *grad, void *work, void *stream);
+int stochqn_b200_logistic_sk_hess_vec(const real_t *X, long long ldx, const real_t *y, const real_t *sw,
+                                      long long nrows, long long ncols, int fit_intercept, const real_t *w,
+                                      const real_t *v, real_t alpha, real_t *hess_vec, void *work, void *stream);
+int stochqn_b200_logistic_sk_loss(const real_t *X, long long ldx, const real_t *y, const real_t *sw,
+                                  long long nrows, long long ncols, int fit_intercept, const real_t *w,
+                                  real_t alpha, double *loss_dev, void *work, void *stream);
+
 /* Sharded gradient in ONE launch: the halo exchange is fused into the gradient kernel (CTA 0 exchanges the shard
    ends over the communicator's peer-memory mailboxes while the other CTAs stream; falls back to
    stochqn_b200_rosenbrock_halo + stochqn_b200_rosenbrock_grad when the communicator has no peer-memory path).

@@ -25,6 +25,7 @@ EXT_SYMBOLS = (
     "stochqn_b200_rosenbrock_grad_sharded",
     "stochqn_b200_logistic_work_size", "stochqn_b200_logistic_grad", "stochqn_b200_logistic_hess_vec",
     "stochqn_b200_logistic_loss", "stochqn_b200_export", "stochqn_b200_import",
+    "stochqn_b200_logistic_sk_grad", "stochqn_b200_logistic_sk_hess_vec", "stochqn_b200_logistic_sk_loss",
     "stochqn_b200_multinomial_work_size", "stochqn_b200_multinomial_loss_grad", "stochqn_b200_multinomial_hess_vec",
     "stochqn_b200_gemm_tn",
 )
@@ -91,6 +92,9 @@ def load(dtype=np.float64) -> StochqnABI:
     lib.stochqn_b200_logistic_grad.argtypes = [vp, ll, vp, vp, ll, ll, vp, real, vp, vp, vp]
     lib.stochqn_b200_logistic_hess_vec.argtypes = [vp, ll, vp, vp, ll, ll, vp, vp, real, vp, vp, vp]
     lib.stochqn_b200_logistic_loss.argtypes = [vp, ll, vp, vp, ll, ll, vp, real, vp, vp, vp]
+    lib.stochqn_b200_logistic_sk_grad.argtypes = [vp, ll, vp, vp, ll, ll, ci, vp, real, vp, vp, vp]
+    lib.stochqn_b200_logistic_sk_hess_vec.argtypes = [vp, ll, vp, vp, ll, ll, ci, vp, vp, real, vp, vp, vp]
+    lib.stochqn_b200_logistic_sk_loss.argtypes = [vp, ll, vp, vp, ll, ll, ci, vp, real, vp, vp, vp]
     lib.stochqn_b200_multinomial_work_size.argtypes = [ll, ll, ll]
     lib.stochqn_b200_multinomial_work_size.restype = sz
     lib.stochqn_b200_multinomial_loss_grad.argtypes = [vp, ll, vp, ll, vp, vp, ll, ll, ll, ci, vp, real, vp, vp, vp, vp]

@@ -219,13 +219,38 @@ rosen_fun_kernel(const real_t* __restrict__ x, long long n, long long offset, lo
 // pass B: one thread per column: out[col] = sum_rows r_row X[row][col] / sum(sw) + 2*lambda*u[col]
 enum { LG_GRAD = 0, LG_HVP = 1, LG_LOSS = 2 };
 
+// Two conventions share the kernels:
+//   sk = 0  R/logistic.R:1-37: y in {0,1}, weighted MEANS, penalty lambda*|w|^2 on every coefficient (the intercept is a
+//           column of X);
+//   sk = 1  scikit-learn (<= 1.0) _logistic_loss_and_grad / _logistic_grad_hess, which the reference's Python layer calls
+//           (stochqn/_logistic.py:23-30): y in {-1,+1}, weighted SUMS, penalty alpha/2*|w[:ncols]|^2, and with icpt = 1
+//           an unpenalised intercept stored LAST in w (w has ncols + 1 entries; z = x'w[:ncols] + w[ncols]).
+struct LgForm { int sk; int icpt; };
+
+__device__ __forceinline__ double lg_row_weight(int kind, const LgForm f, double z, double t, double yy, double wt)
+{
+    if (!f.sk) {
+        const double p = 1.0 / (1.0 + exp(-z));
+        if (kind == LG_GRAD) return (p - yy) * wt;
+        if (kind == LG_HVP) return p * (1.0 - p) * wt * t;
+        return -(yy * log(p) + (1.0 - yy) * log(1.0 - p)) * wt;
+    }
+    const double yz = yy * z;
+    const double q = 1.0 / (1.0 + exp(-yz));
+    if (kind == LG_GRAD) return wt * (q - 1.0) * yy;
+    if (kind == LG_HVP) return wt * q * (1.0 - q) * t;
+    return wt * (yz > 0 ? log1p(exp(-yz)) : -yz + log1p(exp(yz)));        // -log sigmoid(yz)
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(kT)
 logistic_rows_kernel(const real_t* __restrict__ X, long long ldx, const real_t* __restrict__ y,
                      const real_t* __restrict__ sw, long long nrows, long long ncols,
-                     const real_t* __restrict__ w, const real_t* __restrict__ v, double* __restrict__ r)
+                     const real_t* __restrict__ w, const real_t* __restrict__ v, double* __restrict__ r, const LgForm form)
 {
     const int lane = threadIdx.x & 31;
+    const double zc = form.icpt ? (double) w[ncols] : 0.0;
+    const double tc = (form.icpt && KIND == LG_HVP) ? (double) v[ncols] : 0.0;
     const long long warp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long) gridDim.x * blockDim.x) >> 5;
     for (long long row = warp; row < nrows; row += nwarps) {
@@ -241,11 +266,8 @@ logistic_rows_kernel(const real_t* __restrict__ X, long long ldx, const real_t* 
             if (KIND == LG_HVP) t += __shfl_down_sync(0xffffffffu, t, o);
         }
         if (lane == 0) {
-            const double p = 1.0 / (1.0 + exp(-z));
             const double wt = sw ? (double) sw[row] : 1.0;
-            if (KIND == LG_GRAD) r[row] = (p - (double) y[row]) * wt;
-            else if (KIND == LG_HVP) r[row] = p * (1.0 - p) * wt * t;
-            else { const double yy = (double) y[row]; r[row] = -(yy * log(p) + (1.0 - yy) * log(1.0 - p)) * wt; }
+            r[row] = lg_row_weight(KIND, form, z + zc, t + tc, (double) y[row], wt);
         }
     }
 }
@@ -287,17 +309,19 @@ logistic_cols_kernel(const real_t* __restrict__ X, long long ldx, long long nrow
 __global__ void __launch_bounds__(kT)
 logistic_finish_kernel(const double* __restrict__ colpart, int slices, long long nrows, long long ncols,
                        const double* __restrict__ r, const real_t* __restrict__ u, real_t lambda,
-                       real_t* __restrict__ out)
+                       real_t* __restrict__ out, const LgForm form)
 {
     const long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == ncols && form.icpt) { out[c] = (real_t) r[nrows + 1]; return; }       // intercept: sum of the row weights
     if (c >= ncols) return;
     double acc = 0;
     for (int s = 0; s < slices; ++s) acc += colpart[(long long) s * ncols + c];
-    out[c] = (real_t) (acc / r[nrows] + 2.0 * (double) lambda * (double) u[c]);
+    out[c] = form.sk ? (real_t) (acc + (double) lambda * (double) u[c])
+                     : (real_t) (acc / r[nrows] + 2.0 * (double) lambda * (double) u[c]);
 }
 
 __global__ void logistic_loss_finish_kernel(const double* __restrict__ r, long long nrows, const real_t* __restrict__ w,
-                                            long long ncols, real_t lambda, double* __restrict__ loss)
+                                            long long ncols, real_t lambda, double* __restrict__ loss, const LgForm form)
 {
     double a = 0;
     for (long long i = threadIdx.x; i < ncols; i += blockDim.x) { const double wv = (double) w[i]; a = fma(wv, wv, a); }
@@ -308,7 +332,7 @@ __global__ void logistic_loss_finish_kernel(const double* __restrict__ r, long l
     if (threadIdx.x == 0) {
         double s = 0;
         for (unsigned k = 0; k < blockDim.x / 32; ++k) s += ra[k];
-        *loss = r[nrows + 1] / r[nrows] + (double) lambda * s;
+        *loss = form.sk ? r[nrows + 1] + 0.5 * (double) lambda * s : r[nrows + 1] / r[nrows] + (double) lambda * s;
     }
 }
 
@@ -333,7 +357,8 @@ template <int CPT, int KIND, int R, int MINB>
 __global__ void __launch_bounds__(LT, MINB)
 logistic_fused_kernel(const real_t* __restrict__ X, long long ldx, const real_t* __restrict__ y,
                       const real_t* __restrict__ sw, long long nrows, long long ncols,
-                      const real_t* __restrict__ w, const real_t* __restrict__ v, double* __restrict__ colpart)
+                      const real_t* __restrict__ w, const real_t* __restrict__ v, double* __restrict__ colpart,
+                      const LgForm form)
 {
     extern __shared__ __align__(16) unsigned char lg_smem[];
     real_t* ws = reinterpret_cast<real_t*>(lg_smem);              // w (and v) staged once per CTA: [CPT*LT] each
@@ -347,7 +372,9 @@ logistic_fused_kernel(const real_t* __restrict__ X, long long ldx, const real_t*
         if (KIND == LG_HVP) vs[tid + k * LT] = c < ncols ? v[c] : (real_t) 0;
         acc[k] = (real_t) 0;
     }
-    double sw_sum = 0.0;
+    double sw_sum = 0.0, r_sum = 0.0;
+    const double zc = form.icpt ? (double) w[ncols] : 0.0;
+    const double tc = (form.icpt && KIND == LG_HVP) ? (double) v[ncols] : 0.0;
     __shared__ double red[2][2][LT / 32][R];
     int par = 0;
     // (each thread reads back only the w / v entries it wrote itself: no barrier needed before the loop)
@@ -396,10 +423,9 @@ logistic_fused_kernel(const real_t* __restrict__ X, long long ldx, const real_t*
             for (int q = 0; q < LT / 32; ++q) { z += red[par][0][q][r]; if (KIND == LG_HVP) t += red[par][1][q][r]; }
             double rr = 0.0;
             if (row < nrows) {
-                const double p = 1.0 / (1.0 + exp(-z));
                 const double wt = sw ? (double) sw[row] : 1.0;
-                rr = (KIND == LG_GRAD) ? (p - (double) y[row]) * wt : p * (1.0 - p) * wt * t;
-                if (tid == 0) sw_sum += wt;
+                rr = lg_row_weight(KIND, form, z + zc, t + tc, (double) y[row], wt);
+                if (tid == 0) { sw_sum += wt; r_sum += rr; }
             }
             const real_t rt = (real_t) rr;
             #pragma unroll
@@ -407,32 +433,40 @@ logistic_fused_kernel(const real_t* __restrict__ X, long long ldx, const real_t*
         }
         par ^= 1;
     }
-    double* out = colpart + (size_t) blockIdx.x * (size_t) (ncols + 1);
+    double* out = colpart + (size_t) blockIdx.x * (size_t) (ncols + 2);
     #pragma unroll
     for (int k = 0; k < CPT; ++k) {
         const long long c = tid + (long long) k * LT;
         if (c < ncols) out[c] = (double) acc[k];
     }
-    if (tid == 0) out[ncols] = sw_sum;
+    if (tid == 0) { out[ncols] = sw_sum; out[ncols + 1] = r_sum; }
 }
 
 __global__ void __launch_bounds__(kT)
 logistic_fused_finish(const double* __restrict__ colpart, int nparts, long long ncols, const real_t* __restrict__ u,
-                      real_t lambda, real_t* __restrict__ out)
+                      real_t lambda, real_t* __restrict__ out, const LgForm form)
 {
     const long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncols) return;
+    if (c > ncols || (c == ncols && !form.icpt)) return;
+    const size_t rec = (size_t) (ncols + 2);
+    if (c == ncols) {                                       // intercept: sum of the row weights, CTA order
+        double rs = 0;
+        for (int b = 0; b < nparts; ++b) rs += colpart[(size_t) b * rec + ncols + 1];
+        out[c] = (real_t) rs;
+        return;
+    }
     double acc = 0, swt = 0;
     for (int b = 0; b < nparts; ++b) {
-        acc += colpart[(size_t) b * (size_t) (ncols + 1) + c];
-        swt += colpart[(size_t) b * (size_t) (ncols + 1) + ncols];
+        acc += colpart[(size_t) b * rec + c];
+        swt += colpart[(size_t) b * rec + ncols];
     }
-    out[c] = (real_t) (acc / swt + 2.0 * (double) lambda * (double) u[c]);
+    out[c] = form.sk ? (real_t) (acc + (double) lambda * (double) u[c])
+                     : (real_t) (acc / swt + 2.0 * (double) lambda * (double) u[c]);
 }
 
 template <int C, int KIND, int R, int MINB>
 void launch_logistic_fused_t(const real_t* X, long long ldx, const real_t* y, const real_t* sw, long long nrows, long long ncols,
-                             const real_t* w, const real_t* v, double* colpart, int* nparts, int sms, cudaStream_t st)
+                             const real_t* w, const real_t* v, double* colpart, int* nparts, int sms, cudaStream_t st, LgForm form)
 {
     auto kern = logistic_fused_kernel<C, KIND, R, MINB>;
     const size_t smem = (size_t) (KIND == LG_HVP ? 2 : 1) * C * LT * sizeof(real_t);
@@ -442,13 +476,13 @@ void launch_logistic_fused_t(const real_t* X, long long ldx, const real_t* y, co
     const int cap = MINB * sms < kLgMaxGrid ? MINB * sms : kLgMaxGrid;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
-    kern<<<(unsigned) g, LT, smem, st>>>(X, ldx, y, sw, nrows, ncols, w, v, colpart);
+    kern<<<(unsigned) g, LT, smem, st>>>(X, ldx, y, sw, nrows, ncols, w, v, colpart, form);
     *nparts = (int) g;
 }
 
 template <int KIND>
 bool launch_logistic_fused(const real_t* X, long long ldx, const real_t* y, const real_t* sw, long long nrows, long long ncols,
-                           const real_t* w, const real_t* v, double* colpart, int* nparts, cudaStream_t st)
+                           const real_t* w, const real_t* v, double* colpart, int* nparts, cudaStream_t st, LgForm form)
 {
     const int cpt = (int) ((ncols + LT - 1) / LT);
     if (cpt > kLgMaxCpt) return false;
@@ -456,7 +490,7 @@ bool launch_logistic_fused(const real_t* X, long long ldx, const real_t* y, cons
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms < 1) sms = 148; }
     static int variant = -1;
     if (variant < 0) { const char* e = getenv("STOCHQN_B200_LG_VARIANT"); variant = e ? atoi(e) : 0; }
-#define LG_ARGS X, ldx, y, sw, nrows, ncols, w, v, colpart, nparts, sms, st
+#define LG_ARGS X, ldx, y, sw, nrows, ncols, w, v, colpart, nparts, sms, st, form
 #define LG_CASE(C) if (cpt <= C) { launch_logistic_fused_t<C, KIND, lg_rows(C), 2>(LG_ARGS); return true; }
     // wide rows (measured on B200, tools/probe_logistic.py, STOCHQN_B200_LG_VARIANT is a dev switch):
     //   fp64, big batches : two CTAs per SM with 2 rows in flight each (6.0 TB/s at 50000 x 4097; a few spilled bytes)
@@ -565,38 +599,39 @@ int stochqn_b200_rosenbrock_halo(const real_t* x, long long n_local, int rank, i
 size_t stochqn_b200_logistic_work_size(long long nrows, long long ncols)
 {
     const long long two_sweep = (long long) row_slices(nrows) * ncols;
-    const long long fused = (long long) kLgMaxGrid * (ncols + 1);
+    const long long fused = (long long) kLgMaxGrid * (ncols + 2);
     return sizeof(double) * (size_t) (nrows + 2 + (two_sweep > fused ? two_sweep : fused));
 }
 
 static int logistic_common(int kind, const real_t* X, long long ldx, const real_t* y, const real_t* sw,
                            long long nrows, long long ncols, const real_t* w, const real_t* v, real_t lambda,
-                           real_t* out, double* loss, void* work, cudaStream_t st)
+                           real_t* out, double* loss, void* work, cudaStream_t st, LgForm form = LgForm{0, 0})
 {
     double* r = (double*) work;
+    const long long nout = ncols + (form.icpt ? 1 : 0);
     double* colpart = r + nrows + 2;
     if (kind != LG_LOSS && !getenv("STOCHQN_B200_LOGISTIC_TWO_SWEEP")) {      // one sweep of the batch (ncols <= 5120)
         int nparts = 0;
-        const bool done = kind == LG_GRAD ? launch_logistic_fused<LG_GRAD>(X, ldx, y, sw, nrows, ncols, w, v, colpart, &nparts, st)
-                                          : launch_logistic_fused<LG_HVP>(X, ldx, y, sw, nrows, ncols, w, v, colpart, &nparts, st);
+        const bool done = kind == LG_GRAD ? launch_logistic_fused<LG_GRAD>(X, ldx, y, sw, nrows, ncols, w, v, colpart, &nparts, st, form)
+                                          : launch_logistic_fused<LG_HVP>(X, ldx, y, sw, nrows, ncols, w, v, colpart, &nparts, st, form);
         if (done) {
-            logistic_fused_finish<<<(unsigned) ((ncols + kT - 1) / kT), kT, 0, st>>>(colpart, nparts, ncols, kind == LG_HVP ? v : w, lambda, out);
+            logistic_fused_finish<<<(unsigned) ((nout + kT - 1) / kT), kT, 0, st>>>(colpart, nparts, ncols, kind == LG_HVP ? v : w, lambda, out, form);
             return check_launch("logistic (fused)", 2);
         }
     }
     const int g_rows = grid_1d(nrows * 32);
-    if (kind == LG_GRAD) logistic_rows_kernel<LG_GRAD><<<g_rows, kT, 0, st>>>(X, ldx, y, sw, nrows, ncols, w, v, r);
-    else if (kind == LG_HVP) logistic_rows_kernel<LG_HVP><<<g_rows, kT, 0, st>>>(X, ldx, y, sw, nrows, ncols, w, v, r);
-    else logistic_rows_kernel<LG_LOSS><<<g_rows, kT, 0, st>>>(X, ldx, y, sw, nrows, ncols, w, v, r);
+    if (kind == LG_GRAD) logistic_rows_kernel<LG_GRAD><<<g_rows, kT, 0, st>>>(X, ldx, y, sw, nrows, ncols, w, v, r, form);
+    else if (kind == LG_HVP) logistic_rows_kernel<LG_HVP><<<g_rows, kT, 0, st>>>(X, ldx, y, sw, nrows, ncols, w, v, r, form);
+    else logistic_rows_kernel<LG_LOSS><<<g_rows, kT, 0, st>>>(X, ldx, y, sw, nrows, ncols, w, v, r, form);
     logistic_norm_kernel<<<1, kT, 0, st>>>(sw, nrows, r);
     if (kind == LG_LOSS) {
-        logistic_loss_finish_kernel<<<1, kT, 0, st>>>(r, nrows, w, ncols, lambda, loss);
+        logistic_loss_finish_kernel<<<1, kT, 0, st>>>(r, nrows, w, ncols, lambda, loss, form);
     } else {
         const int slices = row_slices(nrows);
         dim3 grid((unsigned) ((ncols + kT - 1) / kT), (unsigned) slices);
         logistic_cols_kernel<<<grid, kT, 0, st>>>(X, ldx, nrows, ncols, r, colpart);
-        logistic_finish_kernel<<<(unsigned) ((ncols + kT - 1) / kT), kT, 0, st>>>(colpart, slices, nrows, ncols, r,
-                                                                                  kind == LG_HVP ? v : w, lambda, out);
+        logistic_finish_kernel<<<(unsigned) ((nout + kT - 1) / kT), kT, 0, st>>>(colpart, slices, nrows, ncols, r,
+                                                                                 kind == LG_HVP ? v : w, lambda, out, form);
     }
     return check_launch("logistic", kind == LG_LOSS ? 3 : 4);
 }
@@ -618,6 +653,31 @@ int stochqn_b200_logistic_loss(const real_t* X, long long ldx, const real_t* y, 
                                long long ncols, const real_t* w, real_t lambda, double* loss_dev, void* work, void* stream)
 {
     return logistic_common(LG_LOSS, X, ldx, y, sw, nrows, ncols, w, nullptr, lambda, nullptr, loss_dev, work, (cudaStream_t) stream);
+}
+
+// scikit-learn (<= 1.0) conventions: see LgForm above and include/stochqn_b200.h
+int stochqn_b200_logistic_sk_grad(const real_t* X, long long ldx, const real_t* y, const real_t* sw, long long nrows,
+                                  long long ncols, int fit_intercept, const real_t* w, real_t alpha, real_t* grad,
+                                  void* work, void* stream)
+{
+    return logistic_common(LG_GRAD, X, ldx, y, sw, nrows, ncols, w, nullptr, alpha, grad, nullptr, work, (cudaStream_t) stream,
+                           LgForm{1, fit_intercept ? 1 : 0});
+}
+
+int stochqn_b200_logistic_sk_hess_vec(const real_t* X, long long ldx, const real_t* y, const real_t* sw, long long nrows,
+                                      long long ncols, int fit_intercept, const real_t* w, const real_t* v, real_t alpha,
+                                      real_t* hess_vec, void* work, void* stream)
+{
+    return logistic_common(LG_HVP, X, ldx, y, sw, nrows, ncols, w, v, alpha, hess_vec, nullptr, work, (cudaStream_t) stream,
+                           LgForm{1, fit_intercept ? 1 : 0});
+}
+
+int stochqn_b200_logistic_sk_loss(const real_t* X, long long ldx, const real_t* y, const real_t* sw, long long nrows,
+                                  long long ncols, int fit_intercept, const real_t* w, real_t alpha, double* loss_dev,
+                                  void* work, void* stream)
+{
+    return logistic_common(LG_LOSS, X, ldx, y, sw, nrows, ncols, w, nullptr, alpha, nullptr, loss_dev, work, (cudaStream_t) stream,
+                           LgForm{1, fit_intercept ? 1 : 0});
 }
 
 }  // extern "C"

@@ -116,3 +116,37 @@ def test_logistic_batch_is_a_row_range_view():
                                           g.data_ptr(), work.data_ptr(), None) == 0
     gr, _, _ = _logistic_np(X[r0:r1], y[r0:r1], None, w, w, 1e-5)
     assert np.max(np.abs(g.cpu().numpy() - gr)) <= 1e-12 * np.max(np.abs(gr))
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 2e-5)])
+@pytest.mark.parametrize("shape", [(1, 1), (7, 3), (1000, 1000), (257, 64), (600, 4096), (300, 5300)])
+@pytest.mark.parametrize("weighted,fit_intercept", [(False, True), (True, False), (True, True)])
+def test_logistic_sklearn_conventions(dtype, tol, shape, weighted, fit_intercept):
+    """stochqn_b200_logistic_sk_* against the restatement of scikit-learn <= 1.0's _logistic_loss_and_grad /
+    _logistic_grad_hess (oracle/logistic_sk_np.py): y in {-1,+1}, sums, intercept last and unpenalised.
+    Covers the fused one-sweep kernel (ncols <= 5120) and the two-sweep form (5300 columns)."""
+    import torch
+    from stochqn_b200 import logistic as L
+    from oracle import logistic_sk_np as LS
+
+    B, d = shape
+    rng = np.random.default_rng(B * 11 + d)
+    X = (rng.standard_normal((B, d)) / np.sqrt(d)).astype(dtype)
+    w = rng.standard_normal(d + fit_intercept).astype(dtype)
+    v = rng.standard_normal(d + fit_intercept).astype(dtype)
+    y = np.where(rng.random(B) < 0.5, 1.0, -1.0).astype(dtype)
+    sw = (rng.random(B) + 0.5).astype(dtype) if weighted else None
+    if sw is not None:
+        sw /= sw.sum()
+    alpha = 0.3
+    Xd, wd, vd, yd = _t(X, dtype), _t(w, dtype), _t(v, dtype), _t(y, dtype)
+    swd = _t(sw, dtype) if weighted else None
+    g = L.grad_fun_bin(wd, Xd, yd, sample_weight=swd, reg_param=alpha).cpu().numpy()
+    hv = L.hessvec_fun_bin(wd, vd, Xd, yd, sample_weight=swd, reg_param=alpha).cpu().numpy()
+    loss = L.obj_fun_bin(wd, Xd, yd, sample_weight=swd, reg_param=alpha)
+    f64 = lambda a: None if a is None else a.astype(np.float64)
+    lr, gr = LS.logistic_loss_and_grad(f64(w), f64(X), f64(y), alpha, f64(sw))
+    hr = LS.logistic_hess_vec(f64(w), f64(v), f64(X), f64(y), alpha, f64(sw))
+    assert np.max(np.abs(g - gr)) <= tol * max(np.max(np.abs(gr)), 1e-3) * 10
+    assert np.max(np.abs(hv - hr)) <= tol * max(np.max(np.abs(hr)), 1e-3) * 10
+    assert abs(loss - lr) <= max(tol, 1e-12) * abs(lr) * 10

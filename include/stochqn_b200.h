@@ -57,7 +57,11 @@ enum stochqn_b200_option {
        still be running, and the results are final in the order of the workspace stream - enqueue the next
        gradient evaluation on that stream (or synchronise it) as with any CUDA library.  1: drain the stream
        before every return, the reference's contract.  Host-pointer calls always return with everything final. */
-    STOCHQN_B200_OPT_SYNC_RETURN = 4
+    STOCHQN_B200_OPT_SYNC_RETURN = 4,
+    /* oLBFGS / SQN: largest n for which a step is ONE cooperative launch (dots, solve and update fused - for the
+       latency-bound sizes where three launches and the flag round trip dominate) instead of K1 -> K2 -> K3.
+       Default 32768 (environment: STOCHQN_B200_SMALL_N); 0 disables.  Not used when the optimizer is sharded. */
+    STOCHQN_B200_OPT_ONE_LAUNCH_MAX_N = 5
 };
 int stochqn_b200_set_option(void *ws, int option, long long value);
 
@@ -67,7 +71,10 @@ enum stochqn_b200_stat {
     STOCHQN_B200_STAT_K4_MS = 5, STOCHQN_B200_STAT_K4_COUNT = 6,
     STOCHQN_B200_STAT_LAST_BOUND = 7,                                 /* bound on ||direction|| of the last step */
     STOCHQN_B200_STAT_EXACT_NORM_STEPS = 8,                           /* steps that needed the exact-norm (two-pass) route */
-    STOCHQN_B200_STAT_KA2_MS = 9, STOCHQN_B200_STAT_KA2_COUNT = 10    /* adaQN: the second dot pass (K1/K3 slots hold KA1/KA3) */
+    STOCHQN_B200_STAT_KA2_MS = 9, STOCHQN_B200_STAT_KA2_COUNT = 10,   /* adaQN: the second dot pass (K1/K3 slots hold KA1/KA3) */
+    /* steps taken by the one-launch kernel used for latency-bound sizes (n <= 32768 unless STOCHQN_B200_SMALL_N
+       says otherwise; 0 there disables it): dots, solve and update in one cooperative launch instead of three */
+    STOCHQN_B200_STAT_ONE_LAUNCH_STEPS = 11
 };
 int stochqn_b200_get_stat(void *ws, int what, double *out);
 

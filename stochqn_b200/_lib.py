@@ -34,9 +34,11 @@ OPT_GRAD_WRITEBACK = 1
 OPT_TRUST_X_MIRROR = 2
 OPT_PROFILE = 3
 OPT_SYNC_RETURN = 4
+OPT_ONE_LAUNCH_MAX_N = 5
 STAT_K1_MS, STAT_K1_COUNT, STAT_K3_MS, STAT_K3_COUNT, STAT_K4_MS, STAT_K4_COUNT, STAT_LAST_BOUND = 1, 2, 3, 4, 5, 6, 7
 STAT_EXACT_NORM_STEPS = 8
 STAT_KA2_MS, STAT_KA2_COUNT = 9, 10
+STAT_ONE_LAUNCH_STEPS = 11
 
 
 def lib_path(dtype) -> str:

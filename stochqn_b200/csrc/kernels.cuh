@@ -265,92 +265,133 @@ __device__ __forceinline__ void reduce_partials(const double* __restrict__ parti
     }
 }
 
-__global__ void __launch_bounds__(kThreads)
-k2_solve(SolveArgs A, PeerArgs pa, const double* __restrict__ partials, double* sums,
-         double* __restrict__ SY, double* __restrict__ YY, double* __restrict__ SS,
-         double* __restrict__ coef, int* __restrict__ status_dev, volatile int* status_host,
-         volatile double* info_host, volatile unsigned long long* seq_host)
-{
-    const int m = A.msize, used = A.used;
-    const int P = 4 * m + 2;
-    if (A.nblocks > 0) { reduce_partials(partials, A.nblocks, P, sums); __syncthreads(); }
-    bool comm_ok = true;
-    if (pa.world > 1) comm_ok = p2p_allreduce_cta(pa, sums, P);      // sharded: sum the records of all ranks (p2p.cuh)
-    if (!A.do_solve) return;
+// The solve proper, shared by k2_solve (one CTA after K1) and ks_step (every CTA of the fused small-n step,
+// kernels_small.cuh).  Whole-CTA call.  `sums` holds the reduced record.  The Gram state is read from global memory
+// with the entries of a pending pair taken from `sums` (so a CTA never depends on another CTA's Gram write);
+// `write_gram` makes this CTA fold the pending column into the global Gram state.  The coefficients land in
+// `coef_s` (shared memory, 2m+3 doubles: same layout as `coef`); the return value is the status word, valid in
+// every thread.
+struct SolveShared {
+    double Rm[kMaxMem][kMaxMem + 1], Yl[kMaxMem][kMaxMem + 1];
+    double pv[kMaxMem], qv[kMaxMem], ssv[kMaxMem], u[kMaxMem], w[kMaxMem], av[kMaxMem];
+    int status;
+};
 
+__device__ __forceinline__ int solve_cta(const SolveArgs& A, const double* sums, double* __restrict__ SY,
+                                         double* __restrict__ YY, double* __restrict__ SS, SolveShared& sh,
+                                         double* coef_s, bool write_gram, bool comm_ok, int nthreads)
+{
+    const int m = A.msize, used = A.used, c = A.pend;
     auto ph = [&](int i) { int s = A.oldest + i; return s >= m ? s - m : s; };      // logical (oldest..newest) -> physical slot
-    if (A.pend >= 0) {                       // fold the newest pair's Gram column in (one thread per slot)
-        const int c = A.pend;
-        for (int j = threadIdx.x; j < used; j += kThreads) {
+    // stage everything the serial solve touches in shared memory, in logical order
+    for (int t = threadIdx.x; t < used * used; t += nthreads) {
+        const int i = t / used, j = t % used;
+        const int pi = ph(i), pj = ph(j);
+        double r = SY[pi * m + pj], yy = YY[pi * m + pj];
+        if (c >= 0) {
+            if (pj == c) { r = sums[2 * m + pi]; yy = sums[3 * m + pi]; }
+            else if (pi == c) yy = sums[3 * m + pj];
+        }
+        sh.Rm[i][j] = r;
+        sh.Yl[i][j] = yy;
+    }
+    for (int i = threadIdx.x; i < used; i += nthreads) {
+        const int pi = ph(i);
+        sh.pv[i] = sums[pi];
+        sh.qv[i] = sums[m + pi];
+        sh.ssv[i] = (pi == c) ? sums[4 * m + 1] : SS[pi];
+    }
+    for (int j = threadIdx.x; j < 2 * m; j += nthreads) coef_s[j] = 0.0;
+    if (write_gram && c >= 0) {              // fold the newest pair's Gram column into the global state
+        for (int j = threadIdx.x; j < used; j += nthreads) {
             SY[j * m + c] = sums[2 * m + j];
             const double yy = sums[3 * m + j];
             YY[j * m + c] = yy;
             YY[c * m + j] = yy;
         }
         if (threadIdx.x == 0) SS[c] = sums[4 * m + 1];
-        __syncthreads();
     }
-    // stage everything the serial solve touches in shared memory, in logical order
-    __shared__ double Rm[kMaxMem][kMaxMem + 1], Yl[kMaxMem][kMaxMem + 1];
-    __shared__ double pv[kMaxMem], qv[kMaxMem], ssv[kMaxMem], u[kMaxMem], w[kMaxMem], av[kMaxMem];
-    for (int t = threadIdx.x; t < used * used; t += kThreads) {
-        const int i = t / used, j = t % used;
-        Rm[i][j] = SY[ph(i) * m + ph(j)];
-        Yl[i][j] = YY[ph(i) * m + ph(j)];
-    }
-    for (int i = threadIdx.x; i < used; i += kThreads) { pv[i] = sums[ph(i)]; qv[i] = sums[m + ph(i)]; ssv[i] = SS[ph(i)]; }
-    for (int j = threadIdx.x; j < 2 * m; j += kThreads) coef[j] = 0.0;
     __syncthreads();
-    if (threadIdx.x != 0) return;
+    if (threadIdx.x == 0) {
+        const double gg = sums[4 * m];
+        double gamma = 1.0, U = sqrt(gg);
+        bool ok = finite_d(gg);
+        if (used > 0) {
+            gamma = (A.h0 > 0) ? A.h0 : sh.Rm[used - 1][used - 1] / sh.Yl[used - 1][used - 1];
+            for (int i = used - 1; i >= 0; --i) {          // u = R^-1 p
+                double t = sh.pv[i];
+                for (int j = i + 1; j < used; ++j) t -= sh.Rm[i][j] * sh.u[j];
+                sh.u[i] = t / sh.Rm[i][i];
+            }
+            for (int i = 0; i < used; ++i) {               // w = (D + gamma*YY) u - gamma*q0
+                double t = 0;
+                for (int j = 0; j < used; ++j) t += sh.Yl[i][j] * sh.u[j];
+                sh.w[i] = sh.Rm[i][i] * sh.u[i] + gamma * t - gamma * sh.qv[i];
+            }
+            for (int i = 0; i < used; ++i) {               // a = R^-T w
+                double t = sh.w[i];
+                for (int j = 0; j < i; ++j) t -= sh.Rm[j][i] * sh.av[j];
+                sh.av[i] = t / sh.Rm[i][i];
+            }
+            U = fabs(gamma) * sqrt(gg);
+            for (int i = 0; i < used; ++i) {
+                const int s = ph(i);
+                const double a = sh.av[i], gb = -gamma * sh.u[i];
+                coef_s[s] = a;
+                coef_s[m + s] = gb;
+                U += fabs(a) * sqrt(sh.ssv[i]) + fabs(gb) * sqrt(sh.Yl[i][i]);
+                ok = ok && finite_d(a) && finite_d(gb);
+            }
+            ok = ok && finite_d(gamma);
+        }
+        ok = ok && finite_d(U);
+        coef_s[2 * m] = gamma;
+        coef_s[2 * m + 1] = U;
+        coef_s[2 * m + 2] = gg;
+        int st = ST_ACCEPT;
+        if (A.check_nan) {
+            if (!ok) st = ST_REJECT_NONFINITE;
+            else if (used == 0) { if (U > A.limit) st = ST_REJECT_NONFINITE; }      // d = g: U is the exact norm (stochqn.c:829)
+            else if (!(U <= 0.99 * A.limit)) st = ST_NEED_EXACT_NORM;
+        }
+        if (!comm_ok) st = ST_COMM_TIMEOUT;
+        sh.status = st;
+    }
+    __syncthreads();
+    return sh.status;
+}
 
-    const double gg = sums[4 * m];
-    double gamma = 1.0, U = sqrt(gg);
-    bool ok = finite_d(gg);
-    if (used > 0) {
-        gamma = (A.h0 > 0) ? A.h0 : Rm[used - 1][used - 1] / Yl[used - 1][used - 1];
-        for (int i = used - 1; i >= 0; --i) {          // u = R^-1 p
-            double t = pv[i];
-            for (int j = i + 1; j < used; ++j) t -= Rm[i][j] * u[j];
-            u[i] = t / Rm[i][i];
-        }
-        for (int i = 0; i < used; ++i) {               // w = (D + gamma*YY) u - gamma*q0
-            double t = 0;
-            for (int j = 0; j < used; ++j) t += Yl[i][j] * u[j];
-            w[i] = Rm[i][i] * u[i] + gamma * t - gamma * qv[i];
-        }
-        for (int i = 0; i < used; ++i) {               // a = R^-T w
-            double t = w[i];
-            for (int j = 0; j < i; ++j) t -= Rm[j][i] * av[j];
-            av[i] = t / Rm[i][i];
-        }
-        U = fabs(gamma) * sqrt(gg);
-        for (int i = 0; i < used; ++i) {
-            const int s = ph(i);
-            const double a = av[i], gb = -gamma * u[i];
-            coef[s] = a;
-            coef[m + s] = gb;
-            U += fabs(a) * sqrt(ssv[i]) + fabs(gb) * sqrt(Yl[i][i]);
-            ok = ok && finite_d(a) && finite_d(gb);
-        }
-        ok = ok && finite_d(gamma);
-    }
-    ok = ok && finite_d(U);
-    coef[2 * m] = gamma;
-    coef[2 * m + 1] = U;
-    coef[2 * m + 2] = gg;
-    int st = ST_ACCEPT;
-    if (A.check_nan) {
-        if (!ok) st = ST_REJECT_NONFINITE;
-        else if (used == 0) { if (U > A.limit) st = ST_REJECT_NONFINITE; }      // d = g: U is the exact norm (stochqn.c:829)
-        else if (!(U <= 0.99 * A.limit)) st = ST_NEED_EXACT_NORM;
-    }
-    if (!comm_ok) st = ST_COMM_TIMEOUT;
+// status word + the three diagnostics to the device word and the mapped host block, then the sequence number
+__device__ __forceinline__ void publish_status(int st, const double* coef_s, int m, int* status_dev, volatile int* status_host,
+                                               volatile double* info_host, volatile unsigned long long* seq_host,
+                                               unsigned long long seq)
+{
     *status_dev = st;
     *status_host = st;
-    info_host[0] = U;
-    info_host[1] = gamma;
-    info_host[2] = gg;
-    publish_seq(seq_host, A.seq);
+    info_host[0] = coef_s[2 * m + 1];
+    info_host[1] = coef_s[2 * m];
+    info_host[2] = coef_s[2 * m + 2];
+    publish_seq(seq_host, seq);
+}
+
+__global__ void __launch_bounds__(kThreads)
+k2_solve(SolveArgs A, PeerArgs pa, const double* __restrict__ partials, double* sums,
+         double* __restrict__ SY, double* __restrict__ YY, double* __restrict__ SS,
+         double* __restrict__ coef, int* __restrict__ status_dev, volatile int* status_host,
+         volatile double* info_host, volatile unsigned long long* seq_host)
+{
+    const int m = A.msize;
+    const int P = 4 * m + 2;
+    if (A.nblocks > 0) { reduce_partials(partials, A.nblocks, P, sums); __syncthreads(); }
+    bool comm_ok = true;
+    if (pa.world > 1) comm_ok = p2p_allreduce_cta(pa, sums, P);      // sharded: sum the records of all ranks (p2p.cuh)
+    if (!A.do_solve) return;
+    __shared__ SolveShared sh;
+    __shared__ double coef_s[2 * kMaxMem + 3];
+    const int st = solve_cta(A, sums, SY, YY, SS, sh, coef_s, true, comm_ok, kThreads);
+    for (int j = threadIdx.x; j < 2 * m + 3; j += kThreads) coef[j] = coef_s[j];
+    __syncthreads();
+    if (threadIdx.x == 0) publish_status(st, coef_s, m, status_dev, status_host, info_host, seq_host, A.seq);
 }
 
 // =========================================================================================
@@ -529,10 +570,40 @@ k3_apply(T* grad, T* S_rw, size_t ld, int new_slot, long long n,
 // =========================================================================================
 enum : int { PAIR_GRAD_DIFF = 0, PAIR_COPY = 1, PAIR_DOTS_ONLY = 2 };
 
+// =========================================================================================
+// K4 with the finalisation folded in ("last block done"): every CTA writes its 2-value record and takes a ticket;
+// the CTA that draws the last ticket sums the records in CTA order (deterministic) and publishes s'y, s's to the
+// mapped host block.  Saves the k_finalize launch whenever the optimizer is not sharded (any n).
+// =========================================================================================
+__device__ __forceinline__ void last_block_publish2(const double* __restrict__ partials, double* __restrict__ sums,
+                                                    unsigned int* ticket, volatile double* host_out,
+                                                    volatile unsigned long long* seq_host, unsigned long long seq)
+{
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp < 2) {
+        double v = 0;
+        for (unsigned b = lane; b < gridDim.x; b += 32) v += __ldcg(partials + (size_t) b * 2 + warp);
+        v = warp_sum(v);
+        if (lane == 0) { sums[warp] = v; host_out[warp] = v; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { *ticket = 0; publish_seq(seq_host, seq); }
+}
+
+
 template <typename T, int KIND, int VEC>
 __global__ void __launch_bounds__(kThreads)
 k4_pair(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ s, T* __restrict__ y,
-        T y_reg, long long n, double* __restrict__ partials)
+        T y_reg, long long n, double* __restrict__ partials,
+        unsigned int* ticket, double* __restrict__ sums, volatile double* host_out,
+        volatile unsigned long long* seq_host, unsigned long long seq)
 {
     double a_sy = 0, a_ss = 0;
     auto one = [&](size_t off, auto vtag) {
@@ -571,6 +642,7 @@ k4_pair(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ 
     }
     double* out = partials + (size_t) blockIdx.x * 2;
     block_reduce<2>(2, [&](int p) { return p == 0 ? a_sy : a_ss; }, [&](int p, double v) { out[p] = v; });
+    if (ticket) last_block_publish2(partials, sums, ticket, host_out, seq_host, seq);
 }
 
 // Sum `count`-wide partial records over CTAs into `sums` (device), across ranks when sharded (p2p.cuh), and, when
@@ -750,4 +822,5 @@ kf2_combine(const T* __restrict__ F, size_t ld, int r0, int rows, const double* 
 
 }  // namespace sqn
 
+#include "kernels_small.cuh"
 #include "kernels_adaqn.cuh"

@@ -166,6 +166,12 @@ struct Ctx {
     double exact_norm_steps = 0;        // steps that took the two-pass (exact ||d||) route
     unsigned long long seq_want[3] = {0, 0, 0};   // sequence numbers the host is waiting for (HostBlock::seq)
     int sync_return = 0;                // 1: drain the stream before every return, also for device-pointer calls
+    // latency-bound sizes: the whole take_step in one cooperative launch (kernels_small.cuh)
+    unsigned long long* bar = nullptr;  // grid-barrier counter (device), monotonically increasing
+    unsigned long long bar_total = 0;   // its value once every launch issued so far has passed its barrier
+    unsigned int* ticket = nullptr;     // "last block done" ticket of K4
+    long long small_n = 0;              // use ks_step when n <= small_n (0: never)
+    double small_steps = 0;             // steps that took the one-launch route
 };
 
 void prof_collect_one(Ctx* c, int k)      // waits for the closing event of kernel class k (long past when re-armed)
@@ -236,6 +242,7 @@ bool is_device_ptr(const void* p)
 }
 
 constexpr int VECW = 16 / sizeof(real_t);
+constexpr long long kSmallNDefault = 32768;
 bool aligned16(const void* p) { return (((uintptr_t) p) & 15u) == 0; }
 
 // ------------------------------------------------------------------------------------------
@@ -384,13 +391,19 @@ void launch_k3_apply(Ctx* c, int mode, real_t* grad, real_t* S, int new_slot, re
     COUNT_LAUNCH();
 }
 
+// `publish`: the last CTA to finish sums the 2-value records and publishes them to the host pair block itself
+// (no k_finalize launch); only when the optimizer is not sharded - the exchange between ranks lives in k_finalize.
 template <int KIND>
-int launch_k4_k(Ctx* c, const real_t* a, const real_t* b, const real_t* s, real_t* y, real_t y_reg)
+int launch_k4_k(Ctx* c, const real_t* a, const real_t* b, const real_t* s, real_t* y, real_t y_reg, bool publish = false)
 {
     const bool vec = aligned16(a) && aligned16(b);
     const int grid = grid_for(c, c->n / (vec ? VECW : 1));
-    if (vec) k4_pair<real_t, KIND, VECW><<<grid, kThreads, 0, c->stream>>>(a, b, s, y, y_reg, c->n, c->partials);
-    else     k4_pair<real_t, KIND, 1><<<grid, kThreads, 0, c->stream>>>(a, b, s, y, y_reg, c->n, c->partials);
+    unsigned int* ticket = publish ? c->ticket : nullptr;
+    const unsigned long long seq = publish ? ++c->seq_want[FLAG_PAIR] : 0;
+    if (vec) k4_pair<real_t, KIND, VECW><<<grid, kThreads, 0, c->stream>>>(a, b, s, y, y_reg, c->n, c->partials, ticket, c->sums,
+                                                                          c->hb_dev->pair, &c->hb_dev->seq[FLAG_PAIR], seq);
+    else     k4_pair<real_t, KIND, 1><<<grid, kThreads, 0, c->stream>>>(a, b, s, y, y_reg, c->n, c->partials, ticket, c->sums,
+                                                                       c->hb_dev->pair, &c->hb_dev->seq[FLAG_PAIR], seq);
     COUNT_LAUNCH();
     return grid;
 }
@@ -466,6 +479,46 @@ int launch_pair_finalize(Ctx* c, int nblocks, volatile double* host_dst)
     return launch_finalize(c, nblocks, 2, host_dst, host_dst == c->hb_dev->pair ? FLAG_PAIR : FLAG_DIR);
 }
 
+// K4 + publication of s'y, s's to the host pair block: one launch when not sharded, K4 + k_finalize otherwise
+template <int KIND>
+int launch_pair(Ctx* c, const real_t* a, const real_t* b, const real_t* s, real_t* y, real_t y_reg)
+{
+    const bool sharded = c->comm && c->comm->world > 1;
+    const int nb = launch_k4_k<KIND>(c, a, b, s, y, y_reg, !sharded);
+    if (sharded) return launch_pair_finalize(c, nb, c->hb_dev->pair);
+    return 0;
+}
+
+// take_step of oLBFGS / SQN in one cooperative launch (kernels_small.cuh); same outputs as K1 -> K2 -> K3
+template <int MODE>
+int launch_small_step(Ctx* c, const real_t* g, real_t* gout, real_t* S, const real_t* Y, int used, int oldest, int pend,
+                      int new_slot, real_t* x, real_t* x_sum, real_t* grad_prev, real_t step, int check_nan, double h0)
+{
+    SmallArgs K;
+    K.msize = c->msize; K.used = used; K.pend = pend; K.new_slot = new_slot; K.n = c->n; K.ld = c->ld;
+    long long grid = (c->n + kThreads - 1) / kThreads;
+    if (grid > c->sm_count) grid = c->sm_count;
+    if (grid < 1) grid = 1;
+    c->bar_total += (unsigned long long) grid;
+    K.bar_target = c->bar_total;
+    SolveArgs A;
+    A.msize = c->msize; A.used = used; A.oldest = oldest; A.pend = pend; A.nblocks = (int) grid; A.do_solve = 1;
+    A.check_nan = check_nan; A.h0 = h0; A.limit = step_limit(c);
+    A.seq = ++c->seq_want[FLAG_STATUS];
+    double *partials = c->partials, *SY = c->SY, *YY = c->YY, *SS = c->SS, *coef = c->coef;
+    int* status_dev = c->status_dev;
+    volatile int* status_host = &c->hb_dev->status;
+    volatile double* info_host = c->hb_dev->info;
+    volatile unsigned long long* seq_host = &c->hb_dev->seq[FLAG_STATUS];
+    unsigned long long* bar = c->bar;
+    void* args[] = {&K, &A, &g, &gout, &S, &Y, &x, &x_sum, &grad_prev, &step, &partials, &SY, &YY, &SS, &coef,
+                    &status_dev, &status_host, &info_host, &seq_host, &bar};
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void*) ks_step<real_t, MODE>, dim3((unsigned) grid), dim3(kThreads), args, 0, c->stream));
+    COUNT_LAUNCH();
+    c->small_steps += 1;
+    return 0;
+}
+
 int sync_stream(Ctx* c)
 {
     cudaError_t e = cudaStreamSynchronize(c->stream);
@@ -513,6 +566,7 @@ void free_ctx(Ctx* c)
     if (!c) return;
     cudaFree(c->SY); cudaFree(c->YY); cudaFree(c->SS);
     cudaFree(c->partials); cudaFree(c->sums); cudaFree(c->coef); cudaFree(c->status_dev);
+    cudaFree(c->bar); cudaFree(c->ticket);
     if (c->hb) cudaFreeHost((void*) c->hb);
     cudaFree(c->dx); cudaFree(c->dg); cudaFree(c->dhv);
     if (c->hreq) cudaFreeHost(c->hreq);
@@ -551,6 +605,16 @@ Ctx* make_ctx(Kind kind, long long n, int msize, int fisher_size)
     ok = ok && dev_alloc_zero(&c->sums, rec) == cudaSuccess;
     ok = ok && dev_alloc_zero(&c->coef, 2 * m + 4) == cudaSuccess;
     ok = ok && dev_alloc_zero(&c->status_dev, 1) == cudaSuccess;
+    ok = ok && dev_alloc_zero(&c->bar, 1) == cudaSuccess;
+    ok = ok && dev_alloc_zero(&c->ticket, 1) == cudaSuccess;
+    if (ok) {
+        // one-launch step for latency-bound sizes (measured crossover on B200: tools/probe_small.py); needs cooperative
+        // launch; STOCHQN_B200_SMALL_N overrides the threshold (0 disables)
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+        const char* e = getenv("STOCHQN_B200_SMALL_N");
+        c->small_n = coop ? (e ? atoll(e) : kSmallNDefault) : 0;
+    }
     ok = ok && cudaHostAlloc((void**) &c->hb, sizeof(HostBlock), cudaHostAllocMapped) == cudaSuccess;
     if (ok) {
         memset((void*) c->hb, 0, sizeof(HostBlock));
@@ -652,14 +716,24 @@ int take_step_qn(Ctx* c, bfgs_mem* m, int mode, real_t step, real_t* x, real_t* 
     const int used = (int) m->mem_used;
     const int st = (int) m->mem_st_ix;
     real_t* gout = c->grad_writeback ? g : nullptr;
-    prof_begin(c, 0);
-    int nb = launch_k1(c, g, m->s_mem, m->y_mem, used, c->pending, grad_prev);
-    prof_end(c, 0);
-    if (int r = launch_solve(c, false, nb, used, oldest_slot(m), c->pending, check_nan, h0)) return r;
-    c->pending = -1;                    // the Gram column is folded in whatever happens next
-    prof_begin(c, 1);
-    launch_k3(c, mode, g, gout, m->s_mem, m->y_mem, used, st, x, x_sum, step, 0);
-    prof_end(c, 1);
+    const bool sharded = c->comm && c->comm->world > 1;
+    if (!sharded && c->small_n > 0 && c->n <= c->small_n) {
+        // latency-bound size: dots, solve and update in ONE cooperative launch
+        int r = mode == MODE_OLBFGS
+            ? launch_small_step<MODE_OLBFGS>(c, g, gout, m->s_mem, m->y_mem, used, oldest_slot(m), c->pending, st, x, x_sum, grad_prev, step, check_nan, h0)
+            : launch_small_step<MODE_AVG>(c, g, gout, m->s_mem, m->y_mem, used, oldest_slot(m), c->pending, st, x, x_sum, grad_prev, step, check_nan, h0);
+        if (r) return r;
+        c->pending = -1;
+    } else {
+        prof_begin(c, 0);
+        int nb = launch_k1(c, g, m->s_mem, m->y_mem, used, c->pending, grad_prev);
+        prof_end(c, 0);
+        if (int r = launch_solve(c, false, nb, used, oldest_slot(m), c->pending, check_nan, h0)) return r;
+        c->pending = -1;                    // the Gram column is folded in whatever happens next
+        prof_begin(c, 1);
+        launch_k3(c, mode, g, gout, m->s_mem, m->y_mem, used, st, x, x_sum, step, 0);
+        prof_end(c, 1);
+    }
     if (int r = wait_flag(c, FLAG_STATUS)) return r;          // K2 has retired; K3 may still be running
     int status = c->hb->status;
     c->last_bound = c->hb->info[0];
@@ -714,9 +788,8 @@ int update_y_grad_diff_dev(Ctx* c, bfgs_mem* m, const real_t* grad, const real_t
     real_t* s = m->s_mem + slot * c->ld;
     real_t* y = m->y_mem + slot * c->ld;
     prof_begin(c, 2);
-    int nb = launch_k4_k<PAIR_GRAD_DIFF>(c, grad, grad_prev, s, y, m->y_reg);
+    if (int r = launch_pair<PAIR_GRAD_DIFF>(c, grad, grad_prev, s, y, m->y_reg)) return r;
     prof_end(c, 2);
-    if (int r = launch_pair_finalize(c, nb, c->hb_dev->pair)) return r;
     if (int r = wait_flag(c, FLAG_PAIR)) return r;
     return curvature_decision(c, m, c->hb->pair[0], c->hb->pair[1], info);
 }
@@ -1034,8 +1107,7 @@ int run_SQN(real_t step_size, real_t x[], real_t grad[], real_t hess_vec[], real
         if (stage_in(c, hess_vec, &c->dhv, &shv, true)) SQN_FAIL();
         launch_avg<AVG_ARCHIVE>(c, ws->x_sum, ws->x_avg_prev, nullptr, (real_t) 1);
         const size_t slot = m->mem_st_ix;
-        int nb = launch_k4_k<PAIR_COPY>(c, shv.dev, shv.dev, m->s_mem + slot * c->ld, m->y_mem + slot * c->ld, (real_t) 0);
-        if (launch_pair_finalize(c, nb, c->hb_dev->pair)) SQN_FAIL();
+        if (launch_pair<PAIR_COPY>(c, shv.dev, shv.dev, m->s_mem + slot * c->ld, m->y_mem + slot * c->ld, (real_t) 0)) SQN_FAIL();
         if (wait_flag(c, FLAG_PAIR)) SQN_FAIL();
         if (curvature_decision(c, m, c->hb->pair[0], c->hb->pair[1], iter_info)) SQN_FAIL();
         if (finish_call(c, host_mode)) SQN_FAIL();

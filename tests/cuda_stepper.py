@@ -57,6 +57,8 @@ class CudaStepper:
                                            kw.get("y_reg", 0.0), kw.get("check_nan", 1), 1)
         if not self.ws:
             raise RuntimeError("initialize_%s failed: %s" % (kind, _lib.last_error(self.abi)))
+        if "one_launch_max_n" in kw:      # 0: force the K1 -> K2 -> K3 route; large: force the fused one-launch step
+            assert lib.stochqn_b200_set_option(self.ws, _lib.OPT_ONE_LAUNCH_MAX_N, int(kw["one_launch_max_n"])) == 0
         if "grad_writeback" in kw:
             lib.stochqn_b200_set_option(self.ws, _lib.OPT_GRAD_WRITEBACK, int(kw["grad_writeback"]))
         self._req = C.c_void_p()
@@ -142,6 +144,9 @@ class CudaStepper:
         base = C.cast(m.s_mem if which == "s" else m.y_mem, C.c_void_p).value
         esz = C.sizeof(self.abi.real)
         return self._dev_to_np(base + i * ld * esz)
+
+    def one_launch_steps(self):
+        return int(_lib.get_stat(self.abi, self.ws, _lib.STAT_ONE_LAUNCH_STEPS))
 
     def close(self):
         if self.ws:

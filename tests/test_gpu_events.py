@@ -16,6 +16,13 @@ pytestmark = pytest.mark.gpu
 ORACLE = {"oLBFGS": O.OracleOLBFGS, "SQN": O.OracleSQN, "adaQN": O.OracleAdaQN}
 
 
+@pytest.fixture(autouse=True, params=["three_launch", "one_launch"])
+def step_route(request, monkeypatch):
+    """Every forced event runs through both step routes of oLBFGS / SQN: K1 -> K2 -> K3 and the fused one-launch
+    step used for latency-bound sizes (the library reads the threshold when a workspace is created)."""
+    monkeypatch.setenv("STOCHQN_B200_SMALL_N", "0" if request.param == "three_launch" else str(1 << 30))
+
+
 def _both(kind, kw, prob_f, calls, step, hooks_o, hooks_c, dtype=np.float64, mode="device"):
     p1, p2 = prob_f(), prob_f()
     so = HostStepper(ORACLE[kind](len(p1.x0()), dtype=dtype, **kw), p1.x0())

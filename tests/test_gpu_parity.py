@@ -15,6 +15,9 @@ pytestmark = pytest.mark.gpu
 
 ORACLE = {"oLBFGS": O.OracleOLBFGS, "SQN": O.OracleSQN, "adaQN": O.OracleAdaQN}
 RTOL = {np.float64: 1e-10, np.float32: 1e-4}
+# oLBFGS / SQN take a step either as K1 -> K2 -> K3 or, for latency-bound sizes, as one fused cooperative launch
+# (kernels_small.cuh); every case of the matrix runs through both (adaQN has the first route only)
+PATHS = {"three_launch": dict(one_launch_max_n=0), "one_launch": dict(one_launch_max_n=1 << 30)}
 
 
 def _run_pair(kind, kw, prob_f, calls, step, dtype, mode="device", **extra):
@@ -24,6 +27,9 @@ def _run_pair(kind, kw, prob_f, calls, step, dtype, mode="device", **extra):
     sc = CudaStepper(kind, x0, dtype=dtype, mode=mode, **kw, **extra)
     to = run_trace(so, p1, calls, step, keep_x=True)
     tc = run_trace(sc, p2, calls, step, keep_x=True)
+    if "one_launch_max_n" in extra and kind != "adaQN":
+        if tc[-1]["niter"] > 0:
+            assert (sc.one_launch_steps() > 0) == (extra["one_launch_max_n"] > 0), "the requested step route was not taken"
     sc.close()
     return to, tc
 
@@ -63,15 +69,18 @@ def _oracle_sensitivity(kind, kw, prob_f, calls, step, to):
     return worst
 
 
+@pytest.mark.parametrize("path", list(PATHS))
 @pytest.mark.parametrize("case", CASES, ids=CASE_IDS)
-def test_parity_fp64_device(case):
+def test_parity_fp64_device(case, path):
     """Bar: rel-inf 1e-10 over the whole trace.  One case (sqn_gd_logistic_yreg: step 0.1, no curvature
     threshold, |x| grows to ~240) is a diverging iteration: the oracle's own trajectory moves by 2e-9 when its
     gradients are jittered by 1e-15, and the reference C library and the NumPy restatement (same algorithm,
     different dot-product order) are 3e-11 apart on it, against 1e-15 elsewhere.  Where 10x the oracle's measured
     sensitivity exceeds the bar, that is the bar (all other cases: sensitivity <= 1.3e-11, bar stays 1e-10)."""
     name, kind, kw, prob_f, calls, step = case
-    to, tc = _run_pair(kind, kw, prob_f, calls, step, np.float64)
+    if kind == "adaQN" and path == "one_launch":
+        pytest.skip("adaQN has no one-launch route")
+    to, tc = _run_pair(kind, kw, prob_f, calls, step, np.float64, **PATHS[path])
     tol = RTOL[np.float64]
     sens = _oracle_sensitivity(kind, kw, prob_f, calls, step, to)
     if np.isfinite(sens) and 10.0 * sens > tol:
@@ -87,14 +96,17 @@ def _rel_err(ta, tb):
     return worst
 
 
+@pytest.mark.parametrize("path", list(PATHS))
 @pytest.mark.parametrize("case", CASES_FP32, ids=CASE_IDS_FP32)
-def test_parity_fp32_device(case):
+def test_parity_fp32_device(case, path):
     """fp32 build against the fp64 oracle: rel 1e-4 (north_star).  A few cases amplify float rounding so
     much that the REFERENCE's own fp32 build is 1e-3..4e-2 away from its fp64 build (checked on CPU:
     sqn_gd_logistic_yreg 3.6e-2, adaqn_fisher_adagrad_logistic 5e-3, adaqn_fisher_quad 2e-3); for those the
     bar is 5x the oracle's own fp32-vs-fp64 distance, measured in the same test."""
     name, kind, kw, prob_f, calls, step = case
-    to32, tc = _run_pair(kind, kw, prob_f, calls, step, np.float32)
+    if kind == "adaQN" and path == "one_launch":
+        pytest.skip("adaQN has no one-launch route")
+    to32, tc = _run_pair(kind, kw, prob_f, calls, step, np.float32, **PATHS[path])
     p = prob_f()
     to64 = run_trace(HostStepper(ORACLE[kind](len(p.x0()), dtype=np.float64, **kw), p.x0()), p, calls, step, keep_x=True)
     do, dc = discrete(to64), discrete(tc)

@@ -60,7 +60,7 @@ enum stochqn_b200_option {
     STOCHQN_B200_OPT_SYNC_RETURN = 4,
     /* oLBFGS / SQN: largest n for which a step is ONE cooperative launch (dots, solve and update fused - for the
        latency-bound sizes where three launches and the flag round trip dominate) instead of K1 -> K2 -> K3.
-       Default 32768 (environment: STOCHQN_B200_SMALL_N); 0 disables.  Not used when the optimizer is sharded. */
+       Default 2048 (environment: STOCHQN_B200_SMALL_N); 0 disables.  Not used when the optimizer is sharded. */
     STOCHQN_B200_OPT_ONE_LAUNCH_MAX_N = 5
 };
 int stochqn_b200_set_option(void *ws, int option, long long value);
@@ -72,7 +72,7 @@ enum stochqn_b200_stat {
     STOCHQN_B200_STAT_LAST_BOUND = 7,                                 /* bound on ||direction|| of the last step */
     STOCHQN_B200_STAT_EXACT_NORM_STEPS = 8,                           /* steps that needed the exact-norm (two-pass) route */
     STOCHQN_B200_STAT_KA2_MS = 9, STOCHQN_B200_STAT_KA2_COUNT = 10,   /* adaQN: the second dot pass (K1/K3 slots hold KA1/KA3) */
-    /* steps taken by the one-launch kernel used for latency-bound sizes (n <= 32768 unless STOCHQN_B200_SMALL_N
+    /* steps taken by the one-launch kernel used for latency-bound sizes (n <= 2048 unless STOCHQN_B200_SMALL_N
        says otherwise; 0 there disables it): dots, solve and update in one cooperative launch instead of three */
     STOCHQN_B200_STAT_ONE_LAUNCH_STEPS = 11
 };
@@ -201,6 +201,55 @@ int stochqn_b200_multinomial_hess_vec(const real_t *X, long long ldx, const real
                                       const real_t *sw, long long nrows, long long nfeat, long long nclasses,
                                       int fit_intercept, const real_t *w, const real_t *v, real_t alpha, real_t *hess_vec,
                                       void *work, void *stream);
+
+/* ---- guided mode: the request loop of one mini-batch, natively ------------------------------------------------
+   The reference's guided classes serve the optimizer's requests from the host language: one interpreter round trip
+   per request (R/optimizers_guided.R:26-111 `run_stochQN_on_batch`; stochqn/_optimizers.py:339-382 `_fit_batch`).
+   stochqn_b200_fit_batch runs that loop inside the library for a DEVICE-resident model matrix and the bundled
+   callbacks: starting from the pending request (*task, *req, *req_vec - as left by the previous run_*() or
+   fit_batch call), it evaluates what is asked on the right rows, hands it to run_oLBFGS / run_SQN / run_adaQN, and
+   repeats until the optimizer asks for a gradient on a NEW batch (task calc_grad), exactly the reference's loop:
+     calc_grad, calc_grad_same_batch      gradient on `batch`
+     calc_grad_big_batch, calc_hess_vec   gradient / Hessian-vector product on `long_batch`
+     calc_fun_val_batch                   objective on `valset` if given, else on `long_batch`
+   Every batch is a ROW RANGE of resident arrays (pointer + row count: no copy; the "long batch" of the last
+   bfgs_upd_freq mini-batches is one range when they are consecutive rows).  All pointers are device pointers.
+   Returns 0 when the loop ended with *task == calc_grad; 1 when a request needs `long_batch` (or `valset`) and
+   none was given, or `long_batch` was already used once in this call (the reference's stash is emptied by the
+   first use, stochqn/_optimizers.py:92-107) - *task / *req / *req_vec then describe the pending request and the
+   caller serves it its own way; negative on failure (-1000: invalid workspace, as run_*()). */
+typedef struct {
+    const real_t *X;        /* [nrows][ncols] row-major, leading dimension ldx */
+    long long ldx;
+    const real_t *y;        /* models 0, 1: labels [nrows]; model 2: one-hot matrix [nrows][nclasses], leading dimension ldy */
+    long long ldy;
+    const real_t *sw;       /* sample weights [nrows] or NULL */
+    long long nrows;
+} stochqn_b200_rows;
+
+typedef struct {
+    int model;              /* 0: two classes, R conventions (stochqn_b200_logistic_*);
+                               1: two classes, scikit-learn conventions (stochqn_b200_logistic_sk_*);
+                               2: multinomial (stochqn_b200_multinomial_*) */
+    int fit_intercept;      /* models 1, 2 */
+    long long ncols;        /* features (columns of X) */
+    long long nclasses;     /* model 2 */
+    real_t reg_param;
+    void *work;             /* device scratch, at least the *_work_size of the largest batch handed over */
+} stochqn_b200_model;
+
+typedef struct {
+    long long calls;        /* run_*() calls made */
+    long long n_info[4];    /* how many of them reported no_problems / func_increased / curvature_too_small / search_direction_was_nan */
+    int last_info;          /* info_enum of the last call */
+    int x_changed;          /* 1 if any call updated x */
+    int long_batch_used;    /* 1 if `long_batch` served a request */
+} stochqn_b200_fit_report;
+
+int stochqn_b200_fit_batch(void *ws, real_t *x, real_t step_size, const stochqn_b200_model *model,
+                           const stochqn_b200_rows *batch, const stochqn_b200_rows *long_batch,
+                           const stochqn_b200_rows *valset, int *task, real_t **req, real_t **req_vec,
+                           stochqn_b200_fit_report *report);
 
 /* ---- workspace export / import (checkpoint / resume) ----------------------------------------
    The reference keeps all state in host-language arrays, so saveRDS / pickle of the R / Python

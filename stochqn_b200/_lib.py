@@ -27,7 +27,7 @@ EXT_SYMBOLS = (
     "stochqn_b200_logistic_loss", "stochqn_b200_export", "stochqn_b200_import",
     "stochqn_b200_logistic_sk_grad", "stochqn_b200_logistic_sk_hess_vec", "stochqn_b200_logistic_sk_loss",
     "stochqn_b200_multinomial_work_size", "stochqn_b200_multinomial_loss_grad", "stochqn_b200_multinomial_hess_vec",
-    "stochqn_b200_gemm_tn",
+    "stochqn_b200_gemm_tn", "stochqn_b200_fit_batch",
 )
 
 OPT_GRAD_WRITEBACK = 1
@@ -50,6 +50,26 @@ class HostState(C.Structure):
     """stochqn_b200_host_state (include/stochqn_b200.h)."""
     _fields_ = [(k, C.c_void_p) for k in
                 ("s_mem", "y_mem", "grad_prev", "x_sum", "x_avg_prev", "grad_sum_sq", "F")]
+
+
+class Rows(C.Structure):
+    """stochqn_b200_rows (include/stochqn_b200.h): a row range of device-resident arrays."""
+    _fields_ = [("X", C.c_void_p), ("ldx", C.c_longlong), ("y", C.c_void_p), ("ldy", C.c_longlong),
+                ("sw", C.c_void_p), ("nrows", C.c_longlong)]
+
+
+def model_struct(real):
+    """stochqn_b200_model for the precision whose C real type is `real`."""
+    class Model(C.Structure):
+        _fields_ = [("model", C.c_int), ("fit_intercept", C.c_int), ("ncols", C.c_longlong), ("nclasses", C.c_longlong),
+                    ("reg_param", real), ("work", C.c_void_p)]
+    return Model
+
+
+class FitReport(C.Structure):
+    """stochqn_b200_fit_report."""
+    _fields_ = [("calls", C.c_longlong), ("n_info", C.c_longlong * 4), ("last_info", C.c_int), ("x_changed", C.c_int),
+                ("long_batch_used", C.c_int)]
 
 
 def load(dtype=np.float64) -> StochqnABI:
@@ -102,6 +122,9 @@ def load(dtype=np.float64) -> StochqnABI:
     lib.stochqn_b200_multinomial_loss_grad.argtypes = [vp, ll, vp, ll, vp, vp, ll, ll, ll, ci, vp, real, vp, vp, vp, vp]
     lib.stochqn_b200_multinomial_hess_vec.argtypes = [vp, ll, vp, ll, vp, vp, ll, ll, ll, ci, vp, vp, real, vp, vp, vp]
     lib.stochqn_b200_gemm_tn.argtypes = [vp, ll, vp, ll, vp, ll, ci, ci, ci, vp]
+    abi.Model = model_struct(real)
+    lib.stochqn_b200_fit_batch.argtypes = [vp, vp, real, C.POINTER(abi.Model), C.POINTER(Rows), C.POINTER(Rows), C.POINTER(Rows),
+                                           C.POINTER(ci), C.POINTER(vp), C.POINTER(vp), C.POINTER(FitReport)]
     lib.stochqn_b200_export.argtypes = [vp, C.POINTER(HostState)]
     lib.stochqn_b200_import.argtypes = [vp, C.POINTER(HostState)]
     for name in EXT_SYMBOLS:

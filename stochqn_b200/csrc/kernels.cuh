@@ -273,7 +273,7 @@ __device__ __forceinline__ void reduce_partials(const double* __restrict__ parti
 // every thread.
 struct SolveShared {
     double Rm[kMaxMem][kMaxMem + 1], Yl[kMaxMem][kMaxMem + 1];
-    double pv[kMaxMem], qv[kMaxMem], ssv[kMaxMem], u[kMaxMem], w[kMaxMem], av[kMaxMem];
+    double pv[kMaxMem], qv[kMaxMem], ssv[kMaxMem];
     int status;
 };
 
@@ -312,50 +312,67 @@ __device__ __forceinline__ int solve_cta(const SolveArgs& A, const double* sums,
         if (threadIdx.x == 0) SS[c] = sums[4 * m + 1];
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+        // warp-parallel solve: lane i owns row i (used <= kMaxMem = 32).  Column-oriented substitutions, one shuffle
+        // broadcast + one FMA per lane and step, reciprocal diagonal computed up front (a zero or non-finite pivot
+        // yields Inf / NaN exactly as the division would).  ~1 us for m = 10 instead of ~5 us on a single thread.
+        const unsigned full = 0xffffffffu;
+        const int i = threadIdx.x;
+        const bool live = i < used;
         const double gg = sums[4 * m];
         double gamma = 1.0, U = sqrt(gg);
         bool ok = finite_d(gg);
         if (used > 0) {
             gamma = (A.h0 > 0) ? A.h0 : sh.Rm[used - 1][used - 1] / sh.Yl[used - 1][used - 1];
-            for (int i = used - 1; i >= 0; --i) {          // u = R^-1 p
-                double t = sh.pv[i];
-                for (int j = i + 1; j < used; ++j) t -= sh.Rm[i][j] * sh.u[j];
-                sh.u[i] = t / sh.Rm[i][i];
+            const double rii = live ? sh.Rm[i][i] : 1.0;
+            const double inv = 1.0 / rii;
+            double t = live ? sh.pv[i] : 0.0, ui = 0.0;
+            for (int j = used - 1; j >= 0; --j) {          // u = R^-1 p   (back substitution)
+                const double uj = __shfl_sync(full, t * inv, j);
+                if (i == j) ui = uj;
+                if (i < j) t = fma(-sh.Rm[i][j], uj, t);
             }
-            for (int i = 0; i < used; ++i) {               // w = (D + gamma*YY) u - gamma*q0
-                double t = 0;
-                for (int j = 0; j < used; ++j) t += sh.Yl[i][j] * sh.u[j];
-                sh.w[i] = sh.Rm[i][i] * sh.u[i] + gamma * t - gamma * sh.qv[i];
+            double acc = 0.0;                               // w = (D + gamma*YY) u - gamma*q0
+            for (int j = 0; j < used; ++j) {
+                const double uj = __shfl_sync(full, ui, j);
+                if (live) acc = fma(sh.Yl[i][j], uj, acc);
             }
-            for (int i = 0; i < used; ++i) {               // a = R^-T w
-                double t = sh.w[i];
-                for (int j = 0; j < i; ++j) t -= sh.Rm[j][i] * sh.av[j];
-                sh.av[i] = t / sh.Rm[i][i];
+            t = live ? rii * ui + gamma * acc - gamma * sh.qv[i] : 0.0;
+            double ai = 0.0;
+            for (int j = 0; j < used; ++j) {               // a = R^-T w   (forward substitution)
+                const double aj = __shfl_sync(full, t * inv, j);
+                if (i == j) ai = aj;
+                if (live && i > j) t = fma(-sh.Rm[j][i], aj, t);
             }
-            U = fabs(gamma) * sqrt(gg);
-            for (int i = 0; i < used; ++i) {
-                const int s = ph(i);
-                const double a = sh.av[i], gb = -gamma * sh.u[i];
-                coef_s[s] = a;
-                coef_s[m + s] = gb;
-                U += fabs(a) * sqrt(sh.ssv[i]) + fabs(gb) * sqrt(sh.Yl[i][i]);
-                ok = ok && finite_d(a) && finite_d(gb);
+            const double gb = -gamma * ui;
+            double term = 0.0;
+            bool fin = true;
+            if (live) {
+                const int sl = ph(i);
+                coef_s[sl] = ai;
+                coef_s[m + sl] = gb;
+                term = fabs(ai) * sqrt(sh.ssv[i]) + fabs(gb) * sqrt(sh.Yl[i][i]);
+                fin = finite_d(ai) && finite_d(gb);
             }
-            ok = ok && finite_d(gamma);
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(full, term, o);
+            U = fabs(gamma) * sqrt(gg) + term;
+            ok = ok && __all_sync(full, fin) && finite_d(gamma);
         }
         ok = ok && finite_d(U);
-        coef_s[2 * m] = gamma;
-        coef_s[2 * m + 1] = U;
-        coef_s[2 * m + 2] = gg;
-        int st = ST_ACCEPT;
-        if (A.check_nan) {
-            if (!ok) st = ST_REJECT_NONFINITE;
-            else if (used == 0) { if (U > A.limit) st = ST_REJECT_NONFINITE; }      // d = g: U is the exact norm (stochqn.c:829)
-            else if (!(U <= 0.99 * A.limit)) st = ST_NEED_EXACT_NORM;
+        if (i == 0) {
+            coef_s[2 * m] = gamma;
+            coef_s[2 * m + 1] = U;
+            coef_s[2 * m + 2] = gg;
+            int st = ST_ACCEPT;
+            if (A.check_nan) {
+                if (!ok) st = ST_REJECT_NONFINITE;
+                else if (used == 0) { if (U > A.limit) st = ST_REJECT_NONFINITE; }      // d = g: U is the exact norm (stochqn.c:829)
+                else if (!(U <= 0.99 * A.limit)) st = ST_NEED_EXACT_NORM;
+            }
+            if (!comm_ok) st = ST_COMM_TIMEOUT;
+            sh.status = st;
         }
-        if (!comm_ok) st = ST_COMM_TIMEOUT;
-        sh.status = st;
     }
     __syncthreads();
     return sh.status;

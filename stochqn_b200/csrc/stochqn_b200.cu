@@ -124,6 +124,7 @@ struct HostBlock {              // pinned, mapped: written by kernels, read by t
     volatile double pair[2];    // s'y, s's
     volatile double dir[2];     // sum d^2, number of non-finite entries
     volatile unsigned long long seq[3];   // written LAST by the kernel that fills status+info / pair / dir
+    volatile double fval;       // objective value of the guided-mode driver (stochqn_b200_fit_batch)
 };
 enum { FLAG_STATUS = 0, FLAG_PAIR = 1, FLAG_DIR = 2 };
 
@@ -242,7 +243,7 @@ bool is_device_ptr(const void* p)
 }
 
 constexpr int VECW = 16 / sizeof(real_t);
-constexpr long long kSmallNDefault = 32768;
+constexpr long long kSmallNDefault = 2048;
 bool aligned16(const void* p) { return (((uintptr_t) p) & 15u) == 0; }
 
 // ------------------------------------------------------------------------------------------
@@ -1122,3 +1123,4 @@ int run_SQN(real_t step_size, real_t x[], real_t grad[], real_t hess_vec[], real
 
 #include "adaqn_impl.inc"
 #include "ext_impl.inc"
+#include "guided_impl.inc"

@@ -247,6 +247,142 @@ def logistic_loss(w, X, y, sample_weight=None, reg_param=1e-5):
     return _r_call("loss", w, None, X, y, sample_weight, reg_param)
 
 
+# ---- the request loop of a mini-batch inside the library ----------------------------------------------------------
+class _NativeLoop:
+    """Mixin for the guided classes: when the data are device-resident row ranges and the callbacks are the bundled
+    ones, ``_fit_batch`` is ONE call into the library (``stochqn_b200_fit_batch``, include/stochqn_b200.h) instead of
+    one Python round trip per request.  Anything the native loop cannot serve exactly as the reference would (a long
+    batch that is not a row range, a step size that changes inside the loop, verbose event messages) goes through
+    the generic Python loop of ``stochqn_b200.guided`` - the results are the same either way
+    (tests/test_gpu_logistic_estimator.py runs both)."""
+
+    _native_model = None          # (model id, fit_intercept, nclasses) set by the estimator
+    native_batches = 0            # mini-batches served natively (diagnostics / tests)
+    use_native_loop = True
+
+    def _rows_struct(self, X, y, w, keep):
+        if X is None or not (_is_torch(X) and X.is_cuda and X.dim() == 2 and X.stride(1) == 1 and X.dtype == self.x.dtype):
+            return None
+        if not (_is_torch(y) and y.is_cuda and y.dtype == X.dtype and y.shape[0] == X.shape[0]):
+            return None
+        if y.dim() == 2:
+            if y.stride(1) != 1:
+                return None
+            ldy = y.stride(0) if y.shape[0] > 1 else y.shape[1]
+        else:
+            if y.shape[0] > 1 and y.stride(0) != 1:
+                return None
+            ldy = 1
+        if w is not None:
+            if not (_is_torch(w) and w.is_cuda and w.dtype == X.dtype and w.dim() == 1 and (w.shape[0] <= 1 or w.stride(0) == 1)):
+                return None
+        keep.extend((X, y, w))
+        ldx = X.stride(0) if X.shape[0] > 1 else X.shape[1]
+        return _lib.Rows(X.data_ptr(), ldx, y.data_ptr(), ldy, w.data_ptr() if w is not None else None, X.shape[0])
+
+    def _peek_stash(self):
+        """The stored batches as ONE row range (X, y, w) without emptying the stash, or None when they are not
+        consecutive rows of the same arrays (or mix weighted and unweighted batches)."""
+        from .guided import _merge_adjacent
+        st = self._stash
+        if not len(st):
+            return None
+        weighted = [w is not None for w in st.w]
+        if any(weighted) and not all(weighted):
+            return None
+        one = len(st) == 1
+        X = st.X[0] if one else _merge_adjacent(st.X)
+        y = st.y[0] if one else _merge_adjacent(st.y)
+        w = None if not weighted[0] else (st.w[0] if one else _merge_adjacent(st.w))
+        if X is None or y is None or (weighted[0] and w is None):
+            return None
+        return X, y, w
+
+    def _fit_batch(self, X_batch, y_batch, w_batch, additional_kwargs, is_user_batch=False,
+                   X_full=None, y_full=None, w_full=None, X_val=None, y_val=None, w_val=None, batch=None):
+        generic = super()._fit_batch
+        args = (X_batch, y_batch, w_batch, additional_kwargs)
+        kw = dict(is_user_batch=is_user_batch, X_full=X_full, y_full=y_full, w_full=w_full, X_val=X_val, y_val=y_val,
+                  w_val=w_val, batch=batch)
+        free = self.optimizer
+        const_step = (not is_user_batch) or self.decr_step_size is _step_size_const
+        if (not self.use_native_loop or self._native_model is None or self.verbose or not const_step
+                or not getattr(free, "initialized", False) or not hasattr(free, "_ws") or not _is_torch(self.x)
+                or set(additional_kwargs) - {"reg_param"}):
+            return generic(*args, **kw)
+        keep = []
+        rb = self._rows_struct(X_batch, y_batch, w_batch, keep)
+        if rb is None:
+            return generic(*args, **kw)
+        # the long batch as ONE row range, when the reference's rule yields one without touching the stash
+        rl, from_stash = None, False
+        if self.optimizer_name != "oLBFGS":
+            if is_user_batch:
+                view = self._peek_stash()
+                if view is not None:
+                    rl = self._rows_struct(view[0], view[1], view[2], keep)
+                    from_stash = rl is not None
+            elif X_full is not None:
+                first, last, diff = self._fit_long_rows(X_full.shape[0], batch)
+                if diff == 0:
+                    rl = self._rows_struct(X_full[first:last], y_full[first:last],
+                                           w_full[first:last] if w_full is not None else None, keep)
+        rv = self._rows_struct(X_val, y_val, w_val, keep) if X_val is not None else None
+        if X_val is not None and rv is None:
+            return generic(*args, **kw)
+
+        abi = free._abi
+        model_id, icpt, nclasses = self._native_model
+        ncols = X_batch.shape[1]
+        nmax = max(r.nrows for r in (rb, rl, rv) if r is not None)
+        if model_id == 2:
+            work = _scratch(X_batch.device, abi.lib.stochqn_b200_multinomial_work_size(nmax, ncols, nclasses))
+        else:
+            work = _scratch(X_batch.device, abi.lib.stochqn_b200_logistic_work_size(nmax, ncols))
+        M = abi.Model(model_id, icpt, ncols, nclasses, float(additional_kwargs.get("reg_param", 0)), work.data_ptr())
+        task = C.c_int({v: k for k, v in _TASK_CODES.items()}[self.req["task"]])
+        if not hasattr(free, "_req_vec"):
+            free._req_vec = C.c_void_p()
+        rep = _lib.FitReport()
+        step = self.decr_step_size(self.step_size, self.niter if is_user_batch else self.epoch)
+        rc = abi.lib.stochqn_b200_fit_batch(free._ws, self.x.data_ptr(), float(step), C.byref(M), C.byref(rb),
+                                            C.byref(rl) if rl is not None else None, C.byref(rv) if rv is not None else None,
+                                            C.byref(task), C.byref(free._req), C.byref(free._req_vec), C.byref(rep))
+        if rc < 0:
+            raise RuntimeError("stochqn_b200_fit_batch failed: " + _lib.last_error(abi))
+        if rep.long_batch_used and from_stash:
+            self._stash.clear()               # the reference empties its stash when it serves a long batch
+        n = self.x.shape[0]
+        at = free._wrap_req(free._req.value, self.x, n)
+        if task.value == 104:
+            at = (at, free._wrap_req(free._req_vec.value, self.x, n))
+        from .optimizers import info_dct
+        self.req = {"task": _TASK_CODES[task.value], "requested_on": at,
+                    "info": {"x_changed_in_run": bool(rep.x_changed), "iteration_number": self.niter,
+                             "iteration_info": info_dct[rep.last_info]}}
+        if rc == 1:                            # a request the native loop could not serve: the generic loop carries on
+            return generic(*args, **kw)
+        self.native_batches = self.native_batches + 1
+        if self.callback_iter is not None:
+            self.callback_iter(self.x, **self.kwargs_cb)
+
+
+_TASK_CODES = {101: "calc_grad", 102: "calc_grad_same_batch", 103: "calc_grad_big_batch", 104: "calc_hess_vec",
+               105: "calc_fun_val_batch"}
+
+
+class _oLBFGS_native(_NativeLoop, oLBFGS):
+    pass
+
+
+class _SQN_native(_NativeLoop, SQN):
+    pass
+
+
+class _adaQN_native(_NativeLoop, adaQN):
+    pass
+
+
 # ---- the estimator ----------------------------------------------------------------------------------------------
 class StochasticLogisticRegression:
     """Logistic regression fit with a stochastic quasi-Newton optimizer (reference: stochqn/_logistic.py:43-247).
@@ -286,6 +422,7 @@ class StochasticLogisticRegression:
         self.is_fitted = False
         self.random_state = random_state
         self.device = device
+        self.native_loop = True       # False: serve every request from Python (same results; for comparison / debugging)
         self._numpy_io = True
 
     # ---- fitted attributes ----------------------------------------------------------------------------------
@@ -386,11 +523,14 @@ class StochasticLogisticRegression:
         w0 = np.random.normal(size=(X.shape[1] + self.fit_intercept) * (y.shape[1] if self._is_mult else 1))
         w0 = torch.as_tensor(w0, device=X.device).to(X.dtype)
         if self.optimizer_name == "oLBFGS":
-            self.optimizer = oLBFGS(x0=w0, **funs, **self.optimizer_kwargs)
+            self.optimizer = _oLBFGS_native(x0=w0, **funs, **self.optimizer_kwargs)
         elif self.optimizer_name == "SQN":
-            self.optimizer = SQN(x0=w0, hess_vec_fun=hv, **funs, **self.optimizer_kwargs)
+            self.optimizer = _SQN_native(x0=w0, hess_vec_fun=hv, **funs, **self.optimizer_kwargs)
         else:
-            self.optimizer = adaQN(x0=w0, **funs, **self.optimizer_kwargs)
+            self.optimizer = _adaQN_native(x0=w0, **funs, **self.optimizer_kwargs)
+        # the request loop of a mini-batch runs inside the library (stochqn_b200_fit_batch) whenever it can
+        self.optimizer._native_model = (2 if self._is_mult else 1, int(self.fit_intercept), self.nclasses if self._is_mult else 0)
+        self.optimizer.use_native_loop = self.native_loop
 
     def fit(self, X, y, sample_weight=None):
         """Fit the model in stochastic batches (``batches_per_epoch`` / ``nepochs`` of the optimizer)."""

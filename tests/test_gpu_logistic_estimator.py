@@ -66,8 +66,8 @@ CASES = [
 
 
 @pytest.mark.parametrize("name,mult,optimizer,okw", CASES, ids=[c[0] for c in CASES])
-@pytest.mark.parametrize("container", ["numpy", "cuda"])
-def test_estimator_matches_host_twin(name, mult, optimizer, okw, container):
+@pytest.mark.parametrize("container,native", [("numpy", True), ("cuda", True), ("cuda", False)])
+def test_estimator_matches_host_twin(name, mult, optimizer, okw, container, native):
     import torch
     from stochqn_b200.logistic import StochasticLogisticRegression
 
@@ -81,7 +81,10 @@ def test_estimator_matches_host_twin(name, mult, optimizer, okw, container):
         conv = (lambda a: torch.tensor(a, device="cuda")) if container == "cuda" else (lambda a: a)
         m = StochasticLogisticRegression(reg_param=reg, fit_intercept=fit_intercept, random_state=1, optimizer=optimizer,
                                          step_size=step, valset_frac=0.1, verbose=False, **okw)
+        m.native_loop = native      # True: the request loop of a mini-batch runs inside the library (stochqn_b200_fit_batch)
         m.fit(conv(X), conv(y), conv(sw))
+    served = m.optimizer.native_batches
+    assert (served > 0) == native, "native request loop: %d mini-batches" % served
     assert m.optimizer.niter == twin.niter and m.optimizer.epoch == twin.epoch
     x = m.optimizer.x.cpu().numpy()
     scale = max(1.0, float(np.max(np.abs(twin.x))))
@@ -117,6 +120,7 @@ def test_estimator_partial_fit_and_float():
     Xd, yd = torch.tensor(X, device="cuda"), torch.tensor(y, device="cuda")
     for k in range(9):
         m.partial_fit(Xd[100 * k:100 * (k + 1)], yd[100 * k:100 * (k + 1)])
+    assert m.optimizer.native_batches > 0
     assert m.is_fitted and m.optimizer.niter == 9 and m.optimizer.x.dtype == torch.float32
     assert bool(torch.isfinite(m.optimizer.x).all())
     assert m.predict(Xd).shape == (X.shape[0],) and m.predict_proba(Xd).shape == (X.shape[0], 2)

@@ -38,7 +38,7 @@ def _gen_rows(nrows, d, dtype, intercept_first, seed):
     return X
 
 
-def run_logistic(name, kind, nrows, d, batch, steps, L=10, big=20000):
+def run_logistic(name, kind, nrows, d, batch, steps, L=10, big=20000, native=False):
     dtype, tdt, esz = np.float64, torch.float64, 8
     abi = _lib.load(dtype)
     lib = abi.lib
@@ -95,8 +95,31 @@ def run_logistic(name, kind, nrows, d, batch, steps, L=10, big=20000):
     call()
     niter = lambda: int(ws.contents.niter)
     warm = 15 * (L if kind == "SQN" else 1)
+    if native:
+        # the request loop of a mini-batch inside the library: ONE call per mini-batch (stochqn_b200_fit_batch);
+        # the long batch (last L mini-batches) is a row range of the resident matrix
+        M = abi.Model(0, 0, n, 0, lam, work.data_ptr())
+        rep = _lib.FitReport()
+
+        def rows_of(r0, cnt):
+            xp, yp = rows(r0, cnt)
+            return _lib.Rows(xp, n, yp, 1, None, cnt)
+
+        def serve_call():
+            state["b"] = b = (state["b"] + 1) % nb
+            rb = rows_of(b * batch, batch)
+            cnt = min(big, (b + 1) * batch)
+            rl = rows_of((b + 1) * batch - cnt, cnt)
+            rc = lib.stochqn_b200_fit_batch(ws, x.data_ptr(), step, C.byref(M), C.byref(rb), C.byref(rl), None, C.byref(task),
+                                            C.byref(req), C.byref(req_vec), C.byref(rep))
+            assert rc == 0, (rc, _lib.last_error(abi))
+            for i in range(4):
+                infos[200 + i] = infos.get(200 + i, 0) + rep.n_info[i]
+    else:
+        def serve_call():
+            serve(); call()
     while niter() < warm:
-        serve(); call()
+        serve_call()
     torch.cuda.synchronize()
     tasks.clear(); infos.clear()
     launches0 = _lib.launch_count()
@@ -104,13 +127,14 @@ def run_logistic(name, kind, nrows, d, batch, steps, L=10, big=20000):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     while niter() < it0 + steps:
-        serve(); call()
+        serve_call()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     xp, yp = rows(0, min(nrows, 20000))
     lib.stochqn_b200_logistic_loss(xp, n, yp, None, min(nrows, 20000), n, x.data_ptr(), lam, loss.data_ptr(), work.data_ptr(), None)
-    out = dict(config=name, optimizer=kind, dtype="f64", n=n, rows=nrows, batch=batch, steps=steps, ms_per_step=ms, steps_per_s=1e3 / ms,
+    out = dict(config=name, optimizer=kind, loop="library (stochqn_b200_fit_batch)" if native else "python (one call per request)",
+               dtype="f64", n=n, rows=nrows, batch=batch, steps=steps, ms_per_step=ms, steps_per_s=1e3 / ms,
                tasks=tasks, infos=infos, mem_used=int(ws.contents.bfgs_memory.contents.mem_used),
                launches_per_step=(_lib.launch_count() - launches0) / steps, loss_after=float(loss.item()), loss_at_zero=float(np.log(2.0)))
     {"oLBFGS": lib.dealloc_oLBFGS, "SQN": lib.dealloc_SQN}[kind](ws)
@@ -330,8 +354,12 @@ def main():
         return
     if "cfg1" in a.configs:
         run_logistic("cfg1", "oLBFGS", 100000, 1000, 1000, a.steps)
+    if "cfg1n" in a.configs:
+        run_logistic("cfg1", "oLBFGS", 100000, 1000, 1000, a.steps, native=True)
     if "cfg2" in a.configs:
         run_logistic("cfg2", "SQN", a.rows_cfg2, 4096, 2000, a.steps, L=10, big=20000)
+    if "cfg2n" in a.configs:
+        run_logistic("cfg2", "SQN", a.rows_cfg2, 4096, 2000, a.steps, L=10, big=20000, native=True)
     if "cfg3" in a.configs:
         run_multinomial("cfg3", np.float64, 1836, 159, 50, 6655, a.steps, 20, 100, 0, 1.01, 0.0, 1e-2)
     if "cfg5" in a.configs:

@@ -48,12 +48,25 @@ template <typename T>
 __device__ __forceinline__ double slice_dot(const T* __restrict__ a, const T* __restrict__ b, long long e0, long long e1, int lane)
 {
     double acc = 0;
-    for (long long i = e0 + lane; i < e1; i += 32) acc = fma((double) a[i], (double) b[i], acc);
+    long long i = e0 + lane;
+    for (; i + 7 * 32 < e1; i += 8 * 32) {              // 16 independent loads in flight per lane
+        T av[8], bv[8];
+        #pragma unroll
+        for (int u = 0; u < 8; ++u) { av[u] = a[i + u * 32]; bv[u] = b[i + u * 32]; }
+        #pragma unroll
+        for (int u = 0; u < 8; ++u) acc = fma((double) av[u], (double) bv[u], acc);
+    }
+    for (; i < e1; i += 32) acc = fma((double) a[i], (double) b[i], acc);
     return warp_sum(acc);
 }
 
+// Launched either as ONE CTA of 1024 threads with an ordinary launch (n <= kOneCtaN: no grid barrier at all) or as a
+// cooperative grid of 256-thread CTAs (one barrier).
+constexpr int kOneCtaThreads = 1024;
+constexpr long long kOneCtaN = 4096;
+
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kOneCtaThreads)
 ks_step(SmallArgs K, SolveArgs A, const T* g, T* gout, T* S, const T* __restrict__ Y,
         T* __restrict__ x, T* __restrict__ x_sum, T* __restrict__ grad_prev, T step,
         double* __restrict__ partials, double* __restrict__ SY, double* __restrict__ YY, double* __restrict__ SS,
@@ -63,6 +76,7 @@ ks_step(SmallArgs K, SolveArgs A, const T* g, T* gout, T* S, const T* __restrict
     const int m = K.msize, used = K.used, c = K.pend;
     const int P = 4 * m + 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nthr = (int) blockDim.x, nwarps = nthr >> 5;
     const long long per = (K.n + gridDim.x - 1) / gridDim.x;
     const long long e0 = (long long) blockIdx.x * per;
     const long long e1 = e0 + per < K.n ? e0 + per : K.n;
@@ -72,12 +86,12 @@ ks_step(SmallArgs K, SolveArgs A, const T* g, T* gout, T* S, const T* __restrict
 
     // ---- phase 1: this CTA's partial record --------------------------------------------------------------
     double* rec = partials + (size_t) blockIdx.x * P;
-    for (int p = threadIdx.x; p < P; p += kThreads) rec[p] = 0.0;
+    for (int p = threadIdx.x; p < P; p += nthr) rec[p] = 0.0;
     __syncthreads();
     const int nd = 2 * used + 1 + (c >= 0 ? 2 * used + 1 : 0);
     const T* yc = c >= 0 ? Y + (size_t) c * K.ld : nullptr;
     const T* sc = c >= 0 ? S + (size_t) c * K.ld : nullptr;
-    for (int d = warp; d < nd; d += kWarps) {
+    for (int d = warp; d < nd; d += nwarps) {
         const T *a, *b;
         int idx;
         if (d < used)              { a = S + (size_t) d * K.ld;                  b = g;  idx = d; }
@@ -89,14 +103,15 @@ ks_step(SmallArgs K, SolveArgs A, const T* g, T* gout, T* S, const T* __restrict
         const double v = slice_dot(a, b, e0, e1, lane);
         if (lane == 0) rec[idx] = v;
     }
-    if (grad_prev) for (long long i = e0 + threadIdx.x; i < e1; i += kThreads) grad_prev[i] = g[i];
+    if (grad_prev) for (long long i = e0 + threadIdx.x; i < e1; i += nthr) grad_prev[i] = g[i];
 
-    grid_barrier(bar, K.bar_target);
+    if (gridDim.x > 1) grid_barrier(bar, K.bar_target);
+    else __syncthreads();
 
     // ---- phase 2: every CTA reduces the records in the same order and solves ------------------------------
     {
         const int nb = (int) gridDim.x;
-        for (int p = warp; p < P; p += kWarps) {
+        for (int p = warp; p < P; p += nwarps) {
             double v = 0;
             for (int b = lane; b < nb; b += 32) v += __ldcg(partials + (size_t) b * P + p);
             v = warp_sum(v);
@@ -104,9 +119,9 @@ ks_step(SmallArgs K, SolveArgs A, const T* g, T* gout, T* S, const T* __restrict
         }
         __syncthreads();
     }
-    const int st = solve_cta(A, sums_s, SY, YY, SS, sh, coef_s, blockIdx.x == 0, true, kThreads);
+    const int st = solve_cta(A, sums_s, SY, YY, SS, sh, coef_s, blockIdx.x == 0, true, nthr);
     if (blockIdx.x == 0) {
-        for (int j = threadIdx.x; j < 2 * m + 3; j += kThreads) coef[j] = coef_s[j];
+        for (int j = threadIdx.x; j < 2 * m + 3; j += nthr) coef[j] = coef_s[j];
         __syncthreads();
         if (threadIdx.x == 0) publish_status(st, coef_s, m, status_dev, status_host, info_host, seq_host, A.seq);
     }
@@ -115,7 +130,7 @@ ks_step(SmallArgs K, SolveArgs A, const T* g, T* gout, T* S, const T* __restrict
     // ---- phase 3: combine + update (arithmetic of k3_combine) ------------------------------------------
     const T gamma = (T) coef_s[2 * m];
     const T nstep = -step;
-    for (long long i = e0 + threadIdx.x; i < e1; i += kThreads) {
+    for (long long i = e0 + threadIdx.x; i < e1; i += nthr) {
         T p0 = gamma * g[i], p1 = (T) 0;
         for (int r = 0; r < used; ++r) {
             p0 = fma((T) coef_s[r], S[(size_t) r * K.ld + i], p0);

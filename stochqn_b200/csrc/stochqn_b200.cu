@@ -172,6 +172,7 @@ struct Ctx {
     unsigned long long bar_total = 0;   // its value once every launch issued so far has passed its barrier
     unsigned int* ticket = nullptr;     // "last block done" ticket of K4
     long long small_n = 0;              // use ks_step when n <= small_n (0: never)
+    long long one_cta_n = kOneCtaN;     // ... as one 1024-thread CTA (ordinary launch) up to this n, cooperative grid above
     double small_steps = 0;             // steps that took the one-launch route
 };
 
@@ -243,7 +244,7 @@ bool is_device_ptr(const void* p)
 }
 
 constexpr int VECW = 16 / sizeof(real_t);
-constexpr long long kSmallNDefault = 2048;
+constexpr long long kSmallNDefault = 4096;
 bool aligned16(const void* p) { return (((uintptr_t) p) & 15u) == 0; }
 
 // ------------------------------------------------------------------------------------------
@@ -497,10 +498,12 @@ int launch_small_step(Ctx* c, const real_t* g, real_t* gout, real_t* S, const re
 {
     SmallArgs K;
     K.msize = c->msize; K.used = used; K.pend = pend; K.new_slot = new_slot; K.n = c->n; K.ld = c->ld;
-    long long grid = (c->n + kThreads - 1) / kThreads;
+    // n <= kOneCtaN: ONE CTA of 1024 threads, ordinary launch, no grid barrier; above: cooperative grid of 256-thread CTAs
+    const bool one_cta = c->n <= c->one_cta_n;
+    long long grid = one_cta ? 1 : (c->n + kThreads - 1) / kThreads;
     if (grid > c->sm_count) grid = c->sm_count;
     if (grid < 1) grid = 1;
-    c->bar_total += (unsigned long long) grid;
+    if (grid > 1) c->bar_total += (unsigned long long) grid;
     K.bar_target = c->bar_total;
     SolveArgs A;
     A.msize = c->msize; A.used = used; A.oldest = oldest; A.pend = pend; A.nblocks = (int) grid; A.do_solve = 1;
@@ -514,7 +517,8 @@ int launch_small_step(Ctx* c, const real_t* g, real_t* gout, real_t* S, const re
     unsigned long long* bar = c->bar;
     void* args[] = {&K, &A, &g, &gout, &S, &Y, &x, &x_sum, &grad_prev, &step, &partials, &SY, &YY, &SS, &coef,
                     &status_dev, &status_host, &info_host, &seq_host, &bar};
-    CUDA_TRY(cudaLaunchCooperativeKernel((const void*) ks_step<real_t, MODE>, dim3((unsigned) grid), dim3(kThreads), args, 0, c->stream));
+    if (grid > 1) CUDA_TRY(cudaLaunchCooperativeKernel((const void*) ks_step<real_t, MODE>, dim3((unsigned) grid), dim3(kThreads), args, 0, c->stream));
+    else CUDA_TRY(cudaLaunchKernel((const void*) ks_step<real_t, MODE>, dim3(1), dim3(kOneCtaThreads), args, 0, c->stream));
     COUNT_LAUNCH();
     c->small_steps += 1;
     return 0;
@@ -614,7 +618,10 @@ Ctx* make_ctx(Kind kind, long long n, int msize, int fisher_size)
         int coop = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
         const char* e = getenv("STOCHQN_B200_SMALL_N");
-        c->small_n = coop ? (e ? atoll(e) : kSmallNDefault) : 0;
+        c->small_n = e ? atoll(e) : kSmallNDefault;
+        const char* e1 = getenv("STOCHQN_B200_ONE_CTA_N");
+        if (e1) c->one_cta_n = atoll(e1);
+        if (!coop && c->small_n > c->one_cta_n) c->small_n = c->one_cta_n;       // the multi-CTA form needs a cooperative launch
     }
     ok = ok && cudaHostAlloc((void**) &c->hb, sizeof(HostBlock), cudaHostAllocMapped) == cudaSuccess;
     if (ok) {

@@ -59,8 +59,8 @@ enum stochqn_b200_option {
        before every return, the reference's contract.  Host-pointer calls always return with everything final. */
     STOCHQN_B200_OPT_SYNC_RETURN = 4,
     /* oLBFGS / SQN: largest n for which a step is ONE launch (dots, solve and update fused - for the latency-bound
-       sizes where three launches dominate) instead of K1 -> K2 -> K3: a single 1024-thread CTA up to n = 4096, a
-       cooperative grid with one grid barrier above.  Default 4096 (environment: STOCHQN_B200_SMALL_N); 0 disables.
+       sizes where three launches dominate) instead of K1 -> K2 -> K3: a single 1024-thread CTA up to n = 2048, a
+       cooperative grid with one grid barrier above.  Default 2048 (environment: STOCHQN_B200_SMALL_N); 0 disables.
        Not used when the optimizer is sharded. */
     STOCHQN_B200_OPT_ONE_LAUNCH_MAX_N = 5
 };
@@ -73,7 +73,7 @@ enum stochqn_b200_stat {
     STOCHQN_B200_STAT_LAST_BOUND = 7,                                 /* bound on ||direction|| of the last step */
     STOCHQN_B200_STAT_EXACT_NORM_STEPS = 8,                           /* steps that needed the exact-norm (two-pass) route */
     STOCHQN_B200_STAT_KA2_MS = 9, STOCHQN_B200_STAT_KA2_COUNT = 10,   /* adaQN: the second dot pass (K1/K3 slots hold KA1/KA3) */
-    /* steps taken by the one-launch kernel used for latency-bound sizes (n <= 4096 unless STOCHQN_B200_SMALL_N
+    /* steps taken by the one-launch kernel used for latency-bound sizes (n <= 2048 unless STOCHQN_B200_SMALL_N
        says otherwise; 0 there disables it): dots, solve and update in one cooperative launch instead of three */
     STOCHQN_B200_STAT_ONE_LAUNCH_STEPS = 11
 };

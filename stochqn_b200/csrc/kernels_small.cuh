@@ -60,10 +60,10 @@ __device__ __forceinline__ double slice_dot(const T* __restrict__ a, const T* __
     return warp_sum(acc);
 }
 
-// Launched either as ONE CTA of 1024 threads with an ordinary launch (n <= kOneCtaN: no grid barrier at all) or as a
+// Launched either as ONE CTA of 1024 threads with an ordinary launch (n <= kOneCtaN = 2048: no grid barrier at all) or as a
 // cooperative grid of 256-thread CTAs (one barrier).
 constexpr int kOneCtaThreads = 1024;
-constexpr long long kOneCtaN = 4096;
+constexpr long long kOneCtaN = 2048;
 
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kOneCtaThreads)

@@ -762,78 +762,144 @@ k_avg(T* __restrict__ x_sum, T* __restrict__ other, T* __restrict__ s_slot, T in
 
 // =========================================================================================
 // Empirical-Fisher product (stochqn.c:936-952):  y = F' (F s) / k  over the first k ring rows.
-//   KF1: t_r = F_r's for rows r0..r0+RB   (record [k], entry r)
-//   KF2: y (+)= sum_r c_r F_r for rows r0..r0+RB, c_r = t_r / k read from device memory
-// Two sweeps of F (2k vector transfers): HBM-bound skinny GEMV pair.
+//   KF1: t_r = F_r's for 4*RPG rows per launch (record [k], entry r) - the work split of K1: 4 row-groups x 64
+//        chunk-lanes, two chunks in flight per thread, rows loaded with L1::no_allocate, s shared through L1
+//   KF2: y = (1/k) sum_r t_r F_r in ONE launch - the work split of K3: 128-thread CTAs = 2 row-groups x 64 lanes, each
+//        group streams half of the rows (RB loads in flight), the halves meet in shared memory, y is written once
+// Two sweeps of F (2k vector transfers + one read of s per KF1 launch + one write of y): HBM-bound skinny GEMV pair.
 // =========================================================================================
-template <typename T, int RB, int VEC>
-__global__ void __launch_bounds__(kThreads)
+template <typename T, int RPG, int VEC>
+__global__ void __launch_bounds__(kThreads, 2)
 kf1_rowdots(const T* __restrict__ F, size_t ld, int r0, int rows, const T* __restrict__ s, long long n,
             int rec, double* __restrict__ partials)
 {
-    double acc[RB];
+    const int group = threadIdx.x / kLanes, lane = threadIdx.x % kLanes;
+    const T* rp[RPG];
     #pragma unroll
-    for (int r = 0; r < RB; ++r) acc[r] = 0;
-    auto one = [&](size_t off, auto vtag) {
+    for (int r = 0; r < RPG; ++r) {
+        int v = group * RPG + r;
+        if (v >= rows) v = rows - 1;                 // clamped duplicate: dropped at the end
+        rp[r] = F + (size_t) (r0 + v) * ld;
+    }
+    double acc[RPG];
+    #pragma unroll
+    for (int r = 0; r < RPG; ++r) acc[r] = 0;
+    auto many = [&](const long long (&c)[kUnroll], auto vtag) {
         constexpr int V = decltype(vtag)::value;
-        Pack<T, V> sv = ld_stream<T, V>(s + off);
+        Pack<T, V> sv[kUnroll], rv[kUnroll][RPG];
         #pragma unroll
-        for (int r = 0; r < RB; ++r) {
-            if (r < rows) {
-                Pack<T, V> fv = ld_stream<T, V>(F + (size_t) (r0 + r) * ld + off);
+        for (int u = 0; u < kUnroll; ++u) {
+            if (c[u] >= 0) {
+                const size_t off = (size_t) c[u] * V;
+                sv[u] = ld_stream<T, V>(s + off);
                 #pragma unroll
-                for (int e = 0; e < V; ++e) acc[r] = fma((double) fv.get(e), (double) sv.get(e), acc[r]);
+                for (int r = 0; r < RPG; ++r) rv[u][r] = ld_row<T, V>(rp[r] + off);
+            }
+        }
+        #pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (c[u] >= 0) {
+                #pragma unroll
+                for (int r = 0; r < RPG; ++r) {
+                    #pragma unroll
+                    for (int e = 0; e < V; ++e) acc[r] = fma((double) rv[u][r].get(e), (double) sv[u].get(e), acc[r]);
+                }
             }
         }
     };
     const long long nchunks = n / VEC;
-    const long long stride = (long long) gridDim.x * kThreads;
-    for (long long c = (long long) blockIdx.x * kThreads + threadIdx.x; c < nchunks; c += stride)
-        one((size_t) c * VEC, std::integral_constant<int, VEC>{});
-    if (VEC > 1 && blockIdx.x == 0) {
-        const long long i = nchunks * VEC + threadIdx.x;
-        if (i < n) one((size_t) i, std::integral_constant<int, 1>{});
+    const long long stride = (long long) gridDim.x * kLanes;
+    for (long long c0 = (long long) blockIdx.x * kLanes + lane; c0 < nchunks; c0 += stride * kUnroll) {
+        long long c[kUnroll];
+        #pragma unroll
+        for (int u = 0; u < kUnroll; ++u) { c[u] = c0 + u * stride; if (c[u] >= nchunks) c[u] = -1; }
+        many(c, std::integral_constant<int, VEC>{});
     }
+    if (VEC > 1 && blockIdx.x == 0) {               // scalar tail: n not a multiple of VEC
+        const long long i = nchunks * VEC + lane;
+        long long c[kUnroll];
+        #pragma unroll
+        for (int u = 0; u < kUnroll; ++u) c[u] = -1;
+        if (i < n) { c[0] = i; many(c, std::integral_constant<int, 1>{}); }
+    }
+    __shared__ double red[kWarps][RPG];
+    const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
+    #pragma unroll
+    for (int r = 0; r < RPG; ++r) {
+        const double v = warp_sum(acc[r]);
+        if (wl == 0) red[warp][r] = v;
+    }
+    __syncthreads();
     double* out = partials + (size_t) blockIdx.x * rec + r0;
-    block_reduce<RB>(RB, [&](int p) -> double { return acc[p < RB ? p : 0]; },
-                     [&](int p, double v) { if (p < rows) out[p] = v; });
+    constexpr int WPG = kWarps / kGroups;
+    for (int t = threadIdx.x; t < kGroups * RPG; t += kThreads) {
+        const int gi = t / RPG, r = t % RPG, vrow = gi * RPG + r;
+        if (vrow >= rows) continue;
+        double v = 0;
+        #pragma unroll
+        for (int w = 0; w < WPG; ++w) v += red[gi * WPG + w][r];
+        out[vrow] = v;
+    }
 }
 
 template <typename T, int RB, int VEC>
-__global__ void __launch_bounds__(kThreads)
-kf2_combine(const T* __restrict__ F, size_t ld, int r0, int rows, const double* __restrict__ t, double inv_k,
-            T* __restrict__ y, int accumulate, long long n)
+__global__ void __launch_bounds__(k3Threads, 4)
+kf2_combine(const T* __restrict__ F, size_t ld, int k, const double* __restrict__ t, double inv_k,
+            T* __restrict__ y, long long n)
 {
-    T c[RB];
-    #pragma unroll
-    for (int r = 0; r < RB; ++r) c[r] = (r < rows) ? (T) t[r0 + r] : (T) 0;    // buffer_y in storage precision (stochqn.c:946-947)
+    extern __shared__ __align__(16) unsigned char kf2_smem[];
+    T* cs = reinterpret_cast<T*>(kf2_smem);                        // buffer_y in storage precision (stochqn.c:946-947)
+    for (int i = threadIdx.x; i < k; i += k3Threads) cs[i] = (T) t[i];
+    __shared__ __align__(16) T xchg[2][k3Lanes * (VEC > 1 ? VEC : 1)];
+    __syncthreads();
+    const int group = threadIdx.x / k3Lanes, lane = threadIdx.x % k3Lanes;
+    const int half = (k + 1) / 2;
+    const int r_begin = group == 0 ? 0 : half, r_end = group == 0 ? half : k;
     const T alpha = (T) inv_k;
-    auto one = [&](size_t off, auto vtag) {
+    int buf = 0;
+    auto one = [&](size_t off, bool valid, auto vtag) {
         constexpr int V = decltype(vtag)::value;
         Pack<T, V> acc;
         #pragma unroll
         for (int e = 0; e < V; ++e) acc.set(e, (T) 0);
-        #pragma unroll
-        for (int r = 0; r < RB; ++r) {
-            if (r < rows) {
-                Pack<T, V> fv = ld_stream<T, V>(F + (size_t) (r0 + r) * ld + off);
+        if (valid) {
+            for (int rb = r_begin; rb < r_end; rb += RB) {
+                Pack<T, V> fv[RB];
                 #pragma unroll
-                for (int e = 0; e < V; ++e) acc.set(e, fma(c[r], fv.get(e), acc.get(e)));
+                for (int q = 0; q < RB; ++q) {
+                    const int r = rb + q < r_end ? rb + q : r_end - 1;
+                    fv[q] = ld_row<T, V>(F + (size_t) r * ld + off);
+                }
+                #pragma unroll
+                for (int q = 0; q < RB; ++q) {
+                    const T cq = rb + q < r_end ? cs[rb + q] : (T) 0;
+                    #pragma unroll
+                    for (int e = 0; e < V; ++e) acc.set(e, fma(cq, fv[q].get(e), acc.get(e)));
+                }
             }
         }
-        Pack<T, V> yv;
-        if (accumulate) yv = ld_rw<T, V>(y + off);
-        #pragma unroll
-        for (int e = 0; e < V; ++e) yv.set(e, accumulate ? fma(alpha, acc.get(e), yv.get(e)) : alpha * acc.get(e));
-        st_vec<T, V>(y + off, yv);
+        if (group == 1) {
+            #pragma unroll
+            for (int e = 0; e < V; ++e) xchg[buf][lane * V + e] = acc.get(e);
+        }
+        __syncthreads();
+        if (group == 0 && valid) {
+            Pack<T, V> yv;
+            #pragma unroll
+            for (int e = 0; e < V; ++e) yv.set(e, alpha * (acc.get(e) + xchg[buf][lane * V + e]));
+            st_vec<T, V>(y + off, yv);
+        }
+        buf ^= 1;
     };
     const long long nchunks = n / VEC;
-    const long long stride = (long long) gridDim.x * kThreads;
-    for (long long c2 = (long long) blockIdx.x * kThreads + threadIdx.x; c2 < nchunks; c2 += stride)
-        one((size_t) c2 * VEC, std::integral_constant<int, VEC>{});
-    if (VEC > 1 && blockIdx.x == 0) {
-        const long long i = nchunks * VEC + threadIdx.x;
-        if (i < n) one((size_t) i, std::integral_constant<int, 1>{});
+    const long long stride = (long long) gridDim.x * k3Lanes;
+    for (long long base = (long long) blockIdx.x * k3Lanes; base < nchunks; base += stride) {     // block-uniform trip count
+        const long long c = base + lane;
+        one((size_t) c * VEC, c < nchunks, std::integral_constant<int, VEC>{});
+    }
+    if (VEC > 1 && blockIdx.x == 0 && nchunks * VEC < n) {
+        const long long i = nchunks * VEC + lane;
+        one((size_t) i, i < n, std::integral_constant<int, 1>{});
     }
 }
 

@@ -134,6 +134,24 @@ def run(name, iters=60, warm=None):
         out.update(ka1_ms=d1, ka1_gbs=v1 * vec / d1 / 1e6, ka2_ms=d2, ka2_gbs=v2 * vec / max(d2, 1e-9) / 1e6, ka3_ms=d3,
                    ka3_gbs=v3 * vec / d3 / 1e6, step_vec=v1 + v2 + v3)
     out["k4_ms"] = d4
+    if kind == "adaQN" and fisher and not gd:
+        # empirical-Fisher pair update y = F'(F s)/k (KF1 + KF2: two sweeps of the k stored gradients): make every step
+        # a pair step and time whole calls; the ordinary-step time measured above is subtracted
+        bm = ws.contents.bfgs_memory.contents
+        bm.upd_freq = 1
+        serve_and_call()
+        torch.cuda.synchronize()
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            serve_and_call()
+        e1.record()
+        torch.cuda.synchronize()
+        pair_ms = e0.elapsed_time(e1) / reps
+        k = int(ws.contents.fisher_memory.contents.mem_used)
+        extra = max(pair_ms - ms, 1e-9)
+        out.update(fisher_rows=k, pair_step_ms=pair_ms, fisher_extra_ms=extra, fisher_gbs=2 * k * vec / extra / 1e6,
+                   fisher_note="pair step minus ordinary step: KF1 + KF2 (2k vec) + s-vector / curvature kernels (about 8 vec, not counted)")
     out["step_gbs_optimizer_only"] = out["step_vec"] * vec / max(d1 + d2 + d3, 1e-9) / 1e6
     {"SQN": lib.dealloc_SQN, "adaQN": lib.dealloc_adaQN}[kind](ws)
     del x, g, a, cc

@@ -197,11 +197,15 @@ __device__ __forceinline__ void ada_stage_and_solve_u(const SolveArgs& A, const 
         st.yyv[i] = YY[ph(i) * m + ph(i)];
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int i = used - 1; i >= 0; --i) {
-            double t = st.pv[i];
-            for (int j = i + 1; j < used; ++j) t -= st.Rm[i][j] * st.u[j];
-            st.u[i] = t / st.Rm[i][i];
+    if (threadIdx.x < 32) {                 // warp-parallel back substitution: lane i owns row i (see solve_cta, kernels.cuh)
+        const int i = threadIdx.x;
+        const bool live = i < used;
+        const double inv = 1.0 / (live ? st.Rm[i][i] : 1.0);
+        double t = live ? st.pv[i] : 0.0;
+        for (int j = used - 1; j >= 0; --j) {
+            const double uj = __shfl_sync(0xffffffffu, t * inv, j);
+            if (i == j) st.u[i] = uj;
+            if (i < j) t = fma(-st.Rm[i][j], uj, t);
         }
     }
     __syncthreads();
@@ -336,22 +340,35 @@ ka_solve_a(SolveArgs A, PeerArgs pa, const double* __restrict__ partials, const 
     auto ph = [&](int i) { int s = A.oldest + i; return s >= m ? s - m : s; };
     for (int i = threadIdx.x; i < used; i += kThreads) st.w[i] = st.Rm[i][i] * st.u[i] + sums2[ph(i)];
     __syncthreads();
-    if (threadIdx.x != 0) return;
+    if (threadIdx.x >= 32) return;
     const double tt = sums2[m];
     double U = sqrt(tt);
     bool ok = finite_d(tt) && (*status_dev != ST_COMM_TIMEOUT);
     comm_ok = comm_ok && (*status_dev != ST_COMM_TIMEOUT);
-    for (int i = 0; i < used; ++i) {
-        double t = st.w[i];
-        for (int j = 0; j < i; ++j) t -= st.Rm[j][i] * st.av[j];
-        st.av[i] = t / st.Rm[i][i];
+    {                                        // warp-parallel forward substitution a = R^-T w: lane i owns row i
+        const unsigned full = 0xffffffffu;
+        const int i = threadIdx.x;
+        const bool live = i < used;
+        const double inv = 1.0 / (live ? st.Rm[i][i] : 1.0);
+        double t = live ? st.w[i] : 0.0, ai = 0.0;
+        for (int j = 0; j < used; ++j) {
+            const double aj = __shfl_sync(full, t * inv, j);
+            if (i == j) ai = aj;
+            if (live && i > j) t = fma(-st.Rm[j][i], aj, t);
+        }
+        double term = 0.0;
+        bool fin = true;
+        if (live) {
+            coef[ph(i)] = ai;
+            term = fabs(ai) * sqrt(st.ssv[i]);
+            fin = finite_d(ai) && finite_d(st.u[i]);
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(full, term, o);
+        U += term;
+        ok = ok && __all_sync(full, fin);
     }
-    for (int i = 0; i < used; ++i) {
-        const double a = st.av[i];
-        coef[ph(i)] = a;
-        U += fabs(a) * sqrt(st.ssv[i]);
-        ok = ok && finite_d(a) && finite_d(st.u[i]);
-    }
+    if (threadIdx.x != 0) return;
     ok = ok && finite_d(U);
     coef[2 * m] = 1.0;
     coef[2 * m + 1] = U;

@@ -6,7 +6,9 @@ PARITY UNPINNED.  The arithmetic is third-party: private functions `_multinomial
 release carrying them: 1.0.2; the reference pins no version: requirements.txt:3, setup.py:45).  That package is
 neither vendored under /root/reference nor importable here (scikit-learn 1.9 removed them), and the reference holds no
 test or golden vector for this path, so this file restates the published algorithm of scikit-learn 1.0.2 and nothing
-checks it against the reference's own output:
+checks it against the reference's own output.  It IS cross-checked against an independent implementation: the installed
+scikit-learn's `LinearModelLoss(HalfMultinomialLoss)`, successor of those functions, agrees to 1e-13 on loss, gradient
+and Hessian-vector product when the sample weights sum to one (tests/test_oracle_sklearn_crosscheck.py):
 
     w            reshaped (n_classes, n_features [+1]) row-major, intercept = last column
     p            = X @ w.T + intercept ;  p -= logsumexp(p, axis=1) ;  loss = -(sw * Y * p).sum() + 0.5*alpha*||w||^2 ; p = exp(p)

@@ -106,7 +106,8 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 template <int BN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 float* __restrict__ C, long long ldc, int M, int N, int K)
+                 float* __restrict__ C, long long ldc, int M, int N, int K,
+                 const float* __restrict__ addend, long long ld_add, float alpha)
 {
     constexpr int STAGES = Cfg<BN>::STAGES;
     constexpr uint32_t STAGE_BYTES = Cfg<BN>::STAGE_BYTES, TMEM_COLS = Cfg<BN>::TMEM_COLS;
@@ -219,7 +220,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 #pragma unroll 4
                 for (int r = 0; r < 32; ++r) {
                     const int row = m0 + q * 32 + r;
-                    if (row < M && col < N) C[(long long) row * ldc + col] = stage[r * EPI_LD + lane];
+                    if (row < M && col < N) {
+                        float val = stage[r * EPI_LD + lane];
+                        // fused epilogue: C = A B' + alpha * addend (the penalty term alpha*W of the gradient rides here)
+                        if (addend) val = fmaf(alpha, __ldg(addend + (long long) row * ld_add + col), val);
+                        C[(long long) row * ldc + col] = val;
+                    }
                 }
                 __syncwarp();
             }
@@ -294,7 +300,8 @@ inline bool sm100_gemm_tf32_usable(const float* A, long long lda, const float* B
 
 // returns 0 = launched, 1 = tensor-core path not available here (caller falls back), < 0 = error
 inline int sm100_gemm_tf32(const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc,
-                           int M, int N, int K, cudaStream_t st)
+                           int M, int N, int K, cudaStream_t st, const float* addend = nullptr, long long ld_add = 0,
+                           float alpha = 0.f)
 {
     using namespace tf32gemm;
     Host& h = host();
@@ -308,7 +315,7 @@ inline int sm100_gemm_tf32(const float* A, long long lda, const float* B, long l
     if (!make_map(h, &ma, A, lda, M, K, BM) || !make_map(h, &mb, B, ldb, N, K, wide ? 256 : 128)) return 1;
     const long long ntiles = tiles_m * ((N + (wide ? 255 : 127)) / (wide ? 256 : 128));
     const int grid = (int) (ntiles < h.sms ? ntiles : h.sms);
-    if (wide) gemm_tf32_kernel<256><<<grid, THREADS, Cfg<256>::SMEM_BYTES, st>>>(ma, mb, C, ldc, M, N, K);
-    else      gemm_tf32_kernel<128><<<grid, THREADS, Cfg<128>::SMEM_BYTES, st>>>(ma, mb, C, ldc, M, N, K);
+    if (wide) gemm_tf32_kernel<256><<<grid, THREADS, Cfg<256>::SMEM_BYTES, st>>>(ma, mb, C, ldc, M, N, K, addend, ld_add, alpha);
+    else      gemm_tf32_kernel<128><<<grid, THREADS, Cfg<128>::SMEM_BYTES, st>>>(ma, mb, C, ldc, M, N, K, addend, ld_add, alpha);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

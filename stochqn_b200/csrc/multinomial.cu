@@ -254,15 +254,30 @@ struct MnPlan {
 };
 
 // Wp[K x ldp] = W[:, :d]  (coefficient block without the intercept column, rows 16-byte aligned: what TMA needs)
+// One CTA per coefficient row at a time (no index division; coalesced 4-byte accesses on both sides).
 template <typename T>
-__global__ void mn_pack(const T* __restrict__ W, long long ldw, T* __restrict__ Wp, long long ldp, int K, int d)
+__global__ void __launch_bounds__(256)
+mn_pack(const T* __restrict__ W, long long ldw, T* __restrict__ Wp, long long ldp, int K, int d)
 {
-    const long long total = (long long) K * d;
-    const long long stride = (long long) gridDim.x * blockDim.x;
-    for (long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-        const long long k = t / d, j = t - k * d;
-        Wp[k * ldp + j] = W[k * ldw + j];
+    for (int k = blockIdx.x; k < K; k += gridDim.x) {
+        const T* src = W + (long long) k * ldw;
+        T* dst = Wp + (long long) k * ldp;
+        for (int j = threadIdx.x; j < d; j += 256) dst[j] = __ldg(src + j);
     }
+}
+
+// intercept column of the gradient / Hessian-vector product: G[k][d] = sum_i DT[k][i]; one warp per class
+template <typename T>
+__global__ void __launch_bounds__(256)
+mn_intercept(T* __restrict__ G, long long ldg, int d, const T* __restrict__ DT, long long ldt, int B, int K)
+{
+    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (k >= K) return;
+    double s = 0.0;
+    for (int i = lane; i < B; i += 32) s += (double) DT[(long long) k * ldt + i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) G[(long long) k * ldg + d] = (T) s;
 }
 
 MnPlan mn_plan(long long B, long long d, long long K)
@@ -295,13 +310,17 @@ MnPlan mn_plan(long long B, long long d, long long K)
 }
 
 // C = A B' with the k-range split `splits` ways (partials `cz_stride` apart); tensor cores when the fp32 build can
+// `addend` / `alpha`: C = A B' + alpha * addend fused into the tensor-core epilogue; *fused tells the caller whether that
+// happened (the CUDA-core kernel leaves it to a separate pass).
 int launch_gemm(const real_t* A, long long lda, const real_t* Bm, long long ldb, real_t* C, long long ldc, long long cz_stride,
-                int M, int N, int Kc, int splits, cudaStream_t st)
+                int M, int N, int Kc, int splits, cudaStream_t st, const real_t* addend = nullptr, long long ld_add = 0,
+                real_t alpha = 0, bool* fused = nullptr)
 {
+    if (fused) *fused = false;
 #ifdef USE_FLOAT
     if (splits == 1 && !getenv("STOCHQN_B200_NO_TENSOR_CORES") && sm100_gemm_tf32_usable(A, lda, Bm, ldb, C, ldc, M, N, Kc)) {
-        const int r = sm100_gemm_tf32(A, lda, Bm, ldb, C, ldc, M, N, Kc, st);
-        if (r == 0) return mn_check("gemm (tcgen05 tf32)", 1);
+        const int r = sm100_gemm_tf32(A, lda, Bm, ldb, C, ldc, M, N, Kc, st, addend, ld_add, alpha);
+        if (r == 0) { if (fused) *fused = addend != nullptr; return mn_check("gemm (tcgen05 tf32)", 1); }
         if (r != 1) return r;                       // 1 = not available on this device / driver: fall through
     }
 #endif
@@ -335,12 +354,12 @@ int mn_common(int kind, const real_t* X, long long ldx, const real_t* Y, long lo
     if (p.splits == 1 && (ldw & 3) && !getenv("STOCHQN_B200_NO_TENSOR_CORES") &&
         sm100_gemm_tf32_usable(X, ldx, (const real_t*) (base + p.off_wp), p.dpad, nullptr, 0, (int) B, (int) K, (int) d)) {
         real_t* Wp = (real_t*) (base + p.off_wp);
-        mn_pack<real_t><<<1184, 256, 0, st>>>(w, ldw, Wp, p.dpad, (int) K, (int) d);
+        mn_pack<real_t><<<(unsigned) (K < 4736 ? K : 4736), 256, 0, st>>>(w, ldw, Wp, p.dpad, (int) K, (int) d);
         w1 = Wp; ld1 = p.dpad;
         int packed = 1;
         if (kind == MN_HVP) {
             real_t* Vp = (real_t*) (base + p.off_vp);
-            mn_pack<real_t><<<1184, 256, 0, st>>>(v, ldw, Vp, p.dpad, (int) K, (int) d);
+            mn_pack<real_t><<<(unsigned) (K < 4736 ? K : 4736), 256, 0, st>>>(v, ldw, Vp, p.dpad, (int) K, (int) d);
             v1 = Vp;
             ++packed;
         }
@@ -371,7 +390,15 @@ int mn_common(int kind, const real_t* X, long long ldx, const real_t* Y, long lo
         ++launched;
         if (int r = mn_check("multinomial rows", launched)) return r;
         // GEMM 2: G = DT XT'
-        if (int r = launch_gemm(DT, p.bpad, XT, p.bpad, out, ldw, 0, (int) K, (int) d, (int) B, 1, st)) return r;
+        // (+ alpha * W or alpha * V fused into the tensor-core epilogue: saves a read-modify-write pass over the gradient)
+        bool fused = false;
+        if (int r = launch_gemm(DT, p.bpad, XT, p.bpad, out, ldw, 0, (int) K, (int) d, (int) B, 1, st,
+                                kind == MN_HVP ? v : w, ldw, alpha, &fused)) return r;
+        if (fused) {
+            if (!fit_intercept) return 0;
+            mn_intercept<real_t><<<(unsigned) ((K + 7) / 8), 256, 0, st>>>(out, ldw, (int) d, DT, p.bpad, (int) B, (int) K);
+            return mn_check("multinomial intercept", 1);
+        }
         mn_finish<real_t><<<(unsigned) K, 256, 0, st>>>(out, ldw, kind == MN_HVP ? v : w, ldw, (int) d, fit_intercept, alpha, DT, p.bpad, (int) B);
         return mn_check("multinomial finish", 1);
     }

@@ -35,9 +35,11 @@ class CudaStepper:
         self.n = n
         tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
         if mode == "device":
-            self.x = torch.tensor(np.asarray(x0, dtype=dtype), device="cuda", dtype=tdt)
-            self.grad = torch.zeros(n, device="cuda", dtype=tdt)
-            self.hess_vec = torch.zeros(n, device="cuda", dtype=tdt)
+            off = 1 if kw.get("misalign") else 0      # views that start one element into an allocation: not 16-byte aligned
+            self.x = torch.zeros(n + off, device="cuda", dtype=tdt)[off:]
+            self.x.copy_(torch.tensor(np.asarray(x0, dtype=dtype), device="cuda", dtype=tdt))
+            self.grad = torch.zeros(n + off, device="cuda", dtype=tdt)[off:]
+            self.hess_vec = torch.zeros(n + off, device="cuda", dtype=tdt)[off:]
         else:
             self.x = np.array(x0, dtype=dtype)
             self.grad = np.zeros(n, dtype)

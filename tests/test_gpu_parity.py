@@ -154,3 +154,23 @@ def test_grad_writeback_off_leaves_grad_untouched():
     to = run_trace(so, p2, 40, step, keep_x=True)
     _assert_parity(to, tc, 1e-10)
     sc.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("case", [c for c in CASES if c[0] in ("olbfgs_rosen_1001", "olbfgs_rosen_1k", "sqn_hv_logistic",
+                                                                "sqn_gd_quad", "adaqn_fisher_logistic", "adaqn_gd_logistic")],
+                         ids=lambda c: c[0])
+def test_parity_with_unaligned_caller_arrays(case, dtype):
+    """x / grad / hess_vec handed over as views that start one element into an allocation (8- or 4-byte aligned only):
+    every streaming kernel must take its scalar-access instantiation for the caller's arrays and still match."""
+    name, kind, kw, prob_f, calls, step = case
+    if dtype == np.float32 and name in ("sqn_gd_quad",):
+        pytest.skip("fp32 bar of this case is covered by test_parity_fp32_device")
+    to, tc = _run_pair(kind, kw, prob_f, calls, step, dtype, misalign=True, one_launch_max_n=0)
+    if dtype == np.float64:
+        _assert_parity(to, tc, RTOL[np.float64])
+    else:
+        p = prob_f()
+        to64 = run_trace(HostStepper(ORACLE[kind](len(p.x0()), dtype=np.float64, **kw), p.x0()), p, calls, step, keep_x=True)
+        assert discrete(to64) == discrete(tc)
+        assert _rel_err(tc, to64) <= max(RTOL[np.float32], 5.0 * _rel_err(to, to64))

@@ -203,6 +203,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             #pragma unroll 1
             for (int c = 0; c < BN; c += 32) {
                 uint32_t v[32];
+                // fused epilogue C = A B' + alpha * addend: the 32 addend values of this lane's column are requested
+                // up front (32 independent loads in flight, overlapping the TMEM read) - loading them one by one next
+                // to the stores made the epilogue latency-bound and doubled the kernel time
+                float ad[32];
+                const int col = n0 + c + lane;
+                if (addend) {
+                    #pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        const int row = m0 + q * 32 + r;
+                        ad[r] = (row < M && col < N) ? __ldg(addend + (long long) row * ld_add + col) : 0.f;
+                    }
+                }
                 const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (as * BN + c);
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -216,15 +228,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 #pragma unroll
                 for (int j = 0; j < 32; ++j) stage[lane * EPI_LD + j] = __uint_as_float(v[j]);
                 __syncwarp();
-                const int col = n0 + c + lane;
-                #pragma unroll 4
-                for (int r = 0; r < 32; ++r) {
-                    const int row = m0 + q * 32 + r;
-                    if (row < M && col < N) {
-                        float val = stage[r * EPI_LD + lane];
-                        // fused epilogue: C = A B' + alpha * addend (the penalty term alpha*W of the gradient rides here)
-                        if (addend) val = fmaf(alpha, __ldg(addend + (long long) row * ld_add + col), val);
-                        C[(long long) row * ldc + col] = val;
+                if (addend) {
+                    #pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        const int row = m0 + q * 32 + r;
+                        if (row < M && col < N) C[(long long) row * ldc + col] = fmaf(alpha, ad[r], stage[r * EPI_LD + lane]);
+                    }
+                } else {
+                    #pragma unroll 4
+                    for (int r = 0; r < 32; ++r) {
+                        const int row = m0 + q * 32 + r;
+                        if (row < M && col < N) C[(long long) row * ldc + col] = stage[r * EPI_LD + lane];
                     }
                 }
                 __syncwarp();

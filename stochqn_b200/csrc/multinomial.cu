@@ -187,6 +187,121 @@ mn_rows(const T* __restrict__ Zp, const T* __restrict__ Rp, int splits, long lon
     }
 }
 
+// ---- the same row work for large batches x many classes, as two well-occupied kernels -----------------------------
+// mn_rows gives one warp a whole sample: at B = 1024, K = 4096 that is 1024 warps on the whole GPU, three strided passes
+// over the intercept column of W per sample, and 32-byte store segments - 297 us between two 115 us GEMMs.  Here:
+//   mn_gather_col  the intercept columns of W (and V) gathered once into contiguous vectors
+//   mn_stats       one CTA per sample: log-sum-exp (and sum_k p_k r_k for the Hessian-vector product), loss term
+//   mn_dtile       32 x 32 tiles: read Z along classes, write DT along samples (both coalesced)
+template <typename T>
+__global__ void __launch_bounds__(256)
+mn_gather_col(const T* __restrict__ W, const T* __restrict__ V, long long ldw, int K, T* __restrict__ bw, T* __restrict__ bv)
+{
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= K) return;
+    bw[k] = W[(long long) k * ldw];
+    if (V) bv[k] = V[(long long) k * ldw];
+}
+
+__device__ __forceinline__ double mn_block_sum(double v, double* red)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0;
+    #pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q];
+    __syncthreads();
+    return t;
+}
+__device__ __forceinline__ double mn_block_max(double v, double* red)
+{
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = red[0];
+    #pragma unroll
+    for (int q = 1; q < 8; ++q) t = fmax(t, red[q]);
+    __syncthreads();
+    return t;
+}
+
+template <typename T, int KIND>
+__global__ void __launch_bounds__(256)
+mn_stats(const T* __restrict__ Zp, const T* __restrict__ Rp, int splits, long long zstride, int B, int K,
+         const T* __restrict__ bw, const T* __restrict__ bv, const T* __restrict__ Y, long long ldy,
+         const int* __restrict__ labels, const T* __restrict__ sw, double* __restrict__ stats, double* __restrict__ loss_terms)
+{
+    __shared__ double red[8];
+    const int i = blockIdx.x;
+    auto zval = [&](int k) -> double {
+        double z = bw ? (double) bw[k] : 0.0;
+        for (int s = 0; s < splits; ++s) z += (double) Zp[(long long) s * zstride + (long long) i * K + k];
+        return z;
+    };
+    double mx = -INFINITY;
+    for (int k = threadIdx.x; k < K; k += 256) mx = fmax(mx, zval(k));
+    mx = mn_block_max(mx, red);
+    double se = 0.0;
+    for (int k = threadIdx.x; k < K; k += 256) se += exp(zval(k) - mx);
+    se = mn_block_sum(se, red);
+    const double lse = mx + log(se);
+    if (loss_terms) {                                          // -sw_i sum_k Y_ik (z_ik - lse)
+        const double wt = sw ? (double) sw[i] : 1.0;
+        double lt = 0.0;
+        if (labels) { if (threadIdx.x == 0) lt = -(zval(labels[i]) - lse); }
+        else for (int k = threadIdx.x; k < K; k += 256) { const double yk = (double) Y[(long long) i * ldy + k]; if (yk != 0.0) lt -= yk * (zval(k) - lse); }
+        lt = mn_block_sum(lt, red);
+        if (threadIdx.x == 0) loss_terms[i] = wt * lt;
+    }
+    double pr = 0.0;
+    if (KIND == MN_HVP) {
+        for (int k = threadIdx.x; k < K; k += 256) {
+            double r = bv ? (double) bv[k] : 0.0;
+            for (int s = 0; s < splits; ++s) r += (double) Rp[(long long) s * zstride + (long long) i * K + k];
+            pr += exp(zval(k) - lse) * r;
+        }
+        pr = mn_block_sum(pr, red);
+    }
+    if (threadIdx.x == 0) { stats[2 * (long long) i] = lse; stats[2 * (long long) i + 1] = pr; }
+}
+
+template <typename T, int KIND>
+__global__ void __launch_bounds__(256)
+mn_dtile(const T* __restrict__ Zp, const T* __restrict__ Rp, int splits, long long zstride, int B, int K,
+         const T* __restrict__ bw, const T* __restrict__ bv, const T* __restrict__ Y, long long ldy,
+         const int* __restrict__ labels, const T* __restrict__ sw, const double* __restrict__ stats,
+         T* __restrict__ DT, long long ldt)
+{
+    __shared__ T tile[32][33];
+    const int k0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + r, k = k0 + tx;
+        T out = (T) 0;
+        if (i < B && k < K) {
+            double z = bw ? (double) bw[k] : 0.0;
+            for (int s = 0; s < splits; ++s) z += (double) Zp[(long long) s * zstride + (long long) i * K + k];
+            const double wt = sw ? (double) sw[i] : 1.0;
+            const double p = exp(z - stats[2 * (long long) i]);
+            if (KIND == MN_GRAD) {
+                const double yk = labels ? (labels[i] == k ? 1.0 : 0.0) : (double) Y[(long long) i * ldy + k];
+                out = (T) (wt * (p - yk));
+            } else {
+                double rr = bv ? (double) bv[k] : 0.0;
+                for (int s = 0; s < splits; ++s) rr += (double) Rp[(long long) s * zstride + (long long) i * K + k];
+                out = (T) (wt * p * (rr - stats[2 * (long long) i + 1]));
+            }
+        }
+        tile[r][tx] = out;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int k = k0 + r, i = i0 + tx;
+        if (k < K && i < B) DT[(long long) k * ldt + i] = tile[tx][r];
+    }
+}
+
 // One CTA per class k: G[k][0..d) += alpha * U[k][0..d) ;  G[k][d] = sum_i DT[k][i] (when there is an intercept).
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -250,7 +365,7 @@ struct MnPlan {
     int splits;
     long long bpad;                   // leading dimension of DT / XT (samples, padded to 16 bytes)
     long long dpad;                   // leading dimension of the packed coefficient copies (features, padded to 16 bytes)
-    size_t off_zp, off_rp, off_dt, off_xt, off_terms, off_wp, off_vp, total;
+    size_t off_zp, off_rp, off_dt, off_xt, off_terms, off_stats, off_bvec, off_wp, off_vp, total;
 };
 
 // Wp[K x ldp] = W[:, :d]  (coefficient block without the intercept column, rows 16-byte aligned: what TMA needs)
@@ -300,6 +415,8 @@ MnPlan mn_plan(long long B, long long d, long long K)
     p.off_dt = off; off = al(off + sizeof(real_t) * (size_t) (K * p.bpad));
     p.off_xt = off; off = al(off + sizeof(real_t) * (size_t) (d * p.bpad));
     p.off_terms = off; off = al(off + sizeof(double) * (size_t) (B + K + 2));       // per-sample loss terms, then per-class ||w_k||^2
+    p.off_stats = off; off = al(off + sizeof(double) * (size_t) (2 * B));           // per-sample log-sum-exp and sum_k p_k r_k
+    p.off_bvec = off; off = al(off + sizeof(real_t) * (size_t) (2 * K));            // intercept columns of W and V, gathered
     p.off_wp = off; p.off_vp = off;
 #ifdef USE_FLOAT
     p.off_wp = off; off = al(off + sizeof(real_t) * (size_t) (K * p.dpad));      // packed W / V for the tensor-core path
@@ -371,14 +488,35 @@ int mn_common(int kind, const real_t* X, long long ldx, const real_t* Y, long lo
     if (kind == MN_HVP) { if (int r = launch_gemm(X, ldx, v1, ld1, Rp, K, zstride, (int) B, (int) K, (int) d, p.splits, st)) return r; }
     const real_t* wb = fit_intercept ? w + d : nullptr;
     const real_t* vb = (fit_intercept && v) ? v + d : nullptr;
-    const unsigned rows_grid = (unsigned) ((B + 7) / 8);
-    if (kind == MN_GRAD)
-        mn_rows<real_t, MN_GRAD><<<rows_grid, 256, 0, st>>>(Zp, Rp, p.splits, zstride, (int) B, (int) K, wb, ldw, vb, Y, ldy, labels, sw,
-                                                           need_out ? DT : nullptr, p.bpad, loss_dev ? terms : nullptr);
-    else
-        mn_rows<real_t, MN_HVP><<<rows_grid, 256, 0, st>>>(Zp, Rp, p.splits, zstride, (int) B, (int) K, wb, ldw, vb, Y, ldy, labels, sw,
-                                                          DT, p.bpad, nullptr);
     int launched = 1;
+    if (B * K >= (1ll << 18) && B <= 65535ll * 32) {
+        // large batch x many classes: gather the intercepts, per-sample statistics with one CTA per sample, tiled write of DT
+        double* stats = (double*) (base + p.off_stats);
+        real_t* bw = (real_t*) (base + p.off_bvec);
+        real_t* bv = bw + K;
+        if (wb) { mn_gather_col<real_t><<<(unsigned) ((K + 255) / 256), 256, 0, st>>>(wb, vb, ldw, (int) K, bw, bv); ++launched; }
+        const real_t* bwp = wb ? bw : nullptr;
+        const real_t* bvp = vb ? bv : nullptr;
+        double* lt = (loss_dev && kind == MN_GRAD) ? terms : nullptr;
+        const bool want_dt = kind == MN_HVP || need_out;
+        dim3 tg((unsigned) ((K + 31) / 32), (unsigned) ((B + 31) / 32));
+        if (kind == MN_GRAD) {
+            mn_stats<real_t, MN_GRAD><<<(unsigned) B, 256, 0, st>>>(Zp, Rp, p.splits, zstride, (int) B, (int) K, bwp, bvp, Y, ldy, labels, sw, stats, lt);
+            if (want_dt) { mn_dtile<real_t, MN_GRAD><<<tg, 256, 0, st>>>(Zp, Rp, p.splits, zstride, (int) B, (int) K, bwp, bvp, Y, ldy, labels, sw, stats, DT, p.bpad); ++launched; }
+        } else {
+            mn_stats<real_t, MN_HVP><<<(unsigned) B, 256, 0, st>>>(Zp, Rp, p.splits, zstride, (int) B, (int) K, bwp, bvp, Y, ldy, labels, sw, stats, nullptr);
+            mn_dtile<real_t, MN_HVP><<<tg, 256, 0, st>>>(Zp, Rp, p.splits, zstride, (int) B, (int) K, bwp, bvp, Y, ldy, labels, sw, stats, DT, p.bpad);
+            ++launched;
+        }
+    } else {
+        const unsigned rows_grid = (unsigned) ((B + 7) / 8);
+        if (kind == MN_GRAD)
+            mn_rows<real_t, MN_GRAD><<<rows_grid, 256, 0, st>>>(Zp, Rp, p.splits, zstride, (int) B, (int) K, wb, ldw, vb, Y, ldy, labels, sw,
+                                                               need_out ? DT : nullptr, p.bpad, loss_dev ? terms : nullptr);
+        else
+            mn_rows<real_t, MN_HVP><<<rows_grid, 256, 0, st>>>(Zp, Rp, p.splits, zstride, (int) B, (int) K, wb, ldw, vb, Y, ldy, labels, sw,
+                                                              DT, p.bpad, nullptr);
+    }
     if (loss_dev && kind == MN_GRAD) {
         mn_wnorm<real_t><<<(unsigned) K, 256, 0, st>>>(w, ldw, (int) d, terms + B);
         mn_loss_finish<<<1, 256, 0, st>>>(terms, (int) B, terms + B, (int) K, (double) alpha, loss_dev);

@@ -54,7 +54,7 @@ def _run(dtype, B, d, K, fit_intercept, use_labels, weighted, seed=0, scale=1.0)
     return (g.cpu().numpy().astype(np.float64), hv.cpu().numpy().astype(np.float64), float(loss.item())), (gr, hr, lr)
 
 
-SHAPES = [(1, 1, 2), (20, 7, 5), (257, 64, 33), (50, 1836, 159), (300, 130, 70)]
+SHAPES = [(1, 1, 2), (20, 7, 5), (257, 64, 33), (50, 1836, 159), (300, 130, 70), (600, 40, 450)]   # the last one takes the stats + tiled row kernels (B*K >= 2^18)
 
 
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-11), (np.float32, 3e-5)])

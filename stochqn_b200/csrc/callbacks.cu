@@ -442,26 +442,36 @@ logistic_fused_kernel(const real_t* __restrict__ X, long long ldx, const real_t*
     if (tid == 0) { out[ncols] = sw_sum; out[ncols + 1] = r_sum; }
 }
 
-__global__ void __launch_bounds__(kT)
+// 32 columns x 8 record-slices per CTA: thread (tx, ty) adds the records ty, ty+8, ... of column tx (CTA order within
+// the slice), the 8 slice sums are added in slice order - deterministic, and 8x shorter dependent chains than one thread
+// per column walking all the records (which made this pass as long as the sweep itself for small batches).
+constexpr int kFinCols = 32, kFinSlices = 8;
+__global__ void __launch_bounds__(kFinCols * kFinSlices)
 logistic_fused_finish(const double* __restrict__ colpart, int nparts, long long ncols, const real_t* __restrict__ u,
                       real_t lambda, real_t* __restrict__ out, const LgForm form)
 {
-    const long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-    if (c > ncols || (c == ncols && !form.icpt)) return;
+    __shared__ double part[kFinSlices][kFinCols + 1], swp[kFinSlices], rsp[kFinSlices];
+    const int tx = threadIdx.x % kFinCols, ty = threadIdx.x / kFinCols;
+    const long long c = (long long) blockIdx.x * kFinCols + tx;
     const size_t rec = (size_t) (ncols + 2);
-    if (c == ncols) {                                       // intercept: sum of the row weights, CTA order
-        double rs = 0;
-        for (int b = 0; b < nparts; ++b) rs += colpart[(size_t) b * rec + ncols + 1];
-        out[c] = (real_t) rs;
-        return;
+    double acc = 0;
+    if (c < ncols)
+        for (int b = ty; b < nparts; b += kFinSlices) acc += __ldcg(colpart + (size_t) b * rec + c);
+    part[ty][tx] = acc;
+    if (tx == 0) {                                          // the two scalars of every record: sum of weights, sum of row weights
+        double sw = 0, rs = 0;
+        for (int b = ty; b < nparts; b += kFinSlices) { sw += __ldcg(colpart + (size_t) b * rec + ncols); rs += __ldcg(colpart + (size_t) b * rec + ncols + 1); }
+        swp[ty] = sw; rsp[ty] = rs;
     }
-    double acc = 0, swt = 0;
-    for (int b = 0; b < nparts; ++b) {
-        acc += colpart[(size_t) b * rec + c];
-        swt += colpart[(size_t) b * rec + ncols];
-    }
-    out[c] = form.sk ? (real_t) (acc + (double) lambda * (double) u[c])
-                     : (real_t) (acc / swt + 2.0 * (double) lambda * (double) u[c]);
+    __syncthreads();
+    if (ty != 0) return;
+    double swt = 0, rst = 0, tot = 0;
+    #pragma unroll
+    for (int q = 0; q < kFinSlices; ++q) { tot += part[q][tx]; swt += swp[q]; rst += rsp[q]; }
+    if (c < ncols)
+        out[c] = form.sk ? (real_t) (tot + (double) lambda * (double) u[c])
+                         : (real_t) (tot / swt + 2.0 * (double) lambda * (double) u[c]);
+    if (form.icpt && blockIdx.x == 0 && tx == 0) out[ncols] = (real_t) rst;      // intercept: sum of the row weights
 }
 
 template <int C, int KIND, int R, int MINB>
@@ -615,7 +625,7 @@ static int logistic_common(int kind, const real_t* X, long long ldx, const real_
         const bool done = kind == LG_GRAD ? launch_logistic_fused<LG_GRAD>(X, ldx, y, sw, nrows, ncols, w, v, colpart, &nparts, st, form)
                                           : launch_logistic_fused<LG_HVP>(X, ldx, y, sw, nrows, ncols, w, v, colpart, &nparts, st, form);
         if (done) {
-            logistic_fused_finish<<<(unsigned) ((nout + kT - 1) / kT), kT, 0, st>>>(colpart, nparts, ncols, kind == LG_HVP ? v : w, lambda, out, form);
+            logistic_fused_finish<<<(unsigned) ((ncols + kFinCols - 1) / kFinCols), kFinCols * kFinSlices, 0, st>>>(colpart, nparts, ncols, kind == LG_HVP ? v : w, lambda, out, form);
             return check_launch("logistic (fused)", 2);
         }
     }

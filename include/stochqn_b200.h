@@ -203,6 +203,20 @@ int stochqn_b200_multinomial_hess_vec(const real_t *X, long long ldx, const real
                                       int fit_intercept, const real_t *w, const real_t *v, real_t alpha, real_t *hess_vec,
                                       void *work, void *stream);
 
+/* Row-sharded gradient with the reduce-scatter FUSED into the product that computes it (float build, peer-memory
+   communicator): every rank evaluates the multinomial gradient on ITS rows of the batch (pass alpha / world_size, the
+   penalty is then added once in the sum); the epilogue of the second GEMM does not store the gradient locally but
+   writes each tile straight into the receive slot of the rank that owns that block of the n-vector
+   (n = world_size * block_count, block r = elements [r*block_count, (r+1)*block_count)) over NVLink, while the tensor
+   pipe works on the next tile; a rank barrier and one pass that adds the world_size slots (rank order, deterministic)
+   leave block `rank` of the summed gradient in grad_block.  Replaces multinomial_loss_grad + reduce_scatter_real.
+   Returns -5 when this path is not available (double build, no peer access, shapes the tensor-core kernel does not
+   take): call the two-step form then.  Collective: every rank must call it in the same order. */
+int stochqn_b200_multinomial_grad_reduce_scatter(void *comm, const real_t *X, long long ldx, const real_t *Y, long long ldy,
+                                                 const int *labels, const real_t *sw, long long nrows, long long nfeat,
+                                                 long long nclasses, int fit_intercept, const real_t *w, real_t alpha,
+                                                 real_t *grad_block, long long block_count, void *work, void *stream);
+
 /* ---- guided mode: the request loop of one mini-batch, natively ------------------------------------------------
    The reference's guided classes serve the optimizer's requests from the host language: one interpreter round trip
    per request (R/optimizers_guided.R:26-111 `run_stochQN_on_batch`; stochqn/_optimizers.py:339-382 `_fit_batch`).

@@ -103,11 +103,22 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar)
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// Fused reduce-scatter: when world > 1 the epilogue does not store into C; the result is viewed as the flat vector
+// e = row*ldc + col, cut into `world` blocks of `blk` elements, and every element is written straight into the receive
+// slot of the rank that owns its block (dst[o]: rank o's slot for THIS sender, a cudaIpc-mapped peer pointer - the
+// stores travel over NVLink while the tensor pipe works on the next tile).  blk >= ldc, so a row crosses at most one
+// block boundary.
+struct ScatterArgs {
+    int world = 0;
+    float* dst[16] = {};
+    long long blk = 0;
+};
+
 template <int BN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  float* __restrict__ C, long long ldc, int M, int N, int K,
-                 const float* __restrict__ addend, long long ld_add, float alpha)
+                 const float* __restrict__ addend, long long ld_add, float alpha, const __grid_constant__ ScatterArgs sc)
 {
     constexpr int STAGES = Cfg<BN>::STAGES;
     constexpr uint32_t STAGE_BYTES = Cfg<BN>::STAGE_BYTES, TMEM_COLS = Cfg<BN>::TMEM_COLS;
@@ -200,6 +211,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             // Each warp transposes its 32 x 32 block through shared memory so that a store instruction writes 32
             // consecutive floats of ONE row of C (128 contiguous bytes, whatever ldc is).
             float* stage = epi + (size_t) q * 32 * EPI_LD;
+            // scatter mode: lane r works out where row (m0 + 32q + r) starts in the block partition, once per tile
+            int own_o = 0;
+            long long own_rem = 0;
+            if (sc.world > 1) {
+                const long long e = (long long) (m0 + q * 32 + lane) * ldc + n0;
+                own_o = (int) (e / sc.blk);
+                own_rem = e - (long long) own_o * sc.blk;
+            }
             #pragma unroll 1
             for (int c = 0; c < BN; c += 32) {
                 uint32_t v[32];
@@ -228,7 +247,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 #pragma unroll
                 for (int j = 0; j < 32; ++j) stage[lane * EPI_LD + j] = __uint_as_float(v[j]);
                 __syncwarp();
-                if (addend) {
+                if (sc.world > 1) {
+                    #pragma unroll 4
+                    for (int r = 0; r < 32; ++r) {
+                        const int row = m0 + q * 32 + r;
+                        int o = __shfl_sync(0xffffffffu, own_o, r);
+                        long long off = __shfl_sync(0xffffffffu, own_rem, r) + c + lane;
+                        if (off >= sc.blk) { off -= sc.blk; ++o; }
+                        if (row < M && col < N && o < sc.world) {
+                            float val = stage[r * EPI_LD + lane];
+                            if (addend) val = fmaf(alpha, ad[r], val);
+                            sc.dst[o][off] = val;
+                        }
+                    }
+                } else if (addend) {
                     #pragma unroll
                     for (int r = 0; r < 32; ++r) {
                         const int row = m0 + q * 32 + r;
@@ -315,7 +347,7 @@ inline bool sm100_gemm_tf32_usable(const float* A, long long lda, const float* B
 // returns 0 = launched, 1 = tensor-core path not available here (caller falls back), < 0 = error
 inline int sm100_gemm_tf32(const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc,
                            int M, int N, int K, cudaStream_t st, const float* addend = nullptr, long long ld_add = 0,
-                           float alpha = 0.f)
+                           float alpha = 0.f, const tf32gemm::ScatterArgs* scatter = nullptr)
 {
     using namespace tf32gemm;
     Host& h = host();
@@ -329,7 +361,8 @@ inline int sm100_gemm_tf32(const float* A, long long lda, const float* B, long l
     if (!make_map(h, &ma, A, lda, M, K, BM) || !make_map(h, &mb, B, ldb, N, K, wide ? 256 : 128)) return 1;
     const long long ntiles = tiles_m * ((N + (wide ? 255 : 127)) / (wide ? 256 : 128));
     const int grid = (int) (ntiles < h.sms ? ntiles : h.sms);
-    if (wide) gemm_tf32_kernel<256><<<grid, THREADS, Cfg<256>::SMEM_BYTES, st>>>(ma, mb, C, ldc, M, N, K, addend, ld_add, alpha);
-    else      gemm_tf32_kernel<128><<<grid, THREADS, Cfg<128>::SMEM_BYTES, st>>>(ma, mb, C, ldc, M, N, K, addend, ld_add, alpha);
+    const ScatterArgs sc = scatter ? *scatter : ScatterArgs();
+    if (wide) gemm_tf32_kernel<256><<<grid, THREADS, Cfg<256>::SMEM_BYTES, st>>>(ma, mb, C, ldc, M, N, K, addend, ld_add, alpha, sc);
+    else      gemm_tf32_kernel<128><<<grid, THREADS, Cfg<128>::SMEM_BYTES, st>>>(ma, mb, C, ldc, M, N, K, addend, ld_add, alpha, sc);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

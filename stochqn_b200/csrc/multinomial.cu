@@ -32,7 +32,16 @@ extern std::atomic<unsigned long long> stochqn_b200_cb_launches;    // callbacks
 #include "gemm_tf32_sm100.cuh"
 #endif
 
+#include "internal_rs.h"
+
 namespace {
+
+// where the optional fused reduce-scatter of the gradient product sends its elements (see gemm_tf32_sm100.cuh)
+struct MnScatter {
+    int world = 0;
+    long long blk = 0;
+    void* dst[16] = {};
+};
 
 constexpr int TM = 64, TN = 64, TK = 16, NT = 256;
 
@@ -384,7 +393,7 @@ mn_pack(const T* __restrict__ W, long long ldw, T* __restrict__ Wp, long long ld
 // intercept column of the gradient / Hessian-vector product: G[k][d] = sum_i DT[k][i]; one warp per class
 template <typename T>
 __global__ void __launch_bounds__(256)
-mn_intercept(T* __restrict__ G, long long ldg, int d, const T* __restrict__ DT, long long ldt, int B, int K)
+mn_intercept(T* __restrict__ G, long long ldg, int d, const T* __restrict__ DT, long long ldt, int B, int K, const MnScatter sc)
 {
     const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -392,7 +401,35 @@ mn_intercept(T* __restrict__ G, long long ldg, int d, const T* __restrict__ DT, 
     double s = 0.0;
     for (int i = lane; i < B; i += 32) s += (double) DT[(long long) k * ldt + i];
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if (lane == 0) G[(long long) k * ldg + d] = (T) s;
+    if (lane != 0) return;
+    const long long e = (long long) k * ldg + d;
+    if (sc.world > 1) {                                    // fused reduce-scatter: straight into the owner's receive slot
+        const int o = (int) (e / sc.blk);
+        if (o < sc.world) reinterpret_cast<T*>(sc.dst[o])[e - (long long) o * sc.blk] = (T) s;
+    } else G[e] = (T) s;
+}
+
+// receive side of the fused reduce-scatter: out[e] = sum over senders (rank order) of slot[s][e]
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+mn_rs_reduce(const T* __restrict__ slots, long long blk, int world, T* __restrict__ out)
+{
+    const long long nv = blk / VEC;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (long long v = (long long) blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += stride) {
+        if constexpr (VEC == 4) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < world; ++r) {
+                const float4 t = __ldcg(reinterpret_cast<const float4*>(slots + (long long) r * blk) + v);
+                acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+            }
+            reinterpret_cast<float4*>(out)[v] = acc;
+        } else {
+            T acc = (T) 0;
+            for (int r = 0; r < world; ++r) acc += __ldcg(slots + (long long) r * blk + v);
+            out[v] = acc;
+        }
+    }
 }
 
 MnPlan mn_plan(long long B, long long d, long long K)
@@ -431,16 +468,22 @@ MnPlan mn_plan(long long B, long long d, long long K)
 // happened (the CUDA-core kernel leaves it to a separate pass).
 int launch_gemm(const real_t* A, long long lda, const real_t* Bm, long long ldb, real_t* C, long long ldc, long long cz_stride,
                 int M, int N, int Kc, int splits, cudaStream_t st, const real_t* addend = nullptr, long long ld_add = 0,
-                real_t alpha = 0, bool* fused = nullptr)
+                real_t alpha = 0, bool* fused = nullptr, const MnScatter* scatter = nullptr)
 {
     if (fused) *fused = false;
 #ifdef USE_FLOAT
     if (splits == 1 && !getenv("STOCHQN_B200_NO_TENSOR_CORES") && sm100_gemm_tf32_usable(A, lda, Bm, ldb, C, ldc, M, N, Kc)) {
-        const int r = sm100_gemm_tf32(A, lda, Bm, ldb, C, ldc, M, N, Kc, st, addend, ld_add, alpha);
+        tf32gemm::ScatterArgs sa;
+        if (scatter && scatter->world > 1) {
+            sa.world = scatter->world; sa.blk = scatter->blk;
+            for (int r = 0; r < scatter->world && r < 16; ++r) sa.dst[r] = (float*) scatter->dst[r];
+        }
+        const int r = sm100_gemm_tf32(A, lda, Bm, ldb, C, ldc, M, N, Kc, st, addend, ld_add, alpha, sa.world > 1 ? &sa : nullptr);
         if (r == 0) { if (fused) *fused = addend != nullptr; return mn_check("gemm (tcgen05 tf32)", 1); }
         if (r != 1) return r;                       // 1 = not available on this device / driver: fall through
     }
 #endif
+    if (scatter && scatter->world > 1) return -5;   // the fused reduce-scatter exists in the tensor-core epilogue only
     const int kper = ((Kc + splits - 1) / splits + TK - 1) / TK * TK;
     dim3 grid((unsigned) ((N + TN - 1) / TN), (unsigned) ((M + TM - 1) / TM), (unsigned) splits);
     gemm_tn<real_t><<<grid, NT, 0, st>>>(A, lda, Bm, ldb, C, ldc, cz_stride, M, N, Kc, kper);
@@ -449,7 +492,7 @@ int launch_gemm(const real_t* A, long long lda, const real_t* Bm, long long ldb,
 
 int mn_common(int kind, const real_t* X, long long ldx, const real_t* Y, long long ldy, const int* labels, const real_t* sw,
               long long B, long long d, long long K, int fit_intercept, const real_t* w, const real_t* v, real_t alpha,
-              real_t* out, double* loss_dev, void* work, cudaStream_t st)
+              real_t* out, double* loss_dev, void* work, cudaStream_t st, const MnScatter* scatter = nullptr)
 {
     if (B <= 0 || d <= 0 || K <= 0 || (kind == MN_GRAD && !Y && !labels) || !X || !w || !work) return -1;
     if (B > 2000000000ll || d > 2000000000ll || K > 2000000000ll) return -1;
@@ -531,10 +574,12 @@ int mn_common(int kind, const real_t* X, long long ldx, const real_t* Y, long lo
         // (+ alpha * W or alpha * V fused into the tensor-core epilogue: saves a read-modify-write pass over the gradient)
         bool fused = false;
         if (int r = launch_gemm(DT, p.bpad, XT, p.bpad, out, ldw, 0, (int) K, (int) d, (int) B, 1, st,
-                                kind == MN_HVP ? v : w, ldw, alpha, &fused)) return r;
+                                kind == MN_HVP ? v : w, ldw, alpha, &fused, scatter)) return r;
+        if (scatter && scatter->world > 1 && !fused) return -5;
         if (fused) {
             if (!fit_intercept) return 0;
-            mn_intercept<real_t><<<(unsigned) ((K + 7) / 8), 256, 0, st>>>(out, ldw, (int) d, DT, p.bpad, (int) B, (int) K);
+            mn_intercept<real_t><<<(unsigned) ((K + 7) / 8), 256, 0, st>>>(out, ldw, (int) d, DT, p.bpad, (int) B, (int) K,
+                                                                           scatter ? *scatter : MnScatter());
             return mn_check("multinomial intercept", 1);
         }
         mn_finish<real_t><<<(unsigned) K, 256, 0, st>>>(out, ldw, kind == MN_HVP ? v : w, ldw, (int) d, fit_intercept, alpha, DT, p.bpad, (int) B);
@@ -568,6 +613,36 @@ int stochqn_b200_multinomial_loss_grad(const real_t* X, long long ldx, const rea
     if (!grad && !loss_dev) return -1;
     return mn_common(MN_GRAD, X, ldx, Y, ldy, labels, sw, nrows, nfeat, nclasses, fit_intercept, w, nullptr, alpha, grad, loss_dev,
                      work, (cudaStream_t) stream);
+}
+
+int stochqn_b200_multinomial_grad_reduce_scatter(void* comm, const real_t* X, long long ldx, const real_t* Y, long long ldy,
+                                                 const int* labels, const real_t* sw, long long nrows, long long nfeat,
+                                                 long long nclasses, int fit_intercept, const real_t* w, real_t alpha,
+                                                 real_t* grad_block, long long block_count, void* work, void* stream)
+{
+#ifdef USE_FLOAT
+    const long long ldw = nfeat + (fit_intercept ? 1 : 0);
+    StochqnRsPlan plan;
+    if (!grad_block || block_count < ldw) return -5;
+    if (int r = stochqn_b200_internal_rs_begin(comm, block_count, &plan)) return r;       // -5: no peer-memory path
+    if ((long long) plan.world * block_count < nclasses * ldw) return -1;
+    MnScatter sc;
+    sc.world = plan.world; sc.blk = block_count;
+    for (int r = 0; r < plan.world; ++r) sc.dst[r] = plan.dst[r];
+    cudaStream_t st = (cudaStream_t) stream;
+    // `out` is only a flat index space here (leading dimension ldw); nothing is stored through it
+    if (int r = mn_common(MN_GRAD, X, ldx, Y, ldy, labels, sw, nrows, nfeat, nclasses, fit_intercept, w, nullptr, alpha,
+                          grad_block, nullptr, work, st, &sc)) return r;
+    if (int r = stochqn_b200_internal_barrier(comm, st)) return r;          // every sender's tiles have landed
+    const bool v4 = (block_count % 4 == 0) && ((((uintptr_t) grad_block) | ((uintptr_t) plan.local)) & 15u) == 0;
+    if (v4) mn_rs_reduce<real_t, 4><<<1184, 256, 0, st>>>((const real_t*) plan.local, block_count, plan.world, grad_block);
+    else    mn_rs_reduce<real_t, 1><<<1184, 256, 0, st>>>((const real_t*) plan.local, block_count, plan.world, grad_block);
+    return mn_check("multinomial reduce-scatter", 1);
+#else
+    (void) comm; (void) X; (void) ldx; (void) Y; (void) ldy; (void) labels; (void) sw; (void) nrows; (void) nfeat; (void) nclasses;
+    (void) fit_intercept; (void) w; (void) alpha; (void) grad_block; (void) block_count; (void) work; (void) stream;
+    return -5;          // the fused path lives in the tensor-core (float) build
+#endif
 }
 
 int stochqn_b200_multinomial_hess_vec(const real_t* X, long long ldx, const real_t* Y, long long ldy, const int* labels,

@@ -25,6 +25,7 @@
 #include "stochqn.h"
 #include "stochqn_b200.h"
 #include "kernels.cuh"
+#include "internal_rs.h"
 
 using namespace sqn;
 
@@ -100,6 +101,12 @@ struct Comm {
     unsigned char* peer[kMaxWorld] = {};          // every rank's mailbox as mapped here (peer[rank] == box)
     unsigned long long seq = 0;                   // exchanges issued so far (identical on every rank)
     int* error_flag = nullptr;                    // device word set by a timed-out stand-alone exchange
+    // receive slots of the fused reduce-scatter (multinomial.cu): [2 parities][world senders][rs_blk elements], IPC-shared
+    unsigned char* rs_local = nullptr;
+    unsigned char* rs_peer[kMaxWorld] = {};
+    long long rs_blk = 0;
+    unsigned long long rs_calls = 0;
+    double* barrier_scratch = nullptr;
 };
 
 // PeerArgs of the NEXT exchange on this communicator (world = 0 when there is nothing to exchange or no p2p)
@@ -483,10 +490,12 @@ int launch_pair_finalize(Ctx* c, int nblocks, volatile double* host_dst)
 
 // K4 + publication of s'y, s's to the host pair block: one launch when not sharded, K4 + k_finalize otherwise
 template <int KIND>
-int launch_pair(Ctx* c, const real_t* a, const real_t* b, const real_t* s, real_t* y, real_t y_reg)
+int launch_pair(Ctx* c, const real_t* a, const real_t* b, const real_t* s, real_t* y, real_t y_reg, bool profile = false)
 {
     const bool sharded = c->comm && c->comm->world > 1;
+    if (profile) prof_begin(c, 2);
     const int nb = launch_k4_k<KIND>(c, a, b, s, y, y_reg, !sharded);
+    if (profile) prof_end(c, 2);                      // K4 alone: the exchange between ranks is not part of its time
     if (sharded) return launch_pair_finalize(c, nb, c->hb_dev->pair);
     return 0;
 }
@@ -795,9 +804,7 @@ int update_y_grad_diff_dev(Ctx* c, bfgs_mem* m, const real_t* grad, const real_t
     const size_t slot = m->mem_st_ix;
     real_t* s = m->s_mem + slot * c->ld;
     real_t* y = m->y_mem + slot * c->ld;
-    prof_begin(c, 2);
-    if (int r = launch_pair<PAIR_GRAD_DIFF>(c, grad, grad_prev, s, y, m->y_reg)) return r;
-    prof_end(c, 2);
+    if (int r = launch_pair<PAIR_GRAD_DIFF>(c, grad, grad_prev, s, y, m->y_reg, true)) return r;
     if (int r = wait_flag(c, FLAG_PAIR)) return r;
     return curvature_decision(c, m, c->hb->pair[0], c->hb->pair[1], info);
 }

@@ -64,3 +64,6 @@ def test_row_sharded_multinomial_two_gpus(tmp_path):
     assert res["res"]["allreduce"]["tasks"] == res["res"]["zero1"]["tasks"], res
     assert res["res"]["allreduce"]["infos"] == res["res"]["zero1"]["infos"], res
     assert res["modes_rel_err"] <= 1e-9, res
+    # fp32 / tensor cores: reduce-scatter fused into the GEMM epilogue over peer memory == ncclReduceScatter of the same tiles
+    assert res["fused_same_tasks"] and res["fused_moved"] > 1e-4, res
+    assert res["fused_rel_err"] <= 1e-5, res

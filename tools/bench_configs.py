@@ -243,8 +243,9 @@ def run_multinomial_sharded(name, dtype, d, K, batch_per_gpu, nrows_per_gpu, ste
     comm = init_comm(abi, rank, world) if world > 1 else None
     n = K * (d + 1)
     assert n % world == 0, "n must divide by the number of ranks for reduce-scatter"
-    blk = n // world if mode == "zero1" else n
-    off = rank * blk if mode == "zero1" else 0
+    sharded_opt = mode in ("zero1", "fused")
+    blk = n // world if sharded_opt else n
+    off = rank * blk if sharded_opt else 0
     # this rank's rows of every global batch: global row = b * (world * batch_per_gpu) + rank * batch_per_gpu + i
     nb = nrows_per_gpu // batch_per_gpu
     gen = torch.Generator(device="cuda").manual_seed(100)
@@ -260,13 +261,13 @@ def run_multinomial_sharded(name, dtype, d, K, batch_per_gpu, nrows_per_gpu, ste
     x_full = torch.zeros(n, device="cuda", dtype=tdt)
     xq = torch.zeros(n, device="cuda", dtype=tdt)              # the requested point, gathered
     g_full = torch.zeros(n, device="cuda", dtype=tdt)
-    g_blk = torch.zeros(blk, device="cuda", dtype=tdt) if mode == "zero1" else g_full
+    g_blk = torch.zeros(blk, device="cuda", dtype=tdt) if sharded_opt else g_full
     work = torch.empty(lib.stochqn_b200_multinomial_work_size(max(batch_per_gpu, big), d, K), device="cuda", dtype=torch.uint8)
     sw = {c: torch.full((c,), 1.0 / (c * world), device="cuda", dtype=tdt) for c in {batch_per_gpu, big}}
     alpha = 1e-3
     ws = lib.initialize_adaQN(blk, 10, 1, L, 0.0, 1e-4, 1e-4, rms, 1, 0.0, 1, 1)
     assert ws, _lib.last_error(abi)
-    if mode == "zero1" and comm is not None:
+    if sharded_opt and comm is not None:
         assert lib.stochqn_b200_set_comm(ws, comm, n) == 0
     x_ptr = x_full.data_ptr() + off * esz
     req, task, info = C.c_void_p(), C.c_int(), C.c_int()
@@ -289,15 +290,22 @@ def run_multinomial_sharded(name, dtype, d, K, batch_per_gpu, nrows_per_gpu, ste
             r0 = max(0, (b + 1) * batch_per_gpu - cnt)
         else:
             raise RuntimeError("unexpected task %d" % t)
-        if mode == "zero1":                                   # gather the point the request names (x, x_avg or x_avg_prev block)
+        if sharded_opt:                                       # gather the point the request names (x, x_avg or x_avg_prev block)
             lib.stochqn_b200_all_gather_real(comm, req.value, xq.data_ptr(), blk, None)
             point = xq.data_ptr()
         else:
             point = req.value
+        if mode == "fused" and world > 1:
+            # gradient on this rank's rows with the reduce-scatter fused into the epilogue of the product that computes it
+            rc = lib.stochqn_b200_multinomial_grad_reduce_scatter(comm, X.data_ptr() + r0 * d * esz, d, None, K, lab.data_ptr() + r0 * 4,
+                                                                  sw[cnt].data_ptr(), cnt, d, K, 1, point, alpha / world, g_blk.data_ptr(), blk,
+                                                                  work.data_ptr(), None)
+            assert rc == 0, (rc, _lib.last_error(abi))
+            return
         # alpha / world per rank: the penalty term is added once in the sum over ranks
         assert lib.stochqn_b200_multinomial_loss_grad(X.data_ptr() + r0 * d * esz, d, None, K, lab.data_ptr() + r0 * 4, sw[cnt].data_ptr(), cnt, d, K, 1,
                                                       point, alpha / world, g_full.data_ptr(), None, work.data_ptr(), None) == 0
-        if mode == "zero1":
+        if sharded_opt:
             lib.stochqn_b200_reduce_scatter_real(comm, g_full.data_ptr(), g_blk.data_ptr(), blk, None)
         else:
             lib.stochqn_b200_allreduce_real(comm, g_full.data_ptr(), n, None)
@@ -322,7 +330,7 @@ def run_multinomial_sharded(name, dtype, d, K, batch_per_gpu, nrows_per_gpu, ste
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
-    if mode == "zero1":
+    if sharded_opt and world > 1:
         lib.stochqn_b200_all_gather_real(comm, x_ptr, x_full.data_ptr(), blk, None)
     torch.cuda.synchronize()
     out = dict(config=name, optimizer="adaQN", mode=mode if world > 1 else "single", n_gpus=world, dtype="f64" if esz == 8 else "f32", n=n,
@@ -344,7 +352,8 @@ def main():
     ap.add_argument("configs", nargs="*", default=["cfg1", "cfg2", "cfg3", "cfg5"])
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--rows-cfg2", type=int, default=1000000)
-    ap.add_argument("--mode", default="zero1", choices=["zero1", "allreduce"], help="cfg5s: how the row-sharded gradient is combined")
+    ap.add_argument("--mode", default="zero1", choices=["zero1", "allreduce", "fused"],
+                    help="cfg5s: how the row-sharded gradient is combined (fused: reduce-scatter inside the GEMM epilogue over NVLink peer memory)")
     a = ap.parse_args()
     if "cfg5s" in a.configs:          # row-sharded config 5 (torch.distributed.run, one rank per GPU)
         import torch.distributed as dist

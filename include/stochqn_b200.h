@@ -114,6 +114,12 @@ int stochqn_b200_allreduce_real(void *comm, real_t *dev_buf, size_t count, void 
 int stochqn_b200_reduce_scatter_real(void *comm, const real_t *send_full, real_t *recv_block, size_t block_count, void *stream);
 int stochqn_b200_all_gather_real(void *comm, const real_t *send_block, real_t *recv_full, size_t block_count, void *stream);
 
+/* all-gather over NVLink peer memory: ONE kernel that stores this rank's block into every rank's copy of the gathered
+   vector, then the rank barrier.  *gathered (world_size * block_count elements) belongs to the library and stays valid,
+   in stream order, until the second next call on this communicator (double-buffered).  -5: no peer-memory path - use
+   stochqn_b200_all_gather_real. */
+int stochqn_b200_all_gather_p2p(void *comm, const real_t *send_block, size_t block_count, real_t **gathered, void *stream);
+
 /* ---- bundled device callbacks -------------------------------------------------------------
    Chained Rosenbrock, formulas of the reference's example (example/c_rosen.c:13-41), on a
    contiguous shard x[0..n_local) of a vector of length n_global that starts at global index

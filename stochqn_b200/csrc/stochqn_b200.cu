@@ -107,6 +107,11 @@ struct Comm {
     long long rs_blk = 0;
     unsigned long long rs_calls = 0;
     double* barrier_scratch = nullptr;
+    // gathered vector of the peer-memory all-gather: [2 parities][world * ag_blk elements], IPC-shared
+    unsigned char* ag_local = nullptr;
+    unsigned char* ag_peer[kMaxWorld] = {};
+    long long ag_blk = 0;
+    unsigned long long ag_calls = 0;
 };
 
 // PeerArgs of the NEXT exchange on this communicator (world = 0 when there is nothing to exchange or no p2p)

@@ -290,7 +290,12 @@ def run_multinomial_sharded(name, dtype, d, K, batch_per_gpu, nrows_per_gpu, ste
             r0 = max(0, (b + 1) * batch_per_gpu - cnt)
         else:
             raise RuntimeError("unexpected task %d" % t)
-        if sharded_opt:                                       # gather the point the request names (x, x_avg or x_avg_prev block)
+        if mode == "fused" and world > 1:                     # gather by pushing over peer memory (one kernel + barrier)
+            gp = C.c_void_p()
+            rc = lib.stochqn_b200_all_gather_p2p(comm, req.value, blk, C.byref(gp), None)
+            assert rc == 0, (rc, _lib.last_error(abi))
+            point = gp.value
+        elif sharded_opt:                                     # gather the point the request names (x, x_avg or x_avg_prev block)
             lib.stochqn_b200_all_gather_real(comm, req.value, xq.data_ptr(), blk, None)
             point = xq.data_ptr()
         else:

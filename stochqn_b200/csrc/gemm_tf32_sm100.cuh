@@ -132,6 +132,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
     float* epi = reinterpret_cast<float*>(smem + (size_t) STAGES * STAGE_BYTES + 256);      // [4 warps][32][EPI_LD]
 
+    __shared__ float* sc_ptr[4][32];                      // scatter-mode row tables of the four epilogue warps
+    __shared__ float* sc_ptr2[4][32];
+    __shared__ int sc_lim[4][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
     const int ntiles = tiles_m * tiles_n;
@@ -211,13 +214,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             // Each warp transposes its 32 x 32 block through shared memory so that a store instruction writes 32
             // consecutive floats of ONE row of C (128 contiguous bytes, whatever ldc is).
             float* stage = epi + (size_t) q * 32 * EPI_LD;
-            // scatter mode: lane r works out where row (m0 + 32q + r) starts in the block partition, once per tile
-            int own_o = 0;
-            long long own_rem = 0;
+            // scatter mode: lane r works out, once per tile, where row (m0 + 32q + r) of this tile lands: a pointer
+            // into its owner's receive slot for column n0, how many columns that owner still takes, and the start of the
+            // next owner's slot (a row crosses at most one block boundary).  The table is read back as broadcasts.
             if (sc.world > 1) {
                 const long long e = (long long) (m0 + q * 32 + lane) * ldc + n0;
-                own_o = (int) (e / sc.blk);
-                own_rem = e - (long long) own_o * sc.blk;
+                const int o = (int) (e / sc.blk);
+                const long long rem = e - (long long) o * sc.blk;
+                const long long lim = sc.blk - rem;
+                sc_ptr[q][lane] = o < sc.world ? sc.dst[o] + rem : nullptr;
+                sc_ptr2[q][lane] = o + 1 < sc.world ? sc.dst[o + 1] : nullptr;
+                sc_lim[q][lane] = lim > (1ll << 30) ? (1 << 30) : (int) lim;
+                __syncwarp();
             }
             #pragma unroll 1
             for (int c = 0; c < BN; c += 32) {
@@ -248,16 +256,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 for (int j = 0; j < 32; ++j) stage[lane * EPI_LD + j] = __uint_as_float(v[j]);
                 __syncwarp();
                 if (sc.world > 1) {
-                    #pragma unroll 4
+                    const int cc = c + lane;                        // column relative to n0
+                    #pragma unroll 8
                     for (int r = 0; r < 32; ++r) {
                         const int row = m0 + q * 32 + r;
-                        int o = __shfl_sync(0xffffffffu, own_o, r);
-                        long long off = __shfl_sync(0xffffffffu, own_rem, r) + c + lane;
-                        if (off >= sc.blk) { off -= sc.blk; ++o; }
-                        if (row < M && col < N && o < sc.world) {
+                        const int lim = sc_lim[q][r];
+                        float* p = cc < lim ? sc_ptr[q][r] + cc : sc_ptr2[q][r] + (cc - lim);
+                        float* base = cc < lim ? sc_ptr[q][r] : sc_ptr2[q][r];
+                        if (row < M && col < N && base) {
                             float val = stage[r * EPI_LD + lane];
                             if (addend) val = fmaf(alpha, ad[r], val);
-                            sc.dst[o][off] = val;
+                            *p = val;
                         }
                     }
                 } else if (addend) {

@@ -279,6 +279,15 @@ def run_multinomial_sharded(name, dtype, d, K, batch_per_gpu, nrows_per_gpu, ste
         tasks[task.value] = tasks.get(task.value, 0) + 1
         infos[info.value] = infos.get(info.value, 0) + 1
 
+    phases = os.environ.get("CFG5S_PHASES", "0") != "0"       # per-phase device times (CUDA events on the stream)
+    marks = []
+
+    def mark(tag):
+        if phases:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append((tag, e))
+
     def serve():
         t = task.value
         b = state["b"]
@@ -290,14 +299,21 @@ def run_multinomial_sharded(name, dtype, d, K, batch_per_gpu, nrows_per_gpu, ste
             r0 = max(0, (b + 1) * batch_per_gpu - cnt)
         else:
             raise RuntimeError("unexpected task %d" % t)
+        mark("start")
+        _serve(t, b, r0, cnt)
+        mark("grad_done")
+
+    def _serve(t, b, r0, cnt):
         if mode == "fused" and world > 1:                     # gather by pushing over peer memory (one kernel + barrier)
             gp = C.c_void_p()
             rc = lib.stochqn_b200_all_gather_p2p(comm, req.value, blk, C.byref(gp), None)
             assert rc == 0, (rc, _lib.last_error(abi))
             point = gp.value
+            mark("gathered")
         elif sharded_opt:                                     # gather the point the request names (x, x_avg or x_avg_prev block)
             lib.stochqn_b200_all_gather_real(comm, req.value, xq.data_ptr(), blk, None)
             point = xq.data_ptr()
+            mark("gathered")
         else:
             point = req.value
         if mode == "fused" and world > 1:
@@ -324,13 +340,20 @@ def run_multinomial_sharded(name, dtype, d, K, batch_per_gpu, nrows_per_gpu, ste
         dist.barrier()
         torch.cuda.synchronize()
     tasks.clear(); infos.clear()
+    marks.clear()
     it0 = niter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     while niter() < it0 + steps:
         serve(); call()
     e1.record()
+    mark("start")
     torch.cuda.synchronize()
+    phase_ms = {}
+    if phases:
+        for (ta, ea), (tb, eb) in zip(marks[:-1], marks[1:]):
+            key = ta + "->" + tb
+            phase_ms[key] = phase_ms.get(key, 0.0) + ea.elapsed_time(eb) / steps
     ms = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -342,6 +365,8 @@ def run_multinomial_sharded(name, dtype, d, K, batch_per_gpu, nrows_per_gpu, ste
                features=d, classes=K, batch_per_gpu=batch_per_gpu, global_batch=batch_per_gpu * world, steps=steps, ms_per_step=ms,
                steps_per_s=1e3 / ms, samples_per_s=1e3 / ms * batch_per_gpu * world, tasks=tasks, infos=infos,
                mem_used=int(ws.contents.bfgs_memory.contents.mem_used), x_norm=float(torch.linalg.vector_norm(x_full.double()).item()))
+    if phases:
+        out["phase_ms_rank0"] = {k: round(v, 4) for k, v in phase_ms.items()}
     lib.dealloc_adaQN(ws)
     if rank == 0 and not quiet:
         print(json.dumps(out), flush=True)

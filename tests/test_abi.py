@@ -110,3 +110,57 @@ def test_no_cpu_fallback_without_a_device():
     ws = abi.lib.initialize_oLBFGS(16, 3, 0.0, 0.0, 0.0, 1, 1)
     assert not ws
     assert "CUDA" in _lib.last_error(abi) or "device" in _lib.last_error(abi)
+
+
+@pytest.mark.parametrize("macro,dtype", [("-DUSE_DOUBLE", np.float64), ("-DUSE_FLOAT", np.float32)])
+def test_extension_struct_layouts_match_ctypes(macro, dtype):
+    """stochqn_b200_rows / stochqn_b200_model / stochqn_b200_fit_report / stochqn_b200_host_state (include/stochqn_b200.h)
+    against the ctypes mirrors the Python layer passes to stochqn_b200_fit_batch / export / import."""
+    src = r'''
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "stochqn_b200.h"
+    #define P(T, f) printf(#T "." #f " %zu\n", offsetof(T, f));
+    int main(void) {
+        printf("sizeof.stochqn_b200_rows %zu\n", sizeof(stochqn_b200_rows));
+        printf("sizeof.stochqn_b200_model %zu\n", sizeof(stochqn_b200_model));
+        printf("sizeof.stochqn_b200_fit_report %zu\n", sizeof(stochqn_b200_fit_report));
+        printf("sizeof.stochqn_b200_host_state %zu\n", sizeof(stochqn_b200_host_state));
+        P(stochqn_b200_rows, X) P(stochqn_b200_rows, ldx) P(stochqn_b200_rows, y) P(stochqn_b200_rows, ldy) P(stochqn_b200_rows, sw) P(stochqn_b200_rows, nrows)
+        P(stochqn_b200_model, model) P(stochqn_b200_model, fit_intercept) P(stochqn_b200_model, ncols) P(stochqn_b200_model, nclasses)
+        P(stochqn_b200_model, reg_param) P(stochqn_b200_model, work)
+        P(stochqn_b200_fit_report, calls) P(stochqn_b200_fit_report, n_info) P(stochqn_b200_fit_report, last_info)
+        P(stochqn_b200_fit_report, x_changed) P(stochqn_b200_fit_report, long_batch_used)
+        P(stochqn_b200_host_state, s_mem) P(stochqn_b200_host_state, F)
+        return 0; }
+    '''
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "t")
+        subprocess.run(["gcc", "-std=c99", macro, "-I" + INC, c, "-o", exe], check=True)
+        out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    lay = dict(line.split() for line in out.strip().splitlines())
+    abi = _lib.load(dtype)
+    mirrors = {"stochqn_b200_rows": _lib.Rows, "stochqn_b200_model": abi.Model, "stochqn_b200_fit_report": _lib.FitReport,
+               "stochqn_b200_host_state": _lib.HostState}
+    for key, val in lay.items():
+        kind, field = key.split(".")
+        if kind == "sizeof":
+            assert C.sizeof(mirrors[field]) == int(val), key
+        else:
+            assert getattr(mirrors[kind], field).offset == int(val), key
+
+
+def test_fit_batch_refuses_a_foreign_workspace():
+    """stochqn_b200_fit_batch answers a pointer it did not create with -1000 (the reference's invalid-input code),
+    without touching a GPU."""
+    abi = _lib.load(np.float64)
+    fake = (C.c_char * 256)()
+    task, req, req_vec = C.c_int(101), C.c_void_p(), C.c_void_p()
+    rows = _lib.Rows()
+    M = abi.Model()
+    rep = _lib.FitReport()
+    rc = abi.lib.stochqn_b200_fit_batch(C.cast(fake, C.c_void_p), C.cast(fake, C.c_void_p), 0.1, C.byref(M), C.byref(rows), None, None,
+                                        C.byref(task), C.byref(req), C.byref(req_vec), C.byref(rep))
+    assert rc == -1000

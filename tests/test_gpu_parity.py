@@ -174,3 +174,17 @@ def test_parity_with_unaligned_caller_arrays(case, dtype):
         to64 = run_trace(HostStepper(ORACLE[kind](len(p.x0()), dtype=np.float64, **kw), p.x0()), p, calls, step, keep_x=True)
         assert discrete(to64) == discrete(tc)
         assert _rel_err(tc, to64) <= max(RTOL[np.float32], 5.0 * _rel_err(to, to64))
+
+
+@pytest.mark.parametrize("kind,kw", [
+    ("oLBFGS", dict(mem_size=10, hess_init=0.0, y_reg=0.0, min_curvature=1e-4, check_nan=1)),
+    ("SQN", dict(mem_size=6, bfgs_upd_freq=4, min_curvature=1e-4, use_grad_diff=1, y_reg=0.0, check_nan=1)),
+])
+def test_one_launch_route_as_a_cooperative_grid(kind, kw):
+    """Above 2048 variables the one-launch step runs as a cooperative grid of 256-thread CTAs with one grid barrier and
+    a redundant solve in every CTA (kernels_small.cuh); the matrix above only reaches the single-CTA form.  n = 5000:
+    20 CTAs.  (tools/probe_small.py: identical |x| to 17 digits between the routes up to n = 2^18.)"""
+    from oracle.problems import Rosenbrock
+    to, tc = _run_pair(kind, kw, lambda: Rosenbrock(5000), 80, 1e-4, np.float64, one_launch_max_n=1 << 30)
+    _assert_parity(to, tc, RTOL[np.float64])
+    assert to[-1]["mem_used"] >= 5

@@ -1,6 +1,5 @@
 """CPU: the Cython binding (bindings/cython/stochqn_b200_cy.pyx) cythonizes and compiles against the public headers and
 links against the double library; the module imports without a GPU and fails loudly (MemoryError) on construction."""
-import glob
 import os
 import subprocess
 import sys

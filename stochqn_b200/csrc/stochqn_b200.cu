@@ -368,7 +368,6 @@ int launch_k3_m(Ctx* c, int rpg, const real_t* g, real_t* gout, real_t* S, const
 #undef K3_RPG
 }
 
-int bucket3(int used) { return used <= 16 ? bucket(used) : 32; }    // MMAX buckets of the adaQN combine
 
 int rpg_for_k3(int used)        // rows per group of K3 = pairs in memory, rounded up to an instantiated bucket
 {

@@ -260,14 +260,9 @@ constexpr long long kSmallNDefault = 2048;      // measured on B200 (tools/probe
 bool aligned16(const void* p) { return (((uintptr_t) p) & 15u) == 0; }
 
 // ------------------------------------------------------------------------------------------
-// kernel dispatch (MMAX bucket x vector width)
+// kernel dispatch (rows per group x vector width)
 // ------------------------------------------------------------------------------------------
 #define COUNT_LAUNCH() g_launches.fetch_add(1, std::memory_order_relaxed)
-
-int bucket(int used)
-{
-    return used <= 4 ? 4 : used <= 8 ? 8 : used <= 10 ? 10 : used <= 12 ? 12 : 16;
-}
 
 int k1_grid(Ctx* c, const void* func, long long chunks, int threads = kThreads, int lanes = kLanes)
 {

@@ -52,6 +52,9 @@ CASES = [
                                               scal_reg=1e-4, rmsprop_weight=0.9, use_grad_diff=1, y_reg=0.0, check_nan=1), _l, 200, 1e-2),
     ("adaqn_fisher_rosen_m12", "adaQN", dict(mem_size=12, fisher_size=7, bfgs_upd_freq=2, max_incr=0.0, min_curvature=0.0,
                                              scal_reg=1e-4, rmsprop_weight=0.5, use_grad_diff=0, y_reg=0.0, check_nan=1), _r(37), 120, 1e-5),
+    # 45 stored gradients: the Fisher product takes three KF1 launches (20 rows each) and several row batches in KF2
+    ("adaqn_fisher_logistic_k45", "adaQN", dict(mem_size=5, fisher_size=45, bfgs_upd_freq=5, max_incr=0.0, min_curvature=1e-4,
+                                                scal_reg=1e-4, rmsprop_weight=0.9, use_grad_diff=0, y_reg=0.0, check_nan=1), _l, 130, 1e-2),
     ("adaqn_fisher_quad", "adaQN", dict(mem_size=3, fisher_size=5, bfgs_upd_freq=3, max_incr=1.01, min_curvature=1e-4,
                                         scal_reg=1e-4, rmsprop_weight=0.9, use_grad_diff=0, y_reg=0.0, check_nan=1), _q, 90, 5e-3),
 ]

@@ -206,6 +206,11 @@ GUIDED_CASES = [
      dict(mode="partial", weights=False,
           ranges=[(0, 100), (100, 200), (200, 300), (300, 400), (400, 500), (500, 600), (600, 700), (700, 800),
                   (800, 900), (900, 1000), (1000, 1100), (1100, 1200)])),
+    # CSR model matrix (the reference's fit accepts scipy CSR, stochqn/_optimizers.py:47-53): batches are CSR row slices, the
+    # out-of-phase long batch goes through the stash and scipy.sparse.vstack; callbacks see sparse X
+    ("sqn_hv_fit_csr", "SQN",
+     dict(batches_per_epoch=9, step_size=2e-1, decr_step_size="auto", shuffle_data=True, random_state=2, nepochs=2,
+          mem_size=4, bfgs_upd_freq=4, min_curvature=1e-4), dict(mode="fit", weights=True, hess_vec=True, sparse=True)),
     ("adaqn_fisher_fit_nomax", "adaQN",
      dict(batches_per_epoch=8, step_size=5e-2, decr_step_size="auto", shuffle_data=False, nepochs=3,
           mem_size=4, fisher_size=10, bfgs_upd_freq=3, max_incr=None, min_curvature=1e-4, rmsprop_weight=None),
@@ -220,6 +225,11 @@ def drive(cls, name, okw, how, to_array=lambda a: a, callbacks=None):
     `to_array` converts the NumPy data to whatever container the implementation under test wants
     (identity, or host -> torch CUDA tensor); `callbacks` = (grad, hess_vec, obj) override the NumPy ones."""
     X, y, sw = make_data(weights=how.get("weights", False))
+    if how.get("sparse"):
+        from scipy.sparse import csr_matrix
+        X[np.abs(X) < 0.8] = 0.0                      # make it worth storing sparsely (deterministic: same seeded data)
+        X[:, 0] = 1.0
+        X = csr_matrix(X)
     g, hv, ob = callbacks or (grad_fun, hess_vec_fun, obj_fun)
     kw = dict(okw)
     kw["verbose"] = False
@@ -236,7 +246,8 @@ def drive(cls, name, okw, how, to_array=lambda a: a, callbacks=None):
         args["hess_vec_fun"] = hv
     if how["mode"] == "fit":
         obj = cls(callback_epoch=snap, **args, **kw)
-        obj.fit(to_array(X), to_array(y), to_array(sw) if sw is not None else None, additional_kwargs=dict(REG))
+        obj.fit(X if how.get("sparse") else to_array(X), to_array(y), to_array(sw) if sw is not None else None,
+                additional_kwargs=dict(REG))
     else:
         obj = cls(callback_iter=snap, **args, **kw)
         Xa, ya = to_array(X), to_array(y)

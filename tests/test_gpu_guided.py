@@ -72,6 +72,8 @@ def _recorded(kind):
 def test_guided_cuda_matches_reference(name, kind, okw, how, container):
     import torch
 
+    if container == "cuda" and how.get("sparse"):
+        pytest.skip("CSR model matrices are host objects: covered by the numpy container")
     if container == "cuda":
         conv = lambda a: torch.tensor(a, device="cuda")
         cbs = _torch_callbacks()

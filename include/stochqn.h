@@ -141,7 +141,11 @@ typedef enum iter_status {
    Allocate the workspace and all of its HBM buffers on the current CUDA device
    (see stochqn_b200_set_device).  Return NULL (after a message on stderr) when host or
    device memory cannot be had - the reference's only error channel for allocation.
-   `nthreads` is accepted and stored for compatibility; it has no effect on the GPU. */
+   `nthreads` is accepted and stored for compatibility; it has no effect on the GPU.
+   LIMIT of this build (the reference has none): 1 <= mem_size <= 32 (STOCHQN_B200_MAX_MEM_SIZE) - the m x m
+   compact-form solve runs in one warp.  A larger mem_size is refused like an allocation failure: message on
+   stderr, NULL returned (stochqn_b200_last_error() carries the text). */
+#define STOCHQN_B200_MAX_MEM_SIZE 32
 workspace_oLBFGS* initialize_oLBFGS(const int n, const size_t mem_size, const real_t hess_init, const real_t y_reg,
     const real_t min_curvature, const int check_nan, const int nthreads);
 void dealloc_oLBFGS(workspace_oLBFGS *oLBFGS);

@@ -15,7 +15,7 @@
 #include "p2p.cuh"
 
 // stochqn_b200.cu: PeerArgs of the next exchange on a communicator (world = 0 when the exchange must go through NCCL)
-sqn::PeerArgs stochqn_b200_internal_next_exchange(void* comm, size_t count, int** error_flag);
+sqn::PeerArgs stochqn_b200_internal_next_exchange(void* comm, size_t count, int** error_flag, cudaStream_t stream);
 
 // kernels launched by the callbacks; added to stochqn_b200_launch_count() by stochqn_b200.cu
 std::atomic<unsigned long long> stochqn_b200_cb_launches{0};
@@ -580,7 +580,7 @@ int stochqn_b200_rosenbrock_grad_sharded(const real_t* x, real_t* grad, long lon
 {
     if (world_size <= 1) return stochqn_b200_rosenbrock_grad(x, grad, n_local, offset, n_global, nullptr, stream);
     int* err = nullptr;
-    sqn::PeerArgs pa = stochqn_b200_internal_next_exchange(comm, (size_t) 2 * world_size, &err);
+    sqn::PeerArgs pa = stochqn_b200_internal_next_exchange(comm, (size_t) 2 * world_size, &err, (cudaStream_t) stream);
     if (pa.world <= 1) {                                 // no peer-memory path: library all-reduce, then the plain kernel
         if (int r = stochqn_b200_rosenbrock_halo(x, n_local, rank, world_size, comm, halo, scratch, stream)) return r;
         return stochqn_b200_rosenbrock_grad(x, grad, n_local, offset, n_global, halo, stream);

@@ -485,8 +485,9 @@ k3_combine(const T* g_in, T* grad_out, const T* S_ro, const T* __restrict__ Y,
             Pack<T, V> rv[RPG], gv;
             // every load of the iteration is issued before the first use; the rows are read through the coherent
             // path because the slot that receives the new s is one of them
+            // (dead rows of a partly filled memory are neither loaded nor combined: 0 * Inf would poison d)
             #pragma unroll
-            for (int r = 0; r < RPG; ++r) rv[r] = ld_rw<T, V>(rows[r] + off);
+            for (int r = 0; r < RPG; ++r) if (r < used) rv[r] = ld_rw<T, V>(rows[r] + off);
             if (group == 0) {
                 gv = ld_rw<T, V>(g_in + off);
                 if constexpr (MODE != MODE_DIRONLY) xv = ld_rw<T, V>(x + off);
@@ -496,8 +497,10 @@ k3_combine(const T* g_in, T* grad_out, const T* S_ro, const T* __restrict__ Y,
             }
             #pragma unroll
             for (int r = 0; r < RPG; ++r) {
-                #pragma unroll
-                for (int e = 0; e < V; ++e) part.set(e, fma(cf[r], rv[r].get(e), part.get(e)));
+                if (r < used) {
+                    #pragma unroll
+                    for (int e = 0; e < V; ++e) part.set(e, fma(cf[r], rv[r].get(e), part.get(e)));
+                }
             }
         }
         T* slot = &xchg[buf][group][lane * V];

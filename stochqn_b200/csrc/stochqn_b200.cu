@@ -100,6 +100,8 @@ struct Comm {
     unsigned char* box = nullptr;                 // this rank's mailbox (cudaMalloc, IPC-exported)
     unsigned char* peer[kMaxWorld] = {};          // every rank's mailbox as mapped here (peer[rank] == box)
     unsigned long long seq = 0;                   // exchanges issued so far (identical on every rank)
+    cudaStream_t last_stream = 0;                 // stream the previous exchange was enqueued on
+    cudaEvent_t order_ev = nullptr;               // chains exchanges issued on different streams (see next_exchange)
     int* error_flag = nullptr;                    // device word set by a timed-out stand-alone exchange
     // receive slots of the fused reduce-scatter (multinomial.cu): [2 parities][world senders][rs_blk elements], IPC-shared
     unsigned char* rs_local = nullptr;
@@ -114,11 +116,20 @@ struct Comm {
     unsigned long long ag_calls = 0;
 };
 
-// PeerArgs of the NEXT exchange on this communicator (world = 0 when there is nothing to exchange or no p2p)
-PeerArgs next_exchange(Comm* cm, size_t count)
+// PeerArgs of the NEXT exchange on this communicator (world = 0 when there is nothing to exchange or no p2p).
+// The double-buffered mailboxes assume that the exchanges of one communicator execute in issue order on every rank
+// (p2p.cuh).  Same stream: stream order gives that.  A caller that moves to another stream (the optimizer runs on the
+// workspace stream, the stand-alone all-reduce / barrier / all-gather take any stream) is chained behind everything
+// enqueued so far on the previous stream with an event, so exchange k+1 can never overtake exchange k.
+PeerArgs next_exchange(Comm* cm, size_t count, cudaStream_t stream)
 {
     PeerArgs pa;
     if (!cm || cm->world <= 1 || !cm->p2p || count > (size_t) kBoxCap) return pa;
+    if (cm->seq > 0 && stream != cm->last_stream) {
+        if (!cm->order_ev) cudaEventCreateWithFlags(&cm->order_ev, cudaEventDisableTiming);
+        if (cm->order_ev && cudaEventRecord(cm->order_ev, cm->last_stream) == cudaSuccess) cudaStreamWaitEvent(stream, cm->order_ev, 0);
+    }
+    cm->last_stream = stream;
     pa.rank = cm->rank;
     pa.world = cm->world;
     pa.seq = ++cm->seq;
@@ -453,7 +464,7 @@ int launch_solve(Ctx* c, bool ada, int nblocks, int used, int oldest, int pend, 
     (void) ada;
     const size_t P = (size_t) (4 * c->msize + 2);
     const bool sharded = c->comm && c->comm->world > 1;
-    PeerArgs pa = sharded ? next_exchange(c->comm, P) : PeerArgs();
+    PeerArgs pa = sharded ? next_exchange(c->comm, P, c->stream) : PeerArgs();
     if (sharded && pa.world == 0) {
         A.nblocks = nblocks; A.do_solve = 0; go(A, pa);
         if (int r = allreduce_sums(c, c->sums, P)) return r;
@@ -470,7 +481,7 @@ int launch_finalize(Ctx* c, int nblocks, int count, volatile double* host_dst, i
     const unsigned long long seq = host_dst ? ++c->seq_want[which] : 0;
     volatile unsigned long long* seq_dst = host_dst ? &c->hb_dev->seq[which] : nullptr;
     const bool sharded = c->comm && c->comm->world > 1;
-    PeerArgs pa = sharded ? next_exchange(c->comm, (size_t) count) : PeerArgs();
+    PeerArgs pa = sharded ? next_exchange(c->comm, (size_t) count, c->stream) : PeerArgs();
     if (sharded && pa.world == 0) {
         k_finalize<<<1, kThreads, 0, c->stream>>>(c->partials, nblocks, count, c->sums, pa, nullptr, nullptr, 0);
         COUNT_LAUNCH();
@@ -547,12 +558,15 @@ int wait_flag(Ctx* c, int which)
 {
     const unsigned long long want = c->seq_want[which];
     volatile unsigned long long* p = &c->hb->seq[which];
+    // the payload words (status, info, pair, dir) are read after this returns: the load that observes the sequence number
+    // is an acquire, so that a weakly ordered host CPU cannot hoist those reads above it
+    auto seen = [&]() { return __atomic_load_n(const_cast<unsigned long long*>(p), __ATOMIC_ACQUIRE) == want; };
     for (unsigned long spins = 1;; ++spins) {
-        if (*p == want) return 0;
+        if (seen()) return 0;
         if ((spins & 0xfffu) == 0) {                     // every 4096 polls: has the stream died or drained?
             cudaError_t e = cudaStreamQuery(c->stream);
             if (e == cudaSuccess) {
-                if (*p == want) return 0;
+                if (seen()) return 0;
                 return fail(-2, "device work finished without publishing its result (flag %d)", which);
             }
             if (e != cudaErrorNotReady) return fail(-2, "device work failed: %s", cudaGetErrorString(e));

@@ -35,6 +35,9 @@ class _RawDeviceArray:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
+MAX_MEM_SIZE = 32       # kMaxMem of csrc/kernels.cuh: initialize_*() returns NULL above it
+
+
 def _is_torch(a):
     return type(a).__module__.split(".")[0] == "torch"
 
@@ -43,6 +46,9 @@ class _StochQN_free:
     def _take_common_inputs(self, mem_size, min_curvature, y_reg, check_nan, nthreads, use_float):
         assert mem_size > 0
         assert isinstance(mem_size, int)
+        if mem_size > MAX_MEM_SIZE:
+            raise ValueError("mem_size = %d: the CUDA build keeps at most %d correction pairs (the compact-form solve "
+                             "runs in one warp); the reference accepts any size" % (mem_size, MAX_MEM_SIZE))
         if min_curvature is not None:
             assert min_curvature > 0
         else:

@@ -95,6 +95,44 @@ def test_nonfinite_gradient_rejects_step_and_flushes(kind, kw, poison):
     sc.close()
 
 
+@pytest.mark.parametrize("kind,kw", [
+    ("oLBFGS", dict(mem_size=3, hess_init=0.0, y_reg=0.0, min_curvature=1e-4, check_nan=1)),
+    ("SQN", dict(mem_size=3, bfgs_upd_freq=3, min_curvature=1e-4, use_grad_diff=0, y_reg=0.0, check_nan=1)),
+    ("SQN", dict(mem_size=3, bfgs_upd_freq=3, min_curvature=1e-4, use_grad_diff=1, y_reg=0.0, check_nan=1)),
+])
+@pytest.mark.parametrize("poison", [np.nan, np.inf])
+def test_nonfinite_pair_in_slot_zero_is_survived(kind, kw, poison):
+    """A non-finite same-batch / big-batch gradient (or Hessian-vector product) that lands in y slot 0 is accepted as a
+    pair (NaN <= min_curvature is false, stochqn.c:892), the next step is rejected and the memory flushed, and the step
+    after that runs with NO pairs: it must be the plain gradient step of stochqn.c:808-812 and must not read the
+    poisoned slot.  Once with the empty memory at the start, once more right after the flush."""
+    state = {"left": 2}
+
+    def bad(stepper, task, payload):
+        if task in (102, 103, 104) and state["left"] > 0 and stepper.counters()["mem_st_ix"] == 0 and stepper.counters()["mem_used"] == 0:
+            key = "hess_vec" if task == 104 else "grad"
+            if task == 103 and stepper.counters()["section"] == 2:
+                return                          # first big-batch gradient of SQN only seeds grad_prev
+            payload[key] = payload[key].copy()
+            payload[key][1] = poison
+            state["left"] -= 1
+
+    traces = []
+    for mk in ("oracle", "cuda"):
+        state["left"] = 2
+        p = Quadratic(6)
+        st = HostStepper(ORACLE[kind](6, **kw), p.x0()) if mk == "oracle" else CudaStepper(kind, p.x0(), **kw)
+        traces.append(run_trace(st, p, 40, 5e-3, hooks={c: bad for c in range(1, 40)}, keep_x=True))
+        if mk == "cuda":
+            st.close()
+    to, tc = traces
+    assert state["left"] == 0
+    assert discrete(to) == discrete(tc)
+    assert sum(r["info"] == 203 for r in tc) >= 2
+    assert np.all(np.isfinite(tc[-1]["x"])) and np.all(np.isfinite(to[-1]["x"]))
+    assert _err(tc, to) <= 1e-9
+
+
 def test_check_nan_off_lets_nan_through_like_the_reference():
     kw = dict(mem_size=3, hess_init=0.0, y_reg=0.0, min_curvature=0.0, check_nan=0)
 

@@ -65,6 +65,8 @@ enum stochqn_b200_option {
     STOCHQN_B200_OPT_ONE_LAUNCH_MAX_N = 5
 };
 int stochqn_b200_set_option(void *ws, int option, long long value);
+/* current value of an option of this workspace (-1: unknown option or workspace) */
+long long stochqn_b200_get_option(void *ws, int option);
 
 enum stochqn_b200_stat {
     STOCHQN_B200_STAT_K1_MS = 1, STOCHQN_B200_STAT_K1_COUNT = 2,     /* accumulated device ms / launches (profile mode) */

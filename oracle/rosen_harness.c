@@ -107,16 +107,24 @@ int main(int argc, char **argv)
     }
     double t_total = now_s() - t_start;
 
-    double nrm = 0;
-    for (long i = 0; i < n; i++) nrm += (double) x[i] * (double) x[i];
+    /* what bench.py compares between the two arms: norm, plain sum and a handful of entries of the final iterate */
+    double nrm = 0, sum = 0;
+    #pragma omp parallel for schedule(static) reduction(+:nrm,sum)
+    for (long i = 0; i < n; i++) { nrm += (double) x[i] * (double) x[i]; sum += (double) x[i]; }
+    const long pidx[7] = {0, n > 1 ? 1 : 0, n / 4, n / 2, (3 * n) / 4, n > 1 ? n - 2 : 0, n - 1};
     printf("{\"n\": %ld, \"mem_size\": %zu, \"warmup\": %ld, \"steps\": %ld, \"nthreads\": %d, "
            "\"seconds\": %.6f, \"opt_seconds\": %.6f, \"steps_per_s\": %.6f, \"opt_steps_per_s\": %.6f, "
-           "\"info_events\": %ld, \"mem_used\": %zu, \"x_norm\": %.17g, \"x0\": %.17g, \"x_mid\": %.17g, \"x_last\": %.17g, "
-           "\"real_bytes\": %d}\n",
+           "\"info_events\": %ld, \"mem_used\": %zu, \"mem_st_ix\": %zu, \"niter\": %zu, "
+           "\"x_norm\": %.17g, \"x_sum\": %.17g, \"x0\": %.17g, \"x_mid\": %.17g, \"x_last\": %.17g, "
+           "\"probe_idx\": [%ld, %ld, %ld, %ld, %ld, %ld, %ld], "
+           "\"probes\": [%.17g, %.17g, %.17g, %.17g, %.17g, %.17g, %.17g], \"real_bytes\": %d}\n",
            n, mem_size, warmup, steps, nthreads, t_total, t_opt,
            (double) steps / t_total, (double) steps / t_opt, n_info,
-           ws->bfgs_memory->mem_used, sqrt(nrm), (double) x[0], (double) x[n / 2], (double) x[n - 1],
-           (int) sizeof(real_t));
+           ws->bfgs_memory->mem_used, ws->bfgs_memory->mem_st_ix, ws->niter,
+           sqrt(nrm), sum, (double) x[0], (double) x[n / 2], (double) x[n - 1],
+           pidx[0], pidx[1], pidx[2], pidx[3], pidx[4], pidx[5], pidx[6],
+           (double) x[pidx[0]], (double) x[pidx[1]], (double) x[pidx[2]], (double) x[pidx[3]], (double) x[pidx[4]],
+           (double) x[pidx[5]], (double) x[pidx[6]], (int) sizeof(real_t));
     dealloc_oLBFGS(ws);
     free(x); free(g);
     return 0;

@@ -32,7 +32,9 @@ def test_fp64(case):
     name, kind, kw, prob_f, calls, step = case
     to, tr = _pair(kind, kw, prob_f, calls, step, np.float64)
     assert discrete(to) == discrete(tr)
-    assert _err(to, tr) <= 1e-6        # 1e-13 on the well-conditioned cases; chaotic adaQN cases amplify dot rounding
+    # north_star's bar.  Measured: <= 3.4e-11 on 21 cases (1e-15 on the well-conditioned ones); adaqn_fisher_rosen_m12 is
+    # chaotic - the reference's own iterates move by 1.2e-8 when its gradients are jittered by 1e-15 - and sits at 6.4e-10
+    assert _err(to, tr) <= (1e-8 if name == "adaqn_fisher_rosen_m12" else 1e-10)
 
 
 @pytest.mark.parametrize("case", [c for c in CASES if c[0] not in ("sqn_gd_logistic_yreg", "adaqn_fisher_adagrad_logistic", "adaqn_fisher_quad")

@@ -38,7 +38,7 @@ def _gen_rows(nrows, d, dtype, intercept_first, seed):
     return X
 
 
-def run_logistic(name, kind, nrows, d, batch, steps, L=10, big=20000, native=False):
+def run_logistic(name, kind, nrows, d, batch, steps, L=10, big=20000, native=False, quiet=False, cpu_fn=None):
     dtype, tdt, esz = np.float64, torch.float64, 8
     abi = _lib.load(dtype)
     lib = abi.lib
@@ -138,10 +138,14 @@ def run_logistic(name, kind, nrows, d, batch, steps, L=10, big=20000, native=Fal
                tasks=tasks, infos=infos, mem_used=int(ws.contents.bfgs_memory.contents.mem_used),
                launches_per_step=(_lib.launch_count() - launches0) / steps, loss_after=float(loss.item()), loss_at_zero=float(np.log(2.0)))
     {"oLBFGS": lib.dealloc_oLBFGS, "SQN": lib.dealloc_SQN}[kind](ws)
-    print(json.dumps(out), flush=True)
+    if cpu_fn is not None:          # the reference on the host cores, on rows of the same matrix (bench.py's secondary block)
+        out["cpu_reference"] = cpu_fn(X, y)
+    if not quiet:
+        print(json.dumps(out), flush=True)
+    return out
 
 
-def run_multinomial(name, dtype, d, K, batch, nrows, steps, L, fisher, use_grad_diff, max_incr, rms, step):
+def run_multinomial(name, dtype, d, K, batch, nrows, steps, L, fisher, use_grad_diff, max_incr, rms, step, quiet=False, cpu_fn=None):
     tdt = torch.float64 if dtype == np.float64 else torch.float32
     esz = 8 if dtype == np.float64 else 4
     abi = _lib.load(dtype)
@@ -198,7 +202,7 @@ def run_multinomial(name, dtype, d, K, batch, nrows, steps, L, fisher, use_grad_
 
     call()
     niter = lambda: int(ws.contents.niter)
-    warm = 3 * L
+    warm = 12 * L                 # mem_size + 2 correction pairs: the timed steps run with the memory full
     while niter() < warm:
         serve(); call()
     torch.cuda.synchronize()
@@ -218,11 +222,15 @@ def run_multinomial(name, dtype, d, K, batch, nrows, steps, L, fisher, use_grad_
                ms_per_step=ms, steps_per_s=1e3 / ms, tasks=tasks, infos=infos, mem_used=int(ws.contents.bfgs_memory.contents.mem_used),
                launches_per_step=(_lib.launch_count() - launches0) / steps, loss_after=float(loss.item()), loss_at_zero=float(np.log(K)))
     lib.dealloc_adaQN(ws)
-    print(json.dumps(out), flush=True)
+    if cpu_fn is not None:
+        out["cpu_reference"] = cpu_fn(X, lab)
+    if not quiet:
+        print(json.dumps(out), flush=True)
+    return out
 
 
 def run_multinomial_sharded(name, dtype, d, K, batch_per_gpu, nrows_per_gpu, steps, L, rms, step, mode="zero1", warm_cycles=3,
-                            return_x=False, quiet=False):
+                            return_x=False, quiet=False, union_world=None):
     """BASELINE config 5 over several GPUs (launch with torch.distributed.run, one rank per GPU): batch ROWS shard across
     the ranks, each rank evaluates the multinomial gradient on its rows (weights 1/global batch), then either
       mode "allreduce": ncclAllReduce of the n-vector, every rank runs the same (replicated) adaQN step, or
@@ -234,6 +242,10 @@ def run_multinomial_sharded(name, dtype, d, K, batch_per_gpu, nrows_per_gpu, ste
 
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
+    if union_world:
+        # the UNSHARDED twin of a run over `union_world` ranks, on this GPU alone: global batch b = the rows every rank
+        # holds for its batch b, one after the other (called by one rank only; no collective inside)
+        rank, world = 0, 1
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     tdt = torch.float64 if dtype == np.float64 else torch.float32
@@ -250,8 +262,16 @@ def run_multinomial_sharded(name, dtype, d, K, batch_per_gpu, nrows_per_gpu, ste
     nb = nrows_per_gpu // batch_per_gpu
     gen = torch.Generator(device="cuda").manual_seed(100)
     Wt = torch.randn(K, d, device="cuda", dtype=tdt, generator=gen)                    # same ground truth on every rank
-    gen_r = torch.Generator(device="cuda").manual_seed(200 + rank)
-    X = torch.randn(nrows_per_gpu, d, device="cuda", dtype=tdt, generator=gen_r) / d ** 0.5
+    if union_world:
+        W_ = int(union_world)
+        parts = [torch.randn(nrows_per_gpu, d, device="cuda", dtype=tdt, generator=torch.Generator(device="cuda").manual_seed(200 + r)) / d ** 0.5
+                 for r in range(W_)]
+        X = torch.stack(parts).reshape(W_, nb, batch_per_gpu, d).permute(1, 0, 2, 3).reshape(-1, d).contiguous()
+        del parts
+        batch_per_gpu, nrows_per_gpu = batch_per_gpu * W_, nrows_per_gpu * W_
+    else:
+        gen_r = torch.Generator(device="cuda").manual_seed(200 + rank)
+        X = torch.randn(nrows_per_gpu, d, device="cuda", dtype=tdt, generator=gen_r) / d ** 0.5
     lab = torch.empty(nrows_per_gpu, device="cuda", dtype=torch.int32)
     for r0 in range(0, nrows_per_gpu, 4096):
         r1 = min(nrows_per_gpu, r0 + 4096)

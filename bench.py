@@ -87,7 +87,8 @@ def rel_probe_distance(a, b):
 
 
 def _cache_paths():
-    return [os.path.join(tempfile.gettempdir(), "stochqn_b200_reference_arm.json"), os.path.join(ROOT, ".bench_reference_arm.json")]
+    # (a file next to the sources would travel with the snapshot and go stale: the temporary directory of the box only)
+    return [os.path.join(tempfile.gettempdir(), "stochqn_b200_reference_arm.json")]
 
 
 # ------------------------------------------------------------------------------------------------

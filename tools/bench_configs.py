@@ -145,28 +145,46 @@ def run_logistic(name, kind, nrows, d, batch, steps, L=10, big=20000, native=Fal
     return out
 
 
-def run_multinomial(name, dtype, d, K, batch, nrows, steps, L, fisher, use_grad_diff, max_incr, rms, step, quiet=False, cpu_fn=None):
+def run_multinomial(name, dtype, d, K, batch, nrows, steps, L, fisher, use_grad_diff, max_incr, rms, step, quiet=False, cpu_fn=None,
+                    profile=None, fixed_big=False):
+    """profile "bibtex": the shape AND the set-up of the reference's notebook (example/example_stochqn.ipynb: BibTeX, 1836 binary
+    bag-of-words features at 3.75 % density, 159 classes): weights of one per sample (summed loss), reg_param 0.1, start point
+    ~ N(0,1) - with these the correction-pair memory fills and stays full (checked with the reference library on the CPU:
+    no func_increased / curvature events in 700 steps at step 1e-2).  fixed_big: serve calc_grad_big_batch on the same rows
+    every time (a caller's choice; the gradient difference then carries no sampling noise and every pair is accepted)."""
     tdt = torch.float64 if dtype == np.float64 else torch.float32
     esz = 8 if dtype == np.float64 else 4
     abi = _lib.load(dtype)
     lib = abi.lib
     n = K * (d + 1)
-    X = _gen_rows(nrows, d, tdt, False, 3)
     gen = torch.Generator(device="cuda").manual_seed(4)
+    if profile == "bibtex":
+        X = (torch.rand(nrows, d, device="cuda", dtype=tdt, generator=torch.Generator(device="cuda").manual_seed(3)) < 0.0375).to(tdt)
+        lab_scale = 1.0
+    else:
+        X = _gen_rows(nrows, d, tdt, False, 3)
+        lab_scale = 4.0
     Wt = torch.randn(K, d, device="cuda", dtype=tdt, generator=gen)
     lab = torch.empty(nrows, device="cuda", dtype=torch.int32)
     for r0 in range(0, nrows, 4096):
         r1 = min(nrows, r0 + 4096)
-        lab[r0:r1] = torch.argmax(X[r0:r1] @ Wt.T * 4.0 + torch.randn(r1 - r0, K, device="cuda", dtype=tdt, generator=gen), dim=1).to(torch.int32)
+        lab[r0:r1] = torch.argmax(X[r0:r1] @ Wt.T * lab_scale + torch.randn(r1 - r0, K, device="cuda", dtype=tdt, generator=gen), dim=1).to(torch.int32)
     del Wt
     nval = min(nrows, 740)
     big = min(nrows, batch * L)
     x = torch.zeros(n, device="cuda", dtype=tdt)
+    if profile == "bibtex":
+        x = torch.randn(n, device="cuda", dtype=tdt, generator=gen)
+    x0_host = x.cpu().numpy().copy()
     g = torch.zeros(n, device="cuda", dtype=tdt)
     loss = torch.zeros(1, device="cuda", dtype=torch.float64)
     work = torch.empty(lib.stochqn_b200_multinomial_work_size(max(batch, big, nval), d, K), device="cuda", dtype=torch.uint8)
-    sw = {c: torch.full((c,), 1.0 / c, device="cuda", dtype=tdt) for c in {batch, big, nval}}     # mean log-loss
-    alpha = 1e-3
+    if profile == "bibtex":
+        sw = {c: torch.ones(c, device="cuda", dtype=tdt) for c in {batch, big, nval}}              # summed log-loss (notebook)
+        alpha = 1e-1
+    else:
+        sw = {c: torch.full((c,), 1.0 / c, device="cuda", dtype=tdt) for c in {batch, big, nval}}     # mean log-loss
+        alpha = 1e-3
     ws = lib.initialize_adaQN(n, 10, max(fisher, 1), L, max_incr, 1e-4, 1e-4, rms, use_grad_diff, 0.0, 1, 1)
     assert ws, _lib.last_error(abi)
     req, task, info = C.c_void_p(), C.c_int(), C.c_int()
@@ -190,9 +208,9 @@ def run_multinomial(name, dtype, d, K, batch, nrows, steps, L, fisher, use_grad_
         if t == 101:
             state["b"] = b = (b + 1) % nb
             assert grad_on(b * batch, batch) == 0
-        elif t == 103:                            # calc_grad_big_batch: the rows of the last L batches
+        elif t == 103:                            # calc_grad_big_batch: the rows of the last L batches (or always the same rows)
             cnt = big
-            r0 = max(0, (b + 1) * batch - cnt)
+            r0 = 0 if fixed_big else max(0, (b + 1) * batch - cnt)
             assert grad_on(r0, cnt) == 0
         elif t == 105:                            # calc_fun_val_batch: validation rows
             assert grad_on(0, nval, want_loss=True) == 0
@@ -223,14 +241,14 @@ def run_multinomial(name, dtype, d, K, batch, nrows, steps, L, fisher, use_grad_
                launches_per_step=(_lib.launch_count() - launches0) / steps, loss_after=float(loss.item()), loss_at_zero=float(np.log(K)))
     lib.dealloc_adaQN(ws)
     if cpu_fn is not None:
-        out["cpu_reference"] = cpu_fn(X, lab)
+        out["cpu_reference"] = cpu_fn(X, lab, x0_host)
     if not quiet:
         print(json.dumps(out), flush=True)
     return out
 
 
 def run_multinomial_sharded(name, dtype, d, K, batch_per_gpu, nrows_per_gpu, steps, L, rms, step, mode="zero1", warm_cycles=3,
-                            return_x=False, quiet=False, union_world=None):
+                            return_x=False, quiet=False, union_world=None, fixed_big=False):
     """BASELINE config 5 over several GPUs (launch with torch.distributed.run, one rank per GPU): batch ROWS shard across
     the ranks, each rank evaluates the multinomial gradient on its rows (weights 1/global batch), then either
       mode "allreduce": ncclAllReduce of the n-vector, every rank runs the same (replicated) adaQN step, or
@@ -316,7 +334,7 @@ def run_multinomial_sharded(name, dtype, d, K, batch_per_gpu, nrows_per_gpu, ste
             r0, cnt = b * batch_per_gpu, batch_per_gpu
         elif t == 103:
             cnt = big
-            r0 = max(0, (b + 1) * batch_per_gpu - cnt)
+            r0 = 0 if fixed_big else max(0, (b + 1) * batch_per_gpu - cnt)
         else:
             raise RuntimeError("unexpected task %d" % t)
         mark("start")
@@ -420,9 +438,9 @@ def main():
     if "cfg2n" in a.configs:
         run_logistic("cfg2", "SQN", a.rows_cfg2, 4096, 2000, a.steps, L=10, big=20000, native=True)
     if "cfg3" in a.configs:
-        run_multinomial("cfg3", np.float64, 1836, 159, 50, 6655, a.steps, 20, 100, 0, 1.01, 0.0, 1e-2)
+        run_multinomial("cfg3", np.float64, 1836, 159, 50, 6655, a.steps, 20, 100, 0, 1.01, 0.0, 1e-2, profile="bibtex")
     if "cfg5" in a.configs:
-        run_multinomial("cfg5", np.float32, 8192, 4096, 1024, 16384, min(a.steps, 100), 10, 0, 1, 0.0, 0.9, 1e-3)
+        run_multinomial("cfg5", np.float32, 8192, 4096, 1024, 16384, min(a.steps, 100), 10, 0, 1, 0.0, 0.9, 1e-3, fixed_big=True)
 
 
 if __name__ == "__main__":

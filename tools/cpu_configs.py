@@ -96,14 +96,16 @@ def logistic_reference(kind, X, y, batch, steps, warm, L=10, big=20000, lam=1e-5
                       % (X.shape[0], warm, steps, nth)}
 
 
-def multinomial_reference(dtype, X, lab, K, batch, steps, warm, L, fisher, use_grad_diff, max_incr, rms, step, alpha=1e-3, mem=10, nval=740, nthreads=None, max_s=12.0):
-    """adaQN + multinomial logistic regression (configs 3 and 5).  X: host (rows, d), lab: host int labels in [0, K)."""
+def multinomial_reference(dtype, X, lab, K, batch, steps, warm, L, fisher, use_grad_diff, max_incr, rms, step, alpha=1e-3, mem=10, nval=740, nthreads=None, max_s=12.0,
+                          wsum=False, x0=None, fixed_big=False):
+    """adaQN + multinomial logistic regression (configs 3 and 5).  X: host (rows, d), lab: host int labels in [0, K).
+    wsum: sample weights of one (summed loss) instead of 1/rows; x0: start point; fixed_big: the big batch is always rows [0, big)."""
     d = X.shape[1]
     n = K * (d + 1)
     nth = nthreads or _threads()
     opt = R.RefAdaQN(n, mem_size=mem, fisher_size=max(fisher, 1), bfgs_upd_freq=L, max_incr=max_incr, min_curvature=1e-4, scal_reg=1e-4,
                      rmsprop_weight=rms, use_grad_diff=use_grad_diff, y_reg=0.0, check_nan=1, nthreads=nth, dtype=dtype)
-    x = np.zeros(n, dtype)
+    x = np.zeros(n, dtype) if x0 is None else np.array(x0, dtype=dtype)
     g = np.zeros(n, dtype)
     nb = X.shape[0] // batch
     big = min(X.shape[0], batch * L)
@@ -117,12 +119,14 @@ def multinomial_reference(dtype, X, lab, K, batch, steps, warm, L, fisher, use_g
         Z -= Z.max(axis=1, keepdims=True)
         np.exp(Z, out=Z)
         s = Z.sum(axis=1, keepdims=True)
+        w = 1.0 if wsum else 1.0 / cnt
         if want_loss:
             pl = Z[np.arange(cnt), lab[r0:r0 + cnt]] / s[:, 0]
-            return float(-np.mean(np.log(pl)) + 0.5 * alpha * np.sum(W[:, :d].astype(np.float64) ** 2))
+            return float(-w * np.sum(np.log(pl)) + 0.5 * alpha * np.sum(W[:, :d].astype(np.float64) ** 2))
         Z /= s
         Z[np.arange(cnt), lab[r0:r0 + cnt]] -= 1.0
-        Z *= (1.0 / cnt)
+        if not wsum:
+            Z *= w
         G = np.empty((K, d + 1), dtype)
         np.matmul(Z.T, Xb, out=G[:, :d])
         G[:, :d] += alpha * W[:, :d]
@@ -145,7 +149,7 @@ def multinomial_reference(dtype, X, lab, K, batch, steps, warm, L, fisher, use_g
             state["b"] = b = (b + 1) % nb
             g[:] = loss_grad(b * batch, batch, opt.req, False)
         elif task == 103:
-            r0 = max(0, (b + 1) * batch - big)
+            r0 = 0 if fixed_big else max(0, (b + 1) * batch - big)
             g[:] = loss_grad(r0, big, opt.req, False)
         elif task == 105:
             state["f"] = loss_grad(0, nval, opt.req, True)

@@ -80,10 +80,13 @@ def _cfg3(peaks, cpu):
     n = K * (d + 1)
     cpu_fn = None
     if cpu:
-        def cpu_fn(X, lab):
+        def cpu_fn(X, lab, x0):
             return CC.best_of_threads(CC.multinomial_reference, dtype=np.float64, X=X.cpu().numpy(), lab=lab.cpu().numpy().astype(np.int64), K=K,
-                                      batch=B, steps=40, warm=12 * L, L=L, fisher=k, use_grad_diff=0, max_incr=1.01, rms=0.0, step=1e-2, max_s=4.0)
-    out = BC.run_multinomial("cfg3", np.float64, d, K, B, 6655, 1000, L, k, 0, 1.01, 0.0, 1e-2, quiet=True, cpu_fn=cpu_fn)
+                                      batch=B, steps=40, warm=12 * L, L=L, fisher=k, use_grad_diff=0, max_incr=1.01, rms=0.0, step=1e-2, max_s=4.0,
+                                      alpha=1e-1, wsum=True, x0=x0)
+    out = BC.run_multinomial("cfg3", np.float64, d, K, B, 6655, 1000, L, k, 0, 1.01, 0.0, 1e-2, quiet=True, cpu_fn=cpu_fn, profile="bibtex")
+    out["workload"] = ("BibTeX-shaped as in example/example_stochqn.ipynb: 1836 binary features (3.75 % dense), 159 classes, batch 50, summed loss, "
+                       "reg_param 0.1, x0 ~ N(0,1), step 1e-2, AdaGrad, Fisher 100, L 20, max_incr 1.01")
     # per step: optimizer 4m + 10 = 50 n-vectors (Fisher ring write included), gradient reads W, alpha*W and writes G (3 vectors)
     # + the batch; per L steps the Fisher product 2k + 4 vectors
     b = (4 * MEM + 10 + 3 + (2 * k + 4) / float(L)) * n * 8 + B * d * 8
@@ -96,7 +99,8 @@ def _cfg5(peaks, cpu):
     import cpu_configs as CC
     d, K, B, L = 8192, 4096, 1024, 10
     n = K * (d + 1)
-    out = BC.run_multinomial("cfg5", np.float32, d, K, B, 16384, 100, L, 0, 1, 0.0, 0.9, 1e-3, quiet=True)
+    out = BC.run_multinomial("cfg5", np.float32, d, K, B, 16384, 100, L, 0, 1, 0.0, 0.9, 1e-3, quiet=True, fixed_big=True)
+    out["workload"] = "X ~ N(0,1)/sqrt(d), mean loss, reg 1e-3, x0 = 0, step 1e-3, RMSProp 0.9, grad-diff pairs on a fixed big batch (L = 10 batches)"
     # per step: tensor work 2 products of 2*B*d*K flop; optimizer 4m + 9 = 49 n-vectors, gradient reads W, alpha*W, writes G (3)
     b = (4 * MEM + 9 + 3) * n * 4 + 2 * B * d * 4
     out["dominant_kernel"] = "ka3_combine / ka1_dots (HBM) + gemm_tf32 (tcgen05)"
@@ -109,7 +113,7 @@ def _cfg5(peaks, cpu):
         Xs = (torch.randn(4096, d, device="cuda", dtype=torch.float32, generator=g) / d ** 0.5).cpu().numpy()
         lab = np.random.default_rng(4).integers(0, Ks, 4096)
         r = CC.best_of_threads(CC.multinomial_reference, dtype=np.float32, X=Xs, lab=lab, K=Ks, batch=B, steps=10, warm=12 * L, L=L, fisher=0,
-                               use_grad_diff=1, max_incr=0.0, rms=0.9, step=1e-3, thread_counts=[os.cpu_count() or 1], max_s=6.0)
+                               use_grad_diff=1, max_incr=0.0, rms=0.9, step=1e-3, thread_counts=[os.cpu_count() or 1], max_s=6.0, fixed_big=True)
         r["value"] /= 8.0
         r["sample"] += "; classes %d (1/8 of %d), steps/s scaled by 1/8" % (Ks, K)
         out["cpu_reference"] = r
@@ -151,7 +155,7 @@ def run(rank, world, comm, dist, peaks, budget_s=60.0):
                 continue
             try:
                 r = fn(peaks, cpu)
-                out[name] = {k: r[k] for k in ("optimizer", "loop", "loops", "dtype", "n", "batch", "steps", "ms_per_step", "steps_per_s", "mem_used",
+                out[name] = {k: r[k] for k in ("workload", "optimizer", "loop", "loops", "dtype", "n", "batch", "steps", "ms_per_step", "steps_per_s", "mem_used",
                                                "launches_per_step", "infos", "dominant_kernel", "roofline", "cpu_reference", "loss_after", "loss_at_zero") if k in r}
                 if "cpu_reference" in r:
                     out[name]["gpu_over_cpu"] = r["steps_per_s"] / r["cpu_reference"]["value"]
@@ -162,7 +166,7 @@ def run(rank, world, comm, dist, peaks, budget_s=60.0):
         os.environ["CFG5S_PHASES"] = "1"
         try:
             out["rowsharded_parity"] = _rowsharded_parity(rank, world, dist)
-            r, _ = BC.run_multinomial_sharded("cfg5 row-sharded", np.float32, 8192, 4096, 1024, 16384, 60, 10, 0.9, 1e-3, mode="zero1", warm_cycles=12, quiet=True)
+            r, _ = BC.run_multinomial_sharded("cfg5 row-sharded", np.float32, 8192, 4096, 1024, 16384, 60, 10, 0.9, 1e-3, mode="zero1", warm_cycles=12, quiet=True, fixed_big=True)
             d, K, B = 8192, 4096, 1024
             n = K * (d + 1)
             # per rank and step: the full tensor work of its rows; optimizer on 1/world of the vectors; the gradient's W read, G write,

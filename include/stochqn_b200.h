@@ -39,14 +39,19 @@ int stochqn_b200_set_stream(void *ws, void *stream);
 
 /* ---- per-workspace options --------------------------------------------------------------- */
 enum stochqn_b200_option {
-    /* 1 (default): `grad` holds the search direction after a step (oLBFGS: -step*direction),
-       exactly what the reference leaves there (src/stochqn.c:838,1006).  0: `grad` is left
-       untouched by device-pointer calls - saves one n-vector write per step; the reference
-       documents the array only as "modified in place" (include/stochqn.h:342). */
+    /* 1: `grad` holds the search direction after a step (oLBFGS: -step*direction), exactly what
+       the reference leaves there (src/stochqn.c:838,1006).  0: `grad` is left untouched - saves
+       one n-vector write (device pointers) or one device->host copy of n values (host pointers)
+       per step; the reference documents the array only as an input that "will be modified in
+       place" (include/stochqn.h:342, 356-358), not as an output.  -1 (default): automatic -
+       1 for device-pointer calls (the write is nearly free), 0 for host-pointer calls. */
     STOCHQN_B200_OPT_GRAD_WRITEBACK = 1,
-    /* host-pointer calls only. 0 (default): `x` is uploaded on every call that reads it, as
-       the reference re-reads the caller's array each call.  1: trust the device mirror (the
-       caller promises not to modify x between calls) - saves one host->device copy per step. */
+    /* host-pointer calls only.  1 (default): the device mirror of `x` is trusted between calls -
+       `x` is uploaded once (and again whenever another array is passed, or after the library
+       itself rewrote it), then only downloaded after each step.  This is the reference's own
+       contract: *req == x "do NOT modify the values in this array" (include/stochqn.h:364-366;
+       stochqn/_optimizers.py:995-999).  0: upload `x` on every call that reads it, for callers
+       that do modify x between calls (projections, restarts). */
     STOCHQN_B200_OPT_TRUST_X_MIRROR = 2,
     /* 1: bracket the streaming kernels of each call (K1 multi-dot, K3 combine/update, K4 pair; adaQN: KA1, KA3, KA2) with CUDA
        events on the workspace stream and accumulate their device times; setting it (to 0 or 1) resets the

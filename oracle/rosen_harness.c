@@ -28,6 +28,18 @@
 #endif
 #include "stochqn.h"
 
+#include <immintrin.h>
+#include <string.h>
+/* write-only streams (the gradient array): non-temporal store, no read-for-ownership of the destination line */
+static inline void stream_store(real_t *p, real_t v)
+{
+#ifdef USE_FLOAT
+    int b; memcpy(&b, &v, sizeof b); _mm_stream_si32((int*) p, b);
+#else
+    long long b; memcpy(&b, &v, sizeof b); _mm_stream_si64((long long*) p, b);
+#endif
+}
+
 /* 0.95 + 1e-4*(h mod 1000) with the product rounded before the sum (no FMA contraction), so that the
    start point is bit-identical in C, NumPy and CUDA */
 static double x0_value(unsigned int h)
@@ -52,7 +64,7 @@ static void rosen_grad(const real_t *x, long n, real_t *g)
         double a = 200.0 * (x[i] - x[i - 1] * x[i - 1]);
         double b = 400.0 * (x[i + 1] - x[i] * x[i]) * x[i];
         double c = 2.0 * (1.0 - x[i]);
-        g[i] = (real_t)(a - b - c);
+        stream_store(&g[i], (real_t)(a - b - c));
     }
 }
 

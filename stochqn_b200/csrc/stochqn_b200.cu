@@ -170,8 +170,17 @@ struct Ctx {
     HostBlock* hb = nullptr;            // host view
     HostBlock* hb_dev = nullptr;        // device view of the same block
     int pending = -1;                   // slot of an accepted pair whose Gram column is not folded in yet
-    int grad_writeback = 1;
-    int trust_x_mirror = 0;
+    int grad_writeback = -1;            // -1: automatic (device-pointer calls write the direction back, host-pointer calls do not)
+    int trust_x_mirror = 1;             // host-pointer calls: x is uploaded once, then the device mirror is the truth
+    bool host_call = false;             // the run_*() call in progress was given host pointers
+    const void* x_host_last = nullptr;  // the caller's x array the mirror mirrors
+    // host-pointer calls of oLBFGS: the caller's arrays cross PCIe in pieces on two copy streams while K1 / K3 / K4 work
+    // on the pieces that have arrived (take_step_host / pair_host)
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_out;
+    cudaEvent_t ev_x = nullptr;
+    long long chunk_elems = 0;          // piece length in elements (0: not set up yet)
+    size_t partials_cap = 0;            // doubles allocated in `partials`
     Comm* comm = nullptr;
     long long n_global = 0;
     // host-pointer compatibility mode
@@ -297,37 +306,46 @@ int k1_grid(Ctx* c, const void* func, long long chunks, int threads = kThreads, 
     return (int) g;
 }
 
+// A contiguous piece [off, off + len) of every n-vector, with the partial records it writes (host-pointer calls stream
+// the caller's arrays in pieces so that the kernels overlap the PCIe copies; device-pointer calls use the whole range)
+struct Range {
+    long long off, len;
+    double* partials;
+};
+Range whole(const Ctx* c) { return Range{0, c->n, c->partials}; }
+
 template <int RPG, bool PENDING, int VEC>
 int launch_k1_t(Ctx* c, const real_t* g, const real_t* S, const real_t* Y, int used, int j0,
-                const real_t* sc, const real_t* yc, real_t* grad_prev)
+                const real_t* sc, const real_t* yc, real_t* grad_prev, const Range& R)
 {
     auto kern = k1_dots<real_t, RPG, PENDING, VEC>;
-    const int grid = k1_grid(c, (const void*) kern, c->n / VEC);
-    kern<<<grid, kThreads, 0, c->stream>>>(g, S, Y, c->ld, c->msize, used, j0, sc, yc, c->n, grad_prev, c->partials);
+    const int grid = k1_grid(c, (const void*) kern, R.len / VEC);
+    kern<<<grid, kThreads, 0, c->stream>>>(g + R.off, S + R.off, Y + R.off, c->ld, c->msize, used, j0, sc ? sc + R.off : nullptr,
+                                          yc ? yc + R.off : nullptr, R.len, grad_prev ? grad_prev + R.off : nullptr, R.partials);
     COUNT_LAUNCH();
     return grid;
 }
 
 template <bool PENDING, int VEC>
 int launch_k1_m(Ctx* c, int rpg, const real_t* g, const real_t* S, const real_t* Y, int used, int j0,
-                const real_t* sc, const real_t* yc, real_t* gp)
+                const real_t* sc, const real_t* yc, real_t* gp, const Range& R)
 {
     switch (rpg) {
-        case 1:  return launch_k1_t<1, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp);
-        case 2:  return launch_k1_t<2, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp);
-        case 3:  return launch_k1_t<3, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp);
-        case 4:  return launch_k1_t<4, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp);
-        case 5:  return launch_k1_t<5, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp);
-        case 6:  return launch_k1_t<6, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp);
-        case 7:  return launch_k1_t<7, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp);
-        default: return launch_k1_t<8, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp);
+        case 1:  return launch_k1_t<1, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp, R);
+        case 2:  return launch_k1_t<2, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp, R);
+        case 3:  return launch_k1_t<3, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp, R);
+        case 4:  return launch_k1_t<4, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp, R);
+        case 5:  return launch_k1_t<5, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp, R);
+        case 6:  return launch_k1_t<6, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp, R);
+        case 7:  return launch_k1_t<7, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp, R);
+        default: return launch_k1_t<8, PENDING, VEC>(c, g, S, Y, used, j0, sc, yc, gp, R);
     }
 }
 
 // returns the number of CTAs whose partial records must be summed
-int launch_k1(Ctx* c, const real_t* g, const real_t* S, const real_t* Y, int used, int pend, real_t* grad_prev)
+int launch_k1(Ctx* c, const real_t* g, const real_t* S, const real_t* Y, int used, int pend, real_t* grad_prev, const Range& R)
 {
-    const bool vec = aligned16(g) && aligned16(grad_prev);
+    const bool vec = aligned16(g + R.off) && aligned16(grad_prev ? grad_prev + R.off : nullptr);
     const real_t* sc = pend >= 0 ? S + (size_t) pend * c->ld : nullptr;
     const real_t* yc = pend >= 0 ? Y + (size_t) pend * c->ld : nullptr;
     // RPG rows per group x 4 groups = 2*slots virtual rows -> up to 16 slots per launch; all launches of one
@@ -338,38 +356,43 @@ int launch_k1(Ctx* c, const real_t* g, const real_t* S, const real_t* Y, int use
     int j0 = 0, grid = 1;
     do {
         if (pend >= 0) {
-            grid = vec ? launch_k1_m<true, VECW>(c, rpg, g, S, Y, used, j0, sc, yc, grad_prev)
-                       : launch_k1_m<true, 1>(c, rpg, g, S, Y, used, j0, sc, yc, grad_prev);
+            grid = vec ? launch_k1_m<true, VECW>(c, rpg, g, S, Y, used, j0, sc, yc, grad_prev, R)
+                       : launch_k1_m<true, 1>(c, rpg, g, S, Y, used, j0, sc, yc, grad_prev, R);
         } else {
-            grid = vec ? launch_k1_m<false, VECW>(c, rpg, g, S, Y, used, j0, sc, yc, grad_prev)
-                       : launch_k1_m<false, 1>(c, rpg, g, S, Y, used, j0, sc, yc, grad_prev);
+            grid = vec ? launch_k1_m<false, VECW>(c, rpg, g, S, Y, used, j0, sc, yc, grad_prev, R)
+                       : launch_k1_m<false, 1>(c, rpg, g, S, Y, used, j0, sc, yc, grad_prev, R);
         }
         j0 += 2 * rpg;
     } while (j0 < used);
     return grid;
 }
+int launch_k1(Ctx* c, const real_t* g, const real_t* S, const real_t* Y, int used, int pend, real_t* grad_prev)
+{
+    return launch_k1(c, g, S, Y, used, pend, grad_prev, whole(c));
+}
 
 template <int RPG, int MODE, int VEC>
 int launch_k3_t(Ctx* c, const real_t* g, real_t* gout, real_t* S, const real_t* Y, int used, int new_slot,
-                real_t* x, real_t* x_sum, real_t step, int force)
+                real_t* x, real_t* x_sum, real_t step, int force, const Range& R)
 {
     auto kern = k3_combine<real_t, RPG, MODE, VEC>;
-    const int grid = k1_grid(c, (const void*) kern, c->n / VEC, k3Threads, k3Lanes);
-    kern<<<grid, k3Threads, 0, c->stream>>>(g, gout, S, Y, S, c->ld, c->msize, used, new_slot, c->n, x, x_sum, step,
-                                           c->coef, c->status_dev, force, c->partials);
+    const int grid = k1_grid(c, (const void*) kern, R.len / VEC, k3Threads, k3Lanes);
+    kern<<<grid, k3Threads, 0, c->stream>>>(g + R.off, gout ? gout + R.off : nullptr, S + R.off, Y + R.off, S + R.off, c->ld, c->msize, used,
+                                           new_slot, R.len, x + R.off, x_sum ? x_sum + R.off : nullptr, step,
+                                           c->coef, c->status_dev, force, R.partials);
     COUNT_LAUNCH();
     return grid;
 }
 
 template <int MODE, int VEC>
 int launch_k3_m(Ctx* c, int rpg, const real_t* g, real_t* gout, real_t* S, const real_t* Y, int used, int new_slot,
-                real_t* x, real_t* x_sum, real_t step, int force)
+                real_t* x, real_t* x_sum, real_t step, int force, const Range& R)
 {
-#define K3_RPG(R) case R: return launch_k3_t<R, MODE, VEC>(c, g, gout, S, Y, used, new_slot, x, x_sum, step, force)
+#define K3_RPG(Q) case Q: return launch_k3_t<Q, MODE, VEC>(c, g, gout, S, Y, used, new_slot, x, x_sum, step, force, R)
     switch (rpg) {
         K3_RPG(1); K3_RPG(2); K3_RPG(3); K3_RPG(4); K3_RPG(5); K3_RPG(6); K3_RPG(7); K3_RPG(8);
         K3_RPG(10); K3_RPG(12); K3_RPG(16); K3_RPG(24);
-        default: return launch_k3_t<32, MODE, VEC>(c, g, gout, S, Y, used, new_slot, x, x_sum, step, force);
+        default: return launch_k3_t<32, MODE, VEC>(c, g, gout, S, Y, used, new_slot, x, x_sum, step, force, R);
     }
 #undef K3_RPG
 }
@@ -383,17 +406,23 @@ int rpg_for_k3(int used)        // rows per group of K3 = pairs in memory, round
 }
 
 int launch_k3(Ctx* c, int mode, const real_t* g, real_t* gout, real_t* S, const real_t* Y, int used, int new_slot,
-              real_t* x, real_t* x_sum, real_t step, int force)
+              real_t* x, real_t* x_sum, real_t step, int force, const Range& R)
 {
-    const bool vec = aligned16(g) && aligned16(gout) && aligned16(x) && aligned16(x_sum);
+    const bool vec = aligned16(g + R.off) && aligned16(gout ? gout + R.off : nullptr) && aligned16(x + R.off) &&
+                     aligned16(x_sum ? x_sum + R.off : nullptr);
     const int rpg = rpg_for_k3(used);
-#define K3_CASE(M)                                                                                               \
-    return vec ? launch_k3_m<M, VECW>(c, rpg, g, gout, S, Y, used, new_slot, x, x_sum, step, force)             \
-               : launch_k3_m<M, 1>(c, rpg, g, gout, S, Y, used, new_slot, x, x_sum, step, force)
+#define K3_CASE(M)                                                                                                  \
+    return vec ? launch_k3_m<M, VECW>(c, rpg, g, gout, S, Y, used, new_slot, x, x_sum, step, force, R)             \
+               : launch_k3_m<M, 1>(c, rpg, g, gout, S, Y, used, new_slot, x, x_sum, step, force, R)
     if (mode == MODE_OLBFGS) { K3_CASE(MODE_OLBFGS); }
     else if (mode == MODE_AVG) { K3_CASE(MODE_AVG); }
     else { K3_CASE(MODE_DIRONLY); }
 #undef K3_CASE
+}
+int launch_k3(Ctx* c, int mode, const real_t* g, real_t* gout, real_t* S, const real_t* Y, int used, int new_slot,
+              real_t* x, real_t* x_sum, real_t step, int force)
+{
+    return launch_k3(c, mode, g, gout, S, Y, used, new_slot, x, x_sum, step, force, whole(c));
 }
 
 void launch_k3_apply(Ctx* c, int mode, real_t* grad, real_t* S, int new_slot, real_t* x, real_t* x_sum, real_t step)
@@ -413,18 +442,23 @@ void launch_k3_apply(Ctx* c, int mode, real_t* grad, real_t* S, int new_slot, re
 // `publish`: the last CTA to finish sums the 2-value records and publishes them to the host pair block itself
 // (no k_finalize launch); only when the optimizer is not sharded - the exchange between ranks lives in k_finalize.
 template <int KIND>
-int launch_k4_k(Ctx* c, const real_t* a, const real_t* b, const real_t* s, real_t* y, real_t y_reg, bool publish = false)
+int launch_k4_k(Ctx* c, const real_t* a, const real_t* b, const real_t* s, real_t* y, real_t y_reg, bool publish, const Range& R)
 {
-    const bool vec = aligned16(a) && aligned16(b);
-    const int grid = grid_for(c, c->n / (vec ? VECW : 1));
+    const bool vec = aligned16(a + R.off) && aligned16(b + R.off);
+    const int grid = grid_for(c, R.len / (vec ? VECW : 1));
     unsigned int* ticket = publish ? c->ticket : nullptr;
     const unsigned long long seq = publish ? ++c->seq_want[FLAG_PAIR] : 0;
-    if (vec) k4_pair<real_t, KIND, VECW><<<grid, kThreads, 0, c->stream>>>(a, b, s, y, y_reg, c->n, c->partials, ticket, c->sums,
-                                                                          c->hb_dev->pair, &c->hb_dev->seq[FLAG_PAIR], seq);
-    else     k4_pair<real_t, KIND, 1><<<grid, kThreads, 0, c->stream>>>(a, b, s, y, y_reg, c->n, c->partials, ticket, c->sums,
-                                                                       c->hb_dev->pair, &c->hb_dev->seq[FLAG_PAIR], seq);
+    if (vec) k4_pair<real_t, KIND, VECW><<<grid, kThreads, 0, c->stream>>>(a + R.off, b + R.off, s + R.off, y + R.off, y_reg, R.len, R.partials, ticket,
+                                                                          c->sums, c->hb_dev->pair, &c->hb_dev->seq[FLAG_PAIR], seq);
+    else     k4_pair<real_t, KIND, 1><<<grid, kThreads, 0, c->stream>>>(a + R.off, b + R.off, s + R.off, y + R.off, y_reg, R.len, R.partials, ticket,
+                                                                       c->sums, c->hb_dev->pair, &c->hb_dev->seq[FLAG_PAIR], seq);
     COUNT_LAUNCH();
     return grid;
+}
+template <int KIND>
+int launch_k4_k(Ctx* c, const real_t* a, const real_t* b, const real_t* s, real_t* y, real_t y_reg, bool publish = false)
+{
+    return launch_k4_k<KIND>(c, a, b, s, y, y_reg, publish, whole(c));
 }
 
 template <int OP>
@@ -599,6 +633,11 @@ void free_ctx(Ctx* c)
     if (c->hreq) cudaFreeHost(c->hreq);
     if (c->hreq_vec) cudaFreeHost(c->hreq_vec);
     for (int k = 0; k < 8; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+    for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_out) cudaEventDestroy(e);
+    if (c->ev_x) cudaEventDestroy(c->ev_x);
+    if (c->copy_in) cudaStreamDestroy(c->copy_in);
+    if (c->copy_out) cudaStreamDestroy(c->copy_out);
     delete c;
 }
 
@@ -629,6 +668,7 @@ Ctx* make_ctx(Kind kind, long long n, int msize, int fisher_size)
     ok = ok && dev_alloc_zero(&c->YY, m * m) == cudaSuccess;
     ok = ok && dev_alloc_zero(&c->SS, m) == cudaSuccess;
     ok = ok && dev_alloc_zero(&c->partials, (size_t) c->max_grid * rec) == cudaSuccess;
+    c->partials_cap = (size_t) c->max_grid * rec;
     ok = ok && dev_alloc_zero(&c->sums, rec) == cudaSuccess;
     ok = ok && dev_alloc_zero(&c->coef, 2 * m + 4) == cudaSuccess;
     ok = ok && dev_alloc_zero(&c->status_dev, 1) == cudaSuccess;
@@ -738,6 +778,10 @@ inline int oldest_slot(const bfgs_mem* m)      // stochqn.c:820 (quirk Q8)
     return (m->mem_st_ix == m->mem_used) ? 0 : (int) m->mem_st_ix;
 }
 
+// does `grad` receive the search direction?  (the reference documents the array only as "modified in place")
+inline bool writeback(const Ctx* c) { return c->grad_writeback < 0 ? !c->host_call : c->grad_writeback != 0; }
+inline bool mirror_is_current(const Ctx* c, const void* x) { return c->trust_x_mirror && c->x_mirror_valid && c->x_host_last == x; }
+
 // take_step (stochqn.c:802-840) for oLBFGS / SQN.  mode = MODE_OLBFGS or MODE_AVG.
 // Returns <0 on a CUDA failure, else 0 and *info is set to search_direction_was_nan on rejection.
 int take_step_qn(Ctx* c, bfgs_mem* m, int mode, real_t step, real_t* x, real_t* g, real_t* grad_prev,
@@ -745,7 +789,7 @@ int take_step_qn(Ctx* c, bfgs_mem* m, int mode, real_t step, real_t* x, real_t* 
 {
     const int used = (int) m->mem_used;
     const int st = (int) m->mem_st_ix;
-    real_t* gout = c->grad_writeback ? g : nullptr;
+    real_t* gout = writeback(c) ? g : nullptr;
     const bool sharded = c->comm && c->comm->world > 1;
     if (!sharded && c->small_n > 0 && c->n <= c->small_n) {
         // latency-bound size: dots, solve and update in ONE cooperative launch
@@ -820,6 +864,158 @@ int update_y_grad_diff_dev(Ctx* c, bfgs_mem* m, const real_t* grad, const real_t
     if (int r = launch_pair<PAIR_GRAD_DIFF>(c, grad, grad_prev, s, y, m->y_reg, true)) return r;
     if (int r = wait_flag(c, FLAG_PAIR)) return r;
     return curvature_decision(c, m, c->hb->pair[0], c->hb->pair[1], info);
+}
+
+// ------------------------------------------------------------------------------------------
+// oLBFGS with HOST pointers (the drop-in compatibility mode), large n: the call is PCIe-bound, so the caller's arrays
+// cross the bus in pieces on two copy streams and the kernels work on the pieces that have arrived:
+//   step call:  H2D grad piece i  ->  K1 on piece i (own partial records)   | all pieces |  K2
+//               K3 on piece i     ->  D2H x piece i (and grad when write-back is asked for)
+//   pair call:  H2D grad piece i  ->  K4 on piece i                          | all pieces |  finalize + publish
+// x itself is uploaded only when the device mirror is not known to be current (first call, another array, option 0).
+// The partial records of the pieces are summed by the same fixed-order reduction, so results do not depend on timing.
+// ------------------------------------------------------------------------------------------
+constexpr long long kPipelineMinBytes = 32ll << 20;      // below this a call is latency-bound: one copy, one launch
+
+bool use_pipeline(const Ctx* c)
+{
+    const bool sharded_nccl = c->comm && c->comm->world > 1 && !c->comm->p2p;
+    return (long long) c->n * (long long) sizeof(real_t) >= kPipelineMinBytes && !sharded_nccl;
+}
+
+int pipeline_setup(Ctx* c, int* nchunks_out)
+{
+    if (!c->chunk_elems) {
+        long long mb = 64;
+        if (const char* e = getenv("STOCHQN_B200_STAGE_CHUNK_MB")) { long long v = atoll(e); if (v >= 1) mb = v; }
+        long long elems = (mb << 20) / (long long) sizeof(real_t);
+        while ((c->n + elems - 1) / elems > 64) elems *= 2;            // at most 64 pieces
+        c->chunk_elems = elems;
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_x, cudaEventDisableTiming));
+    }
+    const int nchunks = (int) ((c->n + c->chunk_elems - 1) / c->chunk_elems);
+    while ((int) c->ev_in.size() < nchunks) {
+        cudaEvent_t a, b;
+        CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        c->ev_in.push_back(a);
+        c->ev_out.push_back(b);
+    }
+    const size_t need = (size_t) nchunks * (size_t) c->max_grid * c->rec_doubles;
+    if (c->partials_cap < need) {                // every piece writes its own block of partial records
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        cudaFree(c->partials);
+        c->partials = nullptr;
+        c->partials_cap = 0;
+        CUDA_TRY(dev_alloc_zero(&c->partials, need));
+        c->partials_cap = need;
+    }
+    if (!c->dx) CUDA_TRY(cudaMalloc((void**) &c->dx, (size_t) c->n * sizeof(real_t)));
+    if (!c->dg) CUDA_TRY(cudaMalloc((void**) &c->dg, (size_t) c->n * sizeof(real_t)));
+    *nchunks_out = nchunks;
+    return 0;
+}
+
+// step call of run_oLBFGS with host pointers (stochqn.c:992-1021): returns <0 on failure, else 0 with *info set
+int take_step_host(Ctx* c, workspace_oLBFGS* ws, real_t step, real_t* xh, real_t* gh, info_enum* info)
+{
+    bfgs_mem* m = ws->bfgs_memory;
+    int nchunks = 0;
+    if (int r = pipeline_setup(c, &nchunks)) return r;
+    const int used = (int) m->mem_used, st = (int) m->mem_st_ix;
+    const size_t P = (size_t) (4 * c->msize + 2);
+    const bool up_x = !mirror_is_current(c, xh);
+    const bool wb = writeback(c);
+    long long recs = 0;
+    prof_begin(c, 0);
+    for (int i = 0; i < nchunks; ++i) {
+        const long long off = (long long) i * c->chunk_elems;
+        const long long len = (c->n - off < c->chunk_elems) ? c->n - off : c->chunk_elems;
+        CUDA_TRY(cudaMemcpyAsync(c->dg + off, gh + off, (size_t) len * sizeof(real_t), cudaMemcpyHostToDevice, c->copy_in));
+        CUDA_TRY(cudaEventRecord(c->ev_in[i], c->copy_in));
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_in[i], 0));
+        Range R{off, len, c->partials + (size_t) recs * P};
+        recs += launch_k1(c, c->dg, m->s_mem, m->y_mem, used, c->pending, ws->grad_prev, R);
+    }
+    prof_end(c, 0);
+    if (up_x) {
+        CUDA_TRY(cudaMemcpyAsync(c->dx, xh, (size_t) c->n * sizeof(real_t), cudaMemcpyHostToDevice, c->copy_in));
+        CUDA_TRY(cudaEventRecord(c->ev_x, c->copy_in));
+    }
+    if (int r = launch_solve(c, false, (int) recs, used, oldest_slot(m), c->pending, ws->check_nan, (double) ws->hess_init)) return r;
+    c->pending = -1;
+    if (up_x) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_x, 0));
+    // K3 reads the accept flag on the device: the pieces are queued at once, a rejected direction makes them no-ops
+    prof_begin(c, 1);
+    for (int i = 0; i < nchunks; ++i) {
+        const long long off = (long long) i * c->chunk_elems;
+        const long long len = (c->n - off < c->chunk_elems) ? c->n - off : c->chunk_elems;
+        Range R{off, len, c->partials};
+        launch_k3(c, MODE_OLBFGS, c->dg, wb ? c->dg : nullptr, m->s_mem, m->y_mem, used, st, c->dx, nullptr, step, 0, R);
+        CUDA_TRY(cudaEventRecord(c->ev_out[i], c->stream));
+        CUDA_TRY(cudaStreamWaitEvent(c->copy_out, c->ev_out[i], 0));
+        CUDA_TRY(cudaMemcpyAsync(xh + off, c->dx + off, (size_t) len * sizeof(real_t), cudaMemcpyDeviceToHost, c->copy_out));
+        if (wb) CUDA_TRY(cudaMemcpyAsync(gh + off, c->dg + off, (size_t) len * sizeof(real_t), cudaMemcpyDeviceToHost, c->copy_out));
+    }
+    prof_end(c, 1);
+    if (int r = wait_flag(c, FLAG_STATUS)) return r;
+    int status = c->hb->status;
+    c->last_bound = c->hb->info[0];
+    if (status == ST_COMM_TIMEOUT) return fail(-4, "a peer rank did not join the all-reduce of this step");
+    if (status == ST_NEED_EXACT_NORM) {
+        // rare: measure ||d|| exactly on the whole (now resident) vectors before touching x, as take_step_qn does
+        c->exact_norm_steps += 1;
+        CUDA_TRY(cudaStreamSynchronize(c->copy_out));          // the no-op pieces above copied the unchanged x: let them finish
+        int nb2 = launch_k3(c, MODE_DIRONLY, c->dg, c->dg, m->s_mem, m->y_mem, used, st, c->dx, nullptr, step, 1);
+        if (int r = launch_pair_finalize(c, nb2, c->hb_dev->dir)) return r;
+        if (int r = wait_flag(c, FLAG_DIR)) return r;
+        const double dd = c->hb->dir[0], bad = c->hb->dir[1];
+        if (bad > 0 || !(sqrt(dd) <= step_limit(c))) status = ST_REJECT_NONFINITE;
+        else {
+            launch_k3_apply(c, MODE_OLBFGS, c->dg, m->s_mem, st, c->dx, nullptr, step);
+            CUDA_TRY(cudaMemcpyAsync(xh, c->dx, (size_t) c->n * sizeof(real_t), cudaMemcpyDeviceToHost, c->stream));
+            if (wb) CUDA_TRY(cudaMemcpyAsync(gh, c->dg, (size_t) c->n * sizeof(real_t), cudaMemcpyDeviceToHost, c->stream));
+            status = ST_ACCEPT;
+        }
+    }
+    if (status != ST_ACCEPT) {
+        flush_bfgs(m, c);
+        *info = search_direction_was_nan;
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->copy_out));
+    c->x_mirror_valid = true;               // x on the host and its mirror agree again (updated or untouched on both sides)
+    c->x_host_last = xh;
+    return 0;
+}
+
+// pair call of run_oLBFGS with host pointers (stochqn.c:1024-1031)
+int pair_host(Ctx* c, workspace_oLBFGS* ws, real_t* gh, info_enum* info)
+{
+    bfgs_mem* m = ws->bfgs_memory;
+    int nchunks = 0;
+    if (int r = pipeline_setup(c, &nchunks)) return r;
+    const size_t slot = m->mem_st_ix;
+    real_t* s = m->s_mem + slot * c->ld;
+    real_t* y = m->y_mem + slot * c->ld;
+    long long recs = 0;
+    prof_begin(c, 2);
+    for (int i = 0; i < nchunks; ++i) {
+        const long long off = (long long) i * c->chunk_elems;
+        const long long len = (c->n - off < c->chunk_elems) ? c->n - off : c->chunk_elems;
+        CUDA_TRY(cudaMemcpyAsync(c->dg + off, gh + off, (size_t) len * sizeof(real_t), cudaMemcpyHostToDevice, c->copy_in));
+        CUDA_TRY(cudaEventRecord(c->ev_in[i], c->copy_in));
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_in[i], 0));
+        Range R{off, len, c->partials + (size_t) recs * 2};
+        recs += launch_k4_k<PAIR_GRAD_DIFF>(c, c->dg, ws->grad_prev, s, y, m->y_reg, false, R);
+    }
+    prof_end(c, 2);
+    if (int r = launch_pair_finalize(c, (int) recs, c->hb_dev->pair)) return r;
+    if (int r = wait_flag(c, FLAG_PAIR)) return r;
+    if (int r = curvature_decision(c, m, c->hb->pair[0], c->hb->pair[1], info)) return r;
+    return sync_stream(c);
 }
 
 int copy_vec_dev(Ctx* c, real_t* dst, const real_t* src)
@@ -967,6 +1163,7 @@ int run_oLBFGS(real_t step_size, real_t x[], real_t grad[], real_t** req, task_e
     if (enter(c)) return invalid_ws("oLBFGS", task);
     bfgs_mem* m = ws->bfgs_memory;
     const bool host_mode = (x && !is_device_ptr(x)) || (grad && !is_device_ptr(grad));
+    c->host_call = host_mode;
 
     if (ws->section == 0) {                                     // stochqn.c:983-989
         *task = calc_grad;
@@ -975,9 +1172,26 @@ int run_oLBFGS(real_t step_size, real_t x[], real_t grad[], real_t** req, task_e
         return 0;
     }
 
+    const bool piped = x && grad && !is_device_ptr(x) && !is_device_ptr(grad) && use_pipeline(c);
+    if (ws->section == 1 && piped) {                            // the same section, PCIe copies overlapped with the kernels
+        if (take_step_host(c, ws, step_size, x, grad, iter_info) < 0) return invalid_ws("oLBFGS", task);
+        ws->niter++;
+        *req = x;
+        if (*iter_info == no_problems_encountered) { *task = calc_grad_same_batch; ws->section = 2; return 1; }
+        *task = calc_grad;
+        return 0;
+    }
+    if (ws->section == 2 && piped) {
+        if (pair_host(c, ws, grad, iter_info) < 0) return invalid_ws("oLBFGS", task);
+        *task = calc_grad;
+        *req = x;
+        ws->section = 1;
+        return 0;
+    }
+
     if (ws->section == 1) {                                     // stochqn.c:992-1021
         Staged sx, sg;
-        if (stage_in(c, x, &c->dx, &sx, !(c->trust_x_mirror && c->x_mirror_valid))) return invalid_ws("oLBFGS", task);
+        if (stage_in(c, x, &c->dx, &sx, !mirror_is_current(c, x))) return invalid_ws("oLBFGS", task);
         if (stage_in(c, grad, &c->dg, &sg, true)) return invalid_ws("oLBFGS", task);
         // grad_prev <- grad rides inside K1; the step writes s = -step*d into the next slot (1006-1007)
         if (take_step_qn(c, m, MODE_OLBFGS, step_size, sx.dev, sg.dev, ws->grad_prev, nullptr,
@@ -987,8 +1201,8 @@ int run_oLBFGS(real_t step_size, real_t x[], real_t grad[], real_t** req, task_e
         *task = (*iter_info == no_problems_encountered) ? calc_grad_same_batch : calc_grad;
         *req = x;
         if (*iter_info == no_problems_encountered) {
-            if (sx.host) { if (stage_out(c, sx)) return invalid_ws("oLBFGS", task); c->x_mirror_valid = true; }
-            if (sg.host && c->grad_writeback) { if (stage_out(c, sg)) return invalid_ws("oLBFGS", task); }
+            if (sx.host) { if (stage_out(c, sx)) return invalid_ws("oLBFGS", task); c->x_mirror_valid = true; c->x_host_last = x; }
+            if (sg.host && writeback(c)) { if (stage_out(c, sg)) return invalid_ws("oLBFGS", task); }
             if (finish_call(c, host_mode)) return invalid_ws("oLBFGS", task);
             ws->section = 2;
             return 1;
@@ -1061,6 +1275,7 @@ int run_SQN(real_t step_size, real_t x[], real_t grad[], real_t hess_vec[], real
     if (enter(c)) return invalid_ws("SQN", task);
     bfgs_mem* m = ws->bfgs_memory;
     const bool host_mode = x && !is_device_ptr(x);
+    c->host_call = host_mode;
 #define SQN_FAIL() return invalid_ws("SQN", task)
 #define SQN_RESUME() do { ws->section = 1; *task = calc_grad; *req = x; return return_value; } while (0)
 
@@ -1068,15 +1283,15 @@ int run_SQN(real_t step_size, real_t x[], real_t grad[], real_t hess_vec[], real
 
     if (ws->section == 1) {                                     // stochqn.c:1051-1115
         Staged sx, sg;
-        if (stage_in(c, x, &c->dx, &sx, !(c->trust_x_mirror && c->x_mirror_valid))) SQN_FAIL();
+        if (stage_in(c, x, &c->dx, &sx, !mirror_is_current(c, x))) SQN_FAIL();
         if (stage_in(c, grad, &c->dg, &sg, true)) SQN_FAIL();
         if (take_step_qn(c, m, MODE_AVG, step_size, sx.dev, sg.dev, nullptr, ws->x_sum, 0.0, ws->check_nan, iter_info) < 0)
             SQN_FAIL();
         ws->niter++;
         return_value = (*iter_info == search_direction_was_nan) ? 0 : 1;
         if (return_value == 0) launch_avg<AVG_ADD>(c, ws->x_sum, sx.dev, nullptr, (real_t) 0);   // 1067, quirk Q7
-        if (sx.host && return_value) { if (stage_out(c, sx)) SQN_FAIL(); c->x_mirror_valid = true; }
-        if (sg.host && return_value && c->grad_writeback) { if (stage_out(c, sg)) SQN_FAIL(); }
+        if (sx.host && return_value) { if (stage_out(c, sx)) SQN_FAIL(); c->x_mirror_valid = true; c->x_host_last = x; }
+        if (sg.host && return_value && writeback(c)) { if (stage_out(c, sg)) SQN_FAIL(); }
 
         const size_t L = m->upd_freq;
         if ((ws->niter % L) != 0) { if (finish_call(c, host_mode)) SQN_FAIL(); SQN_RESUME(); }

@@ -13,6 +13,18 @@ typedef float real_t;
 typedef double real_t;
 #endif
 
+#include <immintrin.h>
+#include <string.h>
+/* write-only streams (the gradient array): non-temporal store, no read-for-ownership of the destination line */
+static inline void stream_store(real_t *p, real_t v)
+{
+#ifdef USE_FLOAT
+    int b; memcpy(&b, &v, sizeof b); _mm_stream_si32((int*) p, b);
+#else
+    long long b; memcpy(&b, &v, sizeof b); _mm_stream_si64((long long*) p, b);
+#endif
+}
+
 /* 0.95 + 1e-4*(h mod 1000) with the product rounded before the sum (no FMA contraction), so that the
    start point is bit-identical in C, NumPy and CUDA */
 static double x0_value(unsigned int h)
@@ -38,7 +50,7 @@ void host_rosenbrock_grad(const real_t *x, real_t *g, long long n_local, long lo
             out -= 400.0 * (xp - xc * xc) * xc;
             out -= 2.0 * (1.0 - xc);
         }
-        g[i] = (real_t) out;
+        stream_store(&g[i], (real_t) out);
     }
 }
 

@@ -77,7 +77,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     hsrc = os.path.join(REPO, "tools", "host_callbacks.c")
     hout = os.path.join(LIBDIR, "libhostcb_f64.so")
     if force or not os.path.exists(hout) or os.path.getmtime(hout) < os.path.getmtime(hsrc):
-        subprocess.run(["gcc", "-O2", "-fopenmp", "-march=x86-64-v3", "-fPIC", "-shared", hsrc, "-o", hout], check=True)
+        subprocess.run(["gcc", "-O3", "-fopenmp", "-march=x86-64-v3", "-ffp-contract=off", "-fPIC", "-shared", hsrc, "-o", hout], check=True)
     out["hostcb_f64"] = hout
     return out
 

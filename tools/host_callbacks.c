@@ -33,23 +33,34 @@ static double x0_value(unsigned int h)
     return 0.95 + prod;
 }
 
+static inline double rosen_entry(double xm, double xc, double xp, int has_left, int has_right)
+{
+    double out = 0.0;
+    if (has_left) out += 200.0 * (xc - xm * xm);
+    if (has_right) { out -= 400.0 * (xp - xc * xc) * xc; out -= 2.0 * (1.0 - xc); }
+    return out;
+}
+
 void host_rosenbrock_grad(const real_t *x, real_t *g, long long n_local, long long offset, long long n_global,
                           double halo_left, double halo_right)
 {
+    if (n_local <= 0) return;
+    /* the two ends of the shard (they may be the ends of the whole vector, or need the neighbours' halo values) */
+    {
+        const double xp = n_local > 1 ? (double) x[1] : halo_right;
+        g[0] = (real_t) rosen_entry(halo_left, (double) x[0], xp, offset > 0, offset < n_global - 1);
+    }
+    if (n_local > 1) {
+        const long long i = n_local - 1;
+        g[i] = (real_t) rosen_entry((double) x[i - 1], (double) x[i], halo_right, 1, offset + i < n_global - 1);
+    }
+    /* interior: branch-free, same operation order as the boundary form (example/c_rosen.c:32-37) */
     #pragma omp parallel for schedule(static)
-    for (long long i = 0; i < n_local; i++) {
-        const long long gi = i + offset;
-        const double xc = (double) x[i];
-        double out = 0.0;
-        if (gi > 0) {
-            const double xm = (i > 0) ? (double) x[i - 1] : halo_left;
-            out += 200.0 * (xc - xm * xm);
-        }
-        if (gi < n_global - 1) {
-            const double xp = (i < n_local - 1) ? (double) x[i + 1] : halo_right;
-            out -= 400.0 * (xp - xc * xc) * xc;
-            out -= 2.0 * (1.0 - xc);
-        }
+    for (long long i = 1; i < n_local - 1; i++) {
+        const double xm = (double) x[i - 1], xc = (double) x[i], xp = (double) x[i + 1];
+        double out = 200.0 * (xc - xm * xm);
+        out -= 400.0 * (xp - xc * xc) * xc;
+        out -= 2.0 * (1.0 - xc);
         stream_store(&g[i], (real_t) out);
     }
 }

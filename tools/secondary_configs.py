@@ -64,8 +64,8 @@ def _cfg2(peaks, cpu):
     if cpu:
         def cpu_fn(X, y):
             Xh, yh = X[:40000].cpu().numpy(), y[:40000].cpu().numpy()
-            return CC.best_of_threads(CC.logistic_reference, kind="SQN", X=Xh, y=yh, batch=B, steps=50, warm=110, L=L, big=big)
-    out = BC.run_logistic("cfg2", "SQN", 1000000, 4096, B, 1000, L=L, big=big, native=True, quiet=True, cpu_fn=cpu_fn)
+            return CC.best_of_threads(CC.logistic_reference, kind="SQN", X=Xh, y=yh, batch=B, steps=50, warm=120, L=L, big=big, step=1e-2)
+    out = BC.run_logistic("cfg2", "SQN", 1000000, 4096, B, 1000, L=L, big=big, native=True, quiet=True, cpu_fn=cpu_fn, step=1e-2)
     # per step: one gradient sweep (B x n); per L steps one fused Hessian-vector sweep of the big batch and ~9 vectors of
     # pair work; optimizer (4m + 6) n-vectors
     b = B * n * 8 + big * n * 8 / L + (4 * MEM + 6 + 9.0 / L) * n * 8

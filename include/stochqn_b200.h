@@ -67,7 +67,10 @@ enum stochqn_b200_option {
        sizes where three launches dominate) instead of K1 -> K2 -> K3: a single 1024-thread CTA up to n = 2048, a
        cooperative grid with one grid barrier above.  Default 2048 (environment: STOCHQN_B200_SMALL_N); 0 disables.
        Not used when the optimizer is sharded. */
-    STOCHQN_B200_OPT_ONE_LAUNCH_MAX_N = 5
+    STOCHQN_B200_OPT_ONE_LAUNCH_MAX_N = 5,
+    /* stochqn_b200_fit_batch / fit_batches: largest n for which the request loop of a mini-batch runs on the device
+       (csrc/kernels_loop.cuh; default 65536, environment: STOCHQN_B200_LOOP_MAX_N); 0: always the host-driven loop. */
+    STOCHQN_B200_OPT_DEVICE_LOOP_MAX_N = 6
 };
 int stochqn_b200_set_option(void *ws, int option, long long value);
 /* current value of an option of this workspace (-1: unknown option or workspace) */
@@ -82,7 +85,8 @@ enum stochqn_b200_stat {
     STOCHQN_B200_STAT_KA2_MS = 9, STOCHQN_B200_STAT_KA2_COUNT = 10,   /* adaQN: the second dot pass (K1/K3 slots hold KA1/KA3) */
     /* steps taken by the one-launch kernel used for latency-bound sizes (n <= 2048 unless STOCHQN_B200_SMALL_N
        says otherwise; 0 there disables it): dots, solve and update in one cooperative launch instead of three */
-    STOCHQN_B200_STAT_ONE_LAUNCH_STEPS = 11
+    STOCHQN_B200_STAT_ONE_LAUNCH_STEPS = 11,
+    STOCHQN_B200_STAT_DEVICE_LOOP_STEPS = 12                          /* steps taken by the device-side loop kernels */
 };
 int stochqn_b200_get_stat(void *ws, int what, double *out);
 
@@ -278,6 +282,25 @@ int stochqn_b200_fit_batch(void *ws, real_t *x, real_t step_size, const stochqn_
                            const stochqn_b200_rows *batch, const stochqn_b200_rows *long_batch,
                            const stochqn_b200_rows *valset, int *task, real_t **req, real_t **req_vec,
                            stochqn_b200_fit_report *report);
+
+/* Several consecutive mini-batches of one resident matrix in ONE call, with the request loop on the DEVICE:
+   mini-batch b (b = 0 .. nbatches-1) is rows [first_row + b*batch_rows, first_row + (b+1)*batch_rows) of `data` (the
+   last one may be cut short by data->nrows); the long batch a request of mini-batch b may need is rows
+   [long_first[b], long_first[b] + long_rows[b]) of `data` (host arrays of nbatches entries, or NULL: none).
+   For oLBFGS, and for the ordinary steps of SQN (those that are not followed by averaging / pair work), up to
+   STOCHQN_B200_OPT_DEVICE_LOOP_MAX_N variables, nothing is waited for: the ring-buffer counters live in a device record,
+   the step and pair kernels (csrc/kernels_loop.cuh) take the accept / reject / curvature decisions of
+   src/stochqn.c:825-835, 883-900 themselves and skip what the reference would skip, and the host enqueues
+   gradient -> step (-> gradient -> pair) per mini-batch back to back.  The counters of the public struct, the task /
+   info tallies of `report` and *task / *req are brought up to date once, before the call returns.  Every other
+   mini-batch (SQN / adaQN pair boundaries, adaQN, larger n, sharded workspaces) goes through the loop of
+   stochqn_b200_fit_batch.  Same return values as stochqn_b200_fit_batch (1: a request of some mini-batch could not be
+   served from the ranges given; the call stops there with that request pending).  stochqn_b200_fit_batch itself takes
+   the same route for its single mini-batch (one wait per mini-batch instead of one per request). */
+int stochqn_b200_fit_batches(void *ws, real_t *x, real_t step_size, const stochqn_b200_model *model,
+                             const stochqn_b200_rows *data, long long first_row, long long batch_rows, long long nbatches,
+                             const long long *long_first, const long long *long_rows, const stochqn_b200_rows *valset,
+                             int *task, real_t **req, real_t **req_vec, stochqn_b200_fit_report *report);
 
 /* ---- workspace export / import (checkpoint / resume) ----------------------------------------
    The reference keeps all state in host-language arrays, so saveRDS / pickle of the R / Python

@@ -27,7 +27,7 @@ EXT_SYMBOLS = (
     "stochqn_b200_logistic_loss", "stochqn_b200_export", "stochqn_b200_import",
     "stochqn_b200_logistic_sk_grad", "stochqn_b200_logistic_sk_hess_vec", "stochqn_b200_logistic_sk_loss",
     "stochqn_b200_multinomial_work_size", "stochqn_b200_multinomial_loss_grad", "stochqn_b200_multinomial_hess_vec",
-    "stochqn_b200_gemm_tn", "stochqn_b200_fit_batch", "stochqn_b200_multinomial_grad_reduce_scatter",
+    "stochqn_b200_gemm_tn", "stochqn_b200_fit_batch", "stochqn_b200_fit_batches", "stochqn_b200_multinomial_grad_reduce_scatter",
     "stochqn_b200_all_gather_p2p",
 )
 
@@ -36,10 +36,12 @@ OPT_TRUST_X_MIRROR = 2
 OPT_PROFILE = 3
 OPT_SYNC_RETURN = 4
 OPT_ONE_LAUNCH_MAX_N = 5
+OPT_DEVICE_LOOP_MAX_N = 6
 STAT_K1_MS, STAT_K1_COUNT, STAT_K3_MS, STAT_K3_COUNT, STAT_K4_MS, STAT_K4_COUNT, STAT_LAST_BOUND = 1, 2, 3, 4, 5, 6, 7
 STAT_EXACT_NORM_STEPS = 8
 STAT_KA2_MS, STAT_KA2_COUNT = 9, 10
 STAT_ONE_LAUNCH_STEPS = 11
+STAT_DEVICE_LOOP_STEPS = 12
 
 
 def lib_path(dtype) -> str:
@@ -130,6 +132,8 @@ def load(dtype=np.float64) -> StochqnABI:
     abi.Model = model_struct(real)
     lib.stochqn_b200_fit_batch.argtypes = [vp, vp, real, C.POINTER(abi.Model), C.POINTER(Rows), C.POINTER(Rows), C.POINTER(Rows),
                                            C.POINTER(ci), C.POINTER(vp), C.POINTER(vp), C.POINTER(FitReport)]
+    lib.stochqn_b200_fit_batches.argtypes = [vp, vp, real, C.POINTER(abi.Model), C.POINTER(Rows), ll, ll, ll, C.POINTER(ll), C.POINTER(ll),
+                                             C.POINTER(Rows), C.POINTER(ci), C.POINTER(vp), C.POINTER(vp), C.POINTER(FitReport)]
     lib.stochqn_b200_export.argtypes = [vp, C.POINTER(HostState)]
     lib.stochqn_b200_import.argtypes = [vp, C.POINTER(HostState)]
     for name in EXT_SYMBOLS:

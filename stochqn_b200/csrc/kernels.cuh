@@ -921,3 +921,4 @@ kf2_combine(const T* __restrict__ F, size_t ld, int k, const double* __restrict_
 
 #include "kernels_small.cuh"
 #include "kernels_adaqn.cuh"
+#include "kernels_loop.cuh"

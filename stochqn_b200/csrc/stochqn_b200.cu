@@ -181,6 +181,14 @@ struct Ctx {
     cudaEvent_t ev_x = nullptr;
     long long chunk_elems = 0;          // piece length in elements (0: not set up yet)
     size_t partials_cap = 0;            // doubles allocated in `partials`
+    // device-side request loop (kernels_loop.cuh, guided_impl.inc)
+    LoopState* loop_dev = nullptr;      // the ring counters while a fit_batch / fit_batches call is in progress
+    LoopState* loop_host = nullptr;     // pinned staging copy
+    bool loop_active = false;           // the device record is the truth, the public struct is stale
+    unsigned long long* loop_bar = nullptr;   // grid-barrier counter of the loop kernels
+    double* rec2 = nullptr;             // 2-value partial records of the loop kernels
+    long long loop_max_n = 0;           // largest n served by the loop kernels (0: never)
+    double loop_steps = 0;              // steps taken by them
     Comm* comm = nullptr;
     long long n_global = 0;
     // host-pointer compatibility mode
@@ -636,6 +644,8 @@ void free_ctx(Ctx* c)
     for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_out) cudaEventDestroy(e);
     if (c->ev_x) cudaEventDestroy(c->ev_x);
+    cudaFree(c->loop_dev); cudaFree(c->loop_bar); cudaFree(c->rec2);
+    if (c->loop_host) cudaFreeHost(c->loop_host);
     if (c->copy_in) cudaStreamDestroy(c->copy_in);
     if (c->copy_out) cudaStreamDestroy(c->copy_out);
     delete c;
@@ -684,6 +694,9 @@ Ctx* make_ctx(Kind kind, long long n, int msize, int fisher_size)
         const char* e1 = getenv("STOCHQN_B200_ONE_CTA_N");
         if (e1) c->one_cta_n = atoll(e1);
         if (!coop && c->small_n > c->one_cta_n) c->small_n = c->one_cta_n;       // the multi-CTA form needs a cooperative launch
+        const char* e2 = getenv("STOCHQN_B200_LOOP_MAX_N");
+        c->loop_max_n = e2 ? atoll(e2) : (1ll << 16);
+        if (!coop && c->loop_max_n > kOneCtaN) c->loop_max_n = kOneCtaN;
     }
     ok = ok && cudaHostAlloc((void**) &c->hb, sizeof(HostBlock), cudaHostAllocMapped) == cudaSuccess;
     if (ok) {

@@ -121,6 +121,27 @@ def run_logistic(name, kind, nrows, d, batch, steps, L=10, big=20000, native=Fal
     else:
         def serve_call():
             serve(); call()
+    if native == "batches":
+        # the request loop on the DEVICE: `chunk` consecutive mini-batches per library call (stochqn_b200_fit_batches), the
+        # ring counters come back once per call
+        chunk = 50
+        data = _lib.Rows(X.data_ptr(), n, y.data_ptr(), 1, None, nrows)
+        LL = C.c_longlong * chunk
+        lf, lr = LL(), LL()
+
+        def serve_call():
+            b0 = (state["b"] + 1) % nb
+            cnt_b = min(chunk, nb - b0)
+            for i in range(cnt_b):
+                e = (b0 + i + 1) * batch
+                lr[i] = min(big, e)
+                lf[i] = e - lr[i]
+            rc = lib.stochqn_b200_fit_batches(ws, x.data_ptr(), step, C.byref(M), C.byref(data), b0 * batch, batch, cnt_b, lf, lr, None,
+                                              C.byref(task), C.byref(req), C.byref(req_vec), C.byref(rep))
+            assert rc == 0, (rc, _lib.last_error(abi))
+            state["b"] = b0 + cnt_b - 1
+            for i in range(4):
+                infos[200 + i] = infos.get(200 + i, 0) + rep.n_info[i]
     while niter() < warm:
         serve_call()
     torch.cuda.synchronize()
@@ -133,12 +154,16 @@ def run_logistic(name, kind, nrows, d, batch, steps, L=10, big=20000, native=Fal
         serve_call()
     e1.record()
     torch.cuda.synchronize()
+    steps = niter() - it0                     # (a chunked call may run past the requested count)
     ms = e0.elapsed_time(e1) / steps
     xp, yp = rows(0, min(nrows, 20000))
     lib.stochqn_b200_logistic_loss(xp, n, yp, None, min(nrows, 20000), n, x.data_ptr(), lam, loss.data_ptr(), work.data_ptr(), None)
-    out = dict(config=name, optimizer=kind, loop="library (stochqn_b200_fit_batch)" if native else "python (one call per request)",
+    loop = {"batches": "device (stochqn_b200_fit_batches, 50 mini-batches per call)", True: "library (stochqn_b200_fit_batch)"}.get(
+        native, "python (one call per request)")
+    out = dict(config=name, optimizer=kind, loop=loop,
                dtype="f64", n=n, rows=nrows, batch=batch, steps=steps, ms_per_step=ms, steps_per_s=1e3 / ms,
                tasks=tasks, infos=infos, mem_used=int(ws.contents.bfgs_memory.contents.mem_used),
+               device_loop_steps=_lib.get_stat(abi, ws, _lib.STAT_DEVICE_LOOP_STEPS),
                launches_per_step=(_lib.launch_count() - launches0) / steps, loss_after=float(loss.item()), loss_at_zero=float(np.log(2.0)))
     {"oLBFGS": lib.dealloc_oLBFGS, "SQN": lib.dealloc_SQN}[kind](ws)
     if cpu_fn is not None:          # the reference on the host cores, on rows of the same matrix (bench.py's secondary block)
@@ -436,6 +461,10 @@ def main():
         run_logistic("cfg1", "oLBFGS", 100000, 1000, 1000, a.steps)
     if "cfg1n" in a.configs:
         run_logistic("cfg1", "oLBFGS", 100000, 1000, 1000, a.steps, native=True)
+    if "cfg1d" in a.configs:
+        run_logistic("cfg1", "oLBFGS", 100000, 1000, 1000, a.steps, native="batches")
+    if "cfg2d" in a.configs:
+        run_logistic("cfg2", "SQN", a.rows_cfg2, 4096, 2000, a.steps, L=10, big=20000, native="batches", step=1e-2)
     if "cfg2" in a.configs:
         run_logistic("cfg2", "SQN", a.rows_cfg2, 4096, 2000, a.steps, L=10, big=20000, step=1e-2)
     if "cfg2n" in a.configs:

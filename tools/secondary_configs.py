@@ -41,7 +41,7 @@ def _cfg1(peaks, cpu):
             Xh, yh = X[:20000].cpu().numpy(), y[:20000].cpu().numpy()
             return CC.best_of_threads(CC.logistic_reference, kind="oLBFGS", X=Xh, y=yh, batch=B, steps=300, warm=15)
     out = None
-    for native in (True, False):                # the library's own request loop and the caller's loop: report the better, keep both
+    for native in ("batches", True, False):     # device-side loop, the library's host-driven loop, the caller's loop: report the best, keep all
         r = BC.run_logistic("cfg1", "oLBFGS", 100000, 1000, B, 2000, native=native, quiet=True, cpu_fn=cpu_fn if out is None else None)
         if out is None:
             out = r
@@ -65,7 +65,7 @@ def _cfg2(peaks, cpu):
         def cpu_fn(X, y):
             Xh, yh = X[:40000].cpu().numpy(), y[:40000].cpu().numpy()
             return CC.best_of_threads(CC.logistic_reference, kind="SQN", X=Xh, y=yh, batch=B, steps=50, warm=120, L=L, big=big, step=1e-2)
-    out = BC.run_logistic("cfg2", "SQN", 1000000, 4096, B, 1000, L=L, big=big, native=True, quiet=True, cpu_fn=cpu_fn, step=1e-2)
+    out = BC.run_logistic("cfg2", "SQN", 1000000, 4096, B, 1000, L=L, big=big, native="batches", quiet=True, cpu_fn=cpu_fn, step=1e-2)
     # per step: one gradient sweep (B x n); per L steps one fused Hessian-vector sweep of the big batch and ~9 vectors of
     # pair work; optimizer (4m + 6) n-vectors
     b = B * n * 8 + big * n * 8 / L + (4 * MEM + 6 + 9.0 / L) * n * 8

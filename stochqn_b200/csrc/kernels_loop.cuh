@@ -150,14 +150,7 @@ kl_step(LoopArgs A, LoopState* __restrict__ st, const T* g, T* gout, T* S, const
     const T gamma = (T) coef_s[2 * m];
     const T nstep = -step;
 
-    auto direction = [&](long long i) -> T {            // K3's arithmetic: (gamma*g + sum a_j s_j) + sum (gamma b_j) y_j
-        T p0 = gamma * g[i], p1 = (T) 0;
-        for (int r = 0; r < used; ++r) {
-            p0 = fma((T) coef_s[r], S[(size_t) r * A.ld + i], p0);
-            p1 = fma((T) coef_s[m + r], Y[(size_t) r * A.ld + i], p1);
-        }
-        return p0 + p1;
-    };
+    auto direction = [&](long long i) -> T { return combine_direction<T>(g, S, Y, A.ld, i, used, m, gamma, coef_s); };
 
     bool d_in_g = false;
     if (status == ST_NEED_EXACT_NORM) {

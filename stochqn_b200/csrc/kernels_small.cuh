@@ -47,17 +47,48 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsign
 template <typename T>
 __device__ __forceinline__ double slice_dot(const T* __restrict__ a, const T* __restrict__ b, long long e0, long long e1, int lane)
 {
+    // 16 independent loads in flight per lane in EVERY trip, the ragged end included (predicated, not a scalar tail loop:
+    // at these sizes the kernel is a chain of load latencies, and a one-element-per-trip tail was most of it)
     double acc = 0;
-    long long i = e0 + lane;
-    for (; i + 7 * 32 < e1; i += 8 * 32) {              // 16 independent loads in flight per lane
+    for (long long base = e0; base < e1; base += 8 * 32) {
         T av[8], bv[8];
         #pragma unroll
-        for (int u = 0; u < 8; ++u) { av[u] = a[i + u * 32]; bv[u] = b[i + u * 32]; }
+        for (int u = 0; u < 8; ++u) {
+            const long long i = base + lane + u * 32;
+            const bool ok = i < e1;
+            av[u] = ok ? a[i] : (T) 0;
+            bv[u] = ok ? b[i] : (T) 0;
+        }
         #pragma unroll
         for (int u = 0; u < 8; ++u) acc = fma((double) av[u], (double) bv[u], acc);
     }
-    for (; i < e1; i += 32) acc = fma((double) a[i], (double) b[i], acc);
     return warp_sum(acc);
+}
+
+// d_i = (gamma*g_i + sum_j a_j s_ji) + sum_j (gamma b_j) y_ji with K3's FMA order; the row loads are issued eight pairs at
+// a time ahead of the FMA chains (a plain loop over a run-time row count serialises 2*used load latencies)
+template <typename T>
+__device__ __forceinline__ T combine_direction(const T* __restrict__ g, const T* S, const T* __restrict__ Y, size_t ld, long long i,
+                                               int used, int m, T gamma, const double* coef_s)
+{
+    T p0 = gamma * g[i], p1 = (T) 0;
+    for (int r0 = 0; r0 < used; r0 += 8) {
+        T sv[8], yv[8];
+        #pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const bool ok = r0 + q < used;
+            sv[q] = ok ? S[(size_t) (r0 + q) * ld + i] : (T) 0;
+            yv[q] = ok ? Y[(size_t) (r0 + q) * ld + i] : (T) 0;
+        }
+        #pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (r0 + q < used) {
+                p0 = fma((T) coef_s[r0 + q], sv[q], p0);
+                p1 = fma((T) coef_s[m + r0 + q], yv[q], p1);
+            }
+        }
+    }
+    return p0 + p1;
 }
 
 // Launched either as ONE CTA of 1024 threads with an ordinary launch (n <= kOneCtaN = 2048: no grid barrier at all) or as a
@@ -131,12 +162,7 @@ ks_step(SmallArgs K, SolveArgs A, const T* g, T* gout, T* S, const T* __restrict
     const T gamma = (T) coef_s[2 * m];
     const T nstep = -step;
     for (long long i = e0 + threadIdx.x; i < e1; i += nthr) {
-        T p0 = gamma * g[i], p1 = (T) 0;
-        for (int r = 0; r < used; ++r) {
-            p0 = fma((T) coef_s[r], S[(size_t) r * K.ld + i], p0);
-            p1 = fma((T) coef_s[m + r], Y[(size_t) r * K.ld + i], p1);
-        }
-        T d = p0 + p1;
+        T d = combine_direction<T>(g, S, Y, K.ld, i, used, m, gamma, coef_s);
         const T xv = fma(nstep, d, x[i]);
         x[i] = xv;
         if constexpr (MODE == MODE_OLBFGS) {

@@ -77,14 +77,18 @@ def _run(kind, n, batch, nbatches, min_curv, loop_max_n, chunk, step=0.1, L=4, m
 
 @pytest.mark.parametrize("kind", ["oLBFGS", "SQN"])
 @pytest.mark.parametrize("n", [37, 1001, 2049, 5000])        # one 1024-thread CTA up to 2048, a cooperative grid above
-@pytest.mark.parametrize("min_curv", [1e-4, 0.22, 0.35])      # 0.22: a mix; 0.35: every pair is rejected (the Hessian's eigenvalues are ~0.2) -> Q1
-def test_device_loop_matches_the_host_driven_loop(kind, n, min_curv):
+@pytest.mark.parametrize("factor", [0.0, 0.8, 3.0])
+def test_device_loop_matches_the_host_driven_loop(kind, n, factor):
+    # curvature of a pair on a 64-row batch is about 0.2 * max(1, n / 64) (sigmoid'(z) ~ 0.2, |x_i|^2 ~ n): a threshold at
+    # 0.8 of that rejects some pairs, at 3 times that every pair (quirk Q1: the slot is zeroed, with a full memory the
+    # next direction is NaN and the memory is flushed)
+    min_curv = 1e-4 if factor == 0 else factor * 0.2 * max(1.0, n / 64.0)
     a = _run(kind, n, 64, 45, min_curv, loop_max_n=1 << 16, chunk=7)
     b = _run(kind, n, 64, 45, min_curv, loop_max_n=0, chunk=7)
     assert a["loop_steps"] > 0 and b["loop_steps"] == 0
     for k in ("calls", "n_info", "niter", "section", "mem_used", "mem_st_ix"):
         assert a[k] == b[k], (k, a[k], b[k])
-    if min_curv > 0.3:
+    if factor > 2:
         assert a["n_info"][2] > 0, "the forced curvature rejections did not happen"
     assert np.all(np.isfinite(a["x"]))
     assert np.max(np.abs(a["x"] - b["x"])) <= 1e-10 * max(np.max(np.abs(b["x"])), 1e-300)

@@ -237,6 +237,8 @@ class CudaRosen:
         self.stream = torch.cuda.current_stream().cuda_stream
         self.x = torch.empty(self.n_local, device="cuda", dtype=torch.float64)
         self.g = torch.empty(self.n_local, device="cuda", dtype=torch.float64)
+        self.g2 = torch.empty(self.n_local, device="cuda", dtype=torch.float64)
+        self.prefetched, self.halo_valid = False, False
         self.halo = torch.zeros(2, device="cuda", dtype=torch.float64)
         self.scratch = torch.zeros(2 * max(self.world, 1), device="cuda", dtype=torch.float64)
         lib.stochqn_b200_rosenbrock_x0(self.x.data_ptr(), self.n_local, self.offset, self.stream)
@@ -248,30 +250,44 @@ class CudaRosen:
         self.req, self.task, self.info = C.c_void_p(), C.c_int(), C.c_int()
         self.info_events = 0
         self.trace = [] if trace else None
-        self._call()                                                      # section 0: first request
+        self._call(self.g)                                                # section 0: first request
 
-    def _call(self):
-        ret = self.lib.run_oLBFGS(STEP, self.x.data_ptr(), self.g.data_ptr(), C.byref(self.req), C.byref(self.task), self.ws, C.byref(self.info))
+    def _call(self, gbuf):
+        ret = self.lib.run_oLBFGS(STEP, self.x.data_ptr(), gbuf.data_ptr(), C.byref(self.req), C.byref(self.task), self.ws, C.byref(self.info))
         self.info_events += self.info.value != 200
         if self.trace is not None:
             w = self.ws.contents
             m = w.bfgs_memory.contents
             self.trace.append((int(self.task.value), int(ret), int(self.info.value), int(w.niter), int(w.section), int(m.mem_used), int(m.mem_st_ix)))
 
-    def _serve(self):
+    def _serve(self, gbuf, same_point=False):
+        """The caller's gradient callback (bundled device kernel) at *req.  Sharded: the halo exchange is fused into the
+        gradient kernel (peer memory), one launch; a second evaluation at the SAME point reuses the neighbours' edge values
+        the first one fetched (no second exchange)."""
         lib = self.lib
-        if self.comm is not None and self.world > 1:      # halo exchange fused into the gradient kernel (peer memory), one launch
-            lib.stochqn_b200_rosenbrock_grad_sharded(self.req.value, self.g.data_ptr(), self.n_local, self.offset, self.n, self.rank, self.world,
+        if self.comm is not None and self.world > 1 and not (same_point and self.halo_valid):
+            lib.stochqn_b200_rosenbrock_grad_sharded(self.req.value, gbuf.data_ptr(), self.n_local, self.offset, self.n, self.rank, self.world,
                                                      self.comm, self.halo.data_ptr(), self.scratch.data_ptr(), self.stream)
+            self.halo_valid = True
         else:
-            lib.stochqn_b200_rosenbrock_grad(self.req.value, self.g.data_ptr(), self.n_local, self.offset, self.n, self.halo.data_ptr(), self.stream)
+            lib.stochqn_b200_rosenbrock_grad(self.req.value, gbuf.data_ptr(), self.n_local, self.offset, self.n, self.halo.data_ptr(), self.stream)
 
     def iteration(self):
-        self._serve()                       # calc_grad
-        self._call()                        # step
+        """One oLBFGS iteration through the free-mode ABI.  The two gradients of an iteration live in two buffers, so that
+        the gradient the NEXT request will ask for (calc_grad at x, which the pair call does not move: stochqn.c:1024-1031)
+        is already queued behind the same-batch gradient when the pair call waits for its curvature flag - the GPU never
+        idles between the pair call's return and the caller's next launch.  Same requests, same evaluations, same order
+        of optimizer calls; a rejected step simply discards nothing (its next request is served when it is made)."""
+        if not self.prefetched:
+            self._serve(self.g)                 # calc_grad
+        self._call(self.g)                      # step
+        self.prefetched = False
         if self.task.value == 102:
-            self._serve()                   # calc_grad_same_batch
-            self._call()                    # pair
+            self._serve(self.g2)                # calc_grad_same_batch at the new x
+            self._serve(self.g, same_point=True)   # what the pair call will request next: calc_grad at the same x
+            self.prefetched = True
+            self._call(self.g2)                 # pair
+            assert self.task.value == 101 and self.req.value == self.x.data_ptr()
 
     def run(self, iters):
         for _ in range(iters):
@@ -311,7 +327,7 @@ class CudaRosen:
         if self.ws:
             self.lib.dealloc_oLBFGS(self.ws)
             self.ws = None
-        self.x = self.g = None
+        self.x = self.g = self.g2 = None
 
 
 def sharded_parity(torch, dist, abi, rank, world, comm_default):

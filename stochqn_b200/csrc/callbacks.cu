@@ -74,7 +74,8 @@ __device__ __forceinline__ double rosen_g(double xm, double xc, double xp, bool 
 template <int VEC, bool SHARDED, int U, bool SHUFFLE>
 __global__ void __launch_bounds__(kT)
 rosen_grad_kernel(const real_t* __restrict__ x, real_t* __restrict__ g, long long n, long long offset,
-                  long long n_global, const real_t* __restrict__ halo, sqn::PeerArgs pa, int* __restrict__ error_flag)
+                  long long n_global, const real_t* __restrict__ halo, sqn::PeerArgs pa, int* __restrict__ error_flag,
+                  real_t* __restrict__ halo_out)
 {
     const long long nchunks = n / VEC;
     const long long stride = (long long) gridDim.x * blockDim.x;
@@ -144,6 +145,7 @@ rosen_grad_kernel(const real_t* __restrict__ x, real_t* __restrict__ g, long lon
     if (!sqn::p2p_allreduce_cta(pa, rec, 2 * pa.world) && t == 0 && error_flag) *error_flag = 1;
     const double hl = pa.rank > 0 ? rec[2 * (pa.rank - 1) + 1] : 0.0;
     const double hr = pa.rank < pa.world - 1 ? rec[2 * (pa.rank + 1)] : 0.0;
+    if (t == 0 && halo_out) { halo_out[0] = (real_t) hl; halo_out[1] = (real_t) hr; }   // kept for re-evaluations at the same point
     const long long a_end = n < VEC ? n : VEC;                           // [0, a_end): first chunk
     long long b_lo = (nchunks - 1) * VEC;                                // [b_lo, n): last chunk + scalar tail
     if (b_lo < a_end) b_lo = a_end;
@@ -530,29 +532,29 @@ int row_slices(long long nrows)
 
 template <bool SHARDED, int U, bool SHUFFLE>
 static void launch_rosen_grad(const real_t* x, real_t* grad, long long n_local, long long offset, long long n_global,
-                              const real_t* halo, const sqn::PeerArgs& pa, int* err, cudaStream_t st)
+                              const real_t* halo, const sqn::PeerArgs& pa, int* err, cudaStream_t st, real_t* halo_out = nullptr)
 {
     constexpr int V = 16 / sizeof(real_t);
     if (((((uintptr_t) x) | ((uintptr_t) grad)) & 15u) == 0)
-        rosen_grad_kernel<V, SHARDED, U, SHUFFLE><<<grid_1d(n_local / V), kT, 0, st>>>(x, grad, n_local, offset, n_global, halo, pa, err);
+        rosen_grad_kernel<V, SHARDED, U, SHUFFLE><<<grid_1d(n_local / V), kT, 0, st>>>(x, grad, n_local, offset, n_global, halo, pa, err, halo_out);
     else
-        rosen_grad_kernel<1, SHARDED, U, SHUFFLE><<<grid_1d(n_local), kT, 0, st>>>(x, grad, n_local, offset, n_global, halo, pa, err);
+        rosen_grad_kernel<1, SHARDED, U, SHUFFLE><<<grid_1d(n_local), kT, 0, st>>>(x, grad, n_local, offset, n_global, halo, pa, err, halo_out);
 }
 
 template <bool SHARDED>
 static void launch_rosen_grad_variant(const real_t* x, real_t* grad, long long n_local, long long offset, long long n_global,
-                                      const real_t* halo, const sqn::PeerArgs& pa, int* err, cudaStream_t st)
+                                      const real_t* halo, const sqn::PeerArgs& pa, int* err, cudaStream_t st, real_t* halo_out = nullptr)
 {
     static int variant = -1;
     if (variant < 0) { const char* e = getenv("STOCHQN_B200_ROSEN_VARIANT"); variant = e ? atoi(e) : 0; }
     // measured on B200, n = 2^27 fp64 (STOCHQN_B200_ROSEN_VARIANT, dev switch): neighbours by L1-hitting scalar loads
     // with two chunks in flight 0.367 ms (5.85 TB/s); one chunk 0.445 ms; neighbours by warp shuffle 0.449-0.462 ms
     switch (variant) {
-        case 1:  launch_rosen_grad<SHARDED, 1, true>(x, grad, n_local, offset, n_global, halo, pa, err, st); break;
-        case 2:  launch_rosen_grad<SHARDED, 2, true>(x, grad, n_local, offset, n_global, halo, pa, err, st); break;
-        case 3:  launch_rosen_grad<SHARDED, 1, false>(x, grad, n_local, offset, n_global, halo, pa, err, st); break;
-        case 4:  launch_rosen_grad<SHARDED, 4, false>(x, grad, n_local, offset, n_global, halo, pa, err, st); break;
-        default: launch_rosen_grad<SHARDED, 2, false>(x, grad, n_local, offset, n_global, halo, pa, err, st); break;
+        case 1:  launch_rosen_grad<SHARDED, 1, true>(x, grad, n_local, offset, n_global, halo, pa, err, st, halo_out); break;
+        case 2:  launch_rosen_grad<SHARDED, 2, true>(x, grad, n_local, offset, n_global, halo, pa, err, st, halo_out); break;
+        case 3:  launch_rosen_grad<SHARDED, 1, false>(x, grad, n_local, offset, n_global, halo, pa, err, st, halo_out); break;
+        case 4:  launch_rosen_grad<SHARDED, 4, false>(x, grad, n_local, offset, n_global, halo, pa, err, st, halo_out); break;
+        default: launch_rosen_grad<SHARDED, 2, false>(x, grad, n_local, offset, n_global, halo, pa, err, st, halo_out); break;
     }
 }
 
@@ -585,7 +587,8 @@ int stochqn_b200_rosenbrock_grad_sharded(const real_t* x, real_t* grad, long lon
         if (int r = stochqn_b200_rosenbrock_halo(x, n_local, rank, world_size, comm, halo, scratch, stream)) return r;
         return stochqn_b200_rosenbrock_grad(x, grad, n_local, offset, n_global, halo, stream);
     }
-    launch_rosen_grad_variant<true>(x, grad, n_local, offset, n_global, nullptr, pa, err, (cudaStream_t) stream);
+    // (the neighbours' edge values it fetched are left in `halo`: a re-evaluation at the same point can use the plain kernel)
+    launch_rosen_grad_variant<true>(x, grad, n_local, offset, n_global, nullptr, pa, err, (cudaStream_t) stream, halo);
     return check_launch("rosenbrock_grad_sharded");
 }
 

@@ -614,7 +614,8 @@ enum : int { PAIR_GRAD_DIFF = 0, PAIR_COPY = 1, PAIR_DOTS_ONLY = 2 };
 // =========================================================================================
 __device__ __forceinline__ void last_block_publish2(const double* __restrict__ partials, double* __restrict__ sums,
                                                     unsigned int* ticket, volatile double* host_out,
-                                                    volatile unsigned long long* seq_host, unsigned long long seq)
+                                                    volatile unsigned long long* seq_host, unsigned long long seq,
+                                                    const PeerArgs& pa)
 {
     __shared__ int is_last;
     __threadfence();
@@ -628,8 +629,13 @@ __device__ __forceinline__ void last_block_publish2(const double* __restrict__ p
         double v = 0;
         for (unsigned b = lane; b < gridDim.x; b += 32) v += __ldcg(partials + (size_t) b * 2 + warp);
         v = warp_sum(v);
-        if (lane == 0) { sums[warp] = v; host_out[warp] = v; }
+        if (lane == 0) sums[warp] = v;
     }
+    __syncthreads();
+    // sharded: the same CTA exchanges the two values with the other ranks over peer memory (no k_finalize launch)
+    bool ok = true;
+    if (pa.world > 1) ok = p2p_allreduce_cta(pa, sums, 2);
+    if (threadIdx.x < 2) host_out[threadIdx.x] = ok ? sums[threadIdx.x] : __longlong_as_double(0x7ff8000000000000ll);
     __syncthreads();
     if (threadIdx.x == 0) { *ticket = 0; publish_seq(seq_host, seq); }
 }
@@ -640,7 +646,7 @@ __global__ void __launch_bounds__(kThreads)
 k4_pair(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ s, T* __restrict__ y,
         T y_reg, long long n, double* __restrict__ partials,
         unsigned int* ticket, double* __restrict__ sums, volatile double* host_out,
-        volatile unsigned long long* seq_host, unsigned long long seq)
+        volatile unsigned long long* seq_host, unsigned long long seq, PeerArgs pa)
 {
     double a_sy = 0, a_ss = 0;
     auto one = [&](size_t off, auto vtag) {
@@ -679,7 +685,7 @@ k4_pair(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ 
     }
     double* out = partials + (size_t) blockIdx.x * 2;
     block_reduce<2>(2, [&](int p) { return p == 0 ? a_sy : a_ss; }, [&](int p, double v) { out[p] = v; });
-    if (ticket) last_block_publish2(partials, sums, ticket, host_out, seq_host, seq);
+    if (ticket) last_block_publish2(partials, sums, ticket, host_out, seq_host, seq, pa);
 }
 
 // Sum `count`-wide partial records over CTAs into `sums` (device), across ranks when sharded (p2p.cuh), and, when

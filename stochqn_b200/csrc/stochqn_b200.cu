@@ -450,23 +450,25 @@ void launch_k3_apply(Ctx* c, int mode, real_t* grad, real_t* S, int new_slot, re
 // `publish`: the last CTA to finish sums the 2-value records and publishes them to the host pair block itself
 // (no k_finalize launch); only when the optimizer is not sharded - the exchange between ranks lives in k_finalize.
 template <int KIND>
-int launch_k4_k(Ctx* c, const real_t* a, const real_t* b, const real_t* s, real_t* y, real_t y_reg, bool publish, const Range& R)
+int launch_k4_k(Ctx* c, const real_t* a, const real_t* b, const real_t* s, real_t* y, real_t y_reg, bool publish, const Range& R,
+                const PeerArgs& pa = PeerArgs())
 {
     const bool vec = aligned16(a + R.off) && aligned16(b + R.off);
     const int grid = grid_for(c, R.len / (vec ? VECW : 1));
     unsigned int* ticket = publish ? c->ticket : nullptr;
     const unsigned long long seq = publish ? ++c->seq_want[FLAG_PAIR] : 0;
     if (vec) k4_pair<real_t, KIND, VECW><<<grid, kThreads, 0, c->stream>>>(a + R.off, b + R.off, s + R.off, y + R.off, y_reg, R.len, R.partials, ticket,
-                                                                          c->sums, c->hb_dev->pair, &c->hb_dev->seq[FLAG_PAIR], seq);
+                                                                          c->sums, c->hb_dev->pair, &c->hb_dev->seq[FLAG_PAIR], seq, pa);
     else     k4_pair<real_t, KIND, 1><<<grid, kThreads, 0, c->stream>>>(a + R.off, b + R.off, s + R.off, y + R.off, y_reg, R.len, R.partials, ticket,
-                                                                       c->sums, c->hb_dev->pair, &c->hb_dev->seq[FLAG_PAIR], seq);
+                                                                       c->sums, c->hb_dev->pair, &c->hb_dev->seq[FLAG_PAIR], seq, pa);
     COUNT_LAUNCH();
     return grid;
 }
 template <int KIND>
-int launch_k4_k(Ctx* c, const real_t* a, const real_t* b, const real_t* s, real_t* y, real_t y_reg, bool publish = false)
+int launch_k4_k(Ctx* c, const real_t* a, const real_t* b, const real_t* s, real_t* y, real_t y_reg, bool publish = false,
+                const PeerArgs& pa = PeerArgs())
 {
-    return launch_k4_k<KIND>(c, a, b, s, y, y_reg, publish, whole(c));
+    return launch_k4_k<KIND>(c, a, b, s, y, y_reg, publish, whole(c), pa);
 }
 
 template <int OP>
@@ -540,15 +542,19 @@ int launch_pair_finalize(Ctx* c, int nblocks, volatile double* host_dst)
     return launch_finalize(c, nblocks, 2, host_dst, host_dst == c->hb_dev->pair ? FLAG_PAIR : FLAG_DIR);
 }
 
-// K4 + publication of s'y, s's to the host pair block: one launch when not sharded, K4 + k_finalize otherwise
+// K4 + publication of s'y, s's to the host pair block in ONE launch: the CTA that finishes last sums the records and,
+// when the optimizer is sharded over peer memory, exchanges the two values with the other ranks itself.  Only the
+// library-all-reduce fallback still needs k_finalize between K4 and the publication.
 template <int KIND>
 int launch_pair(Ctx* c, const real_t* a, const real_t* b, const real_t* s, real_t* y, real_t y_reg, bool profile = false)
 {
     const bool sharded = c->comm && c->comm->world > 1;
+    PeerArgs pa = sharded ? next_exchange(c->comm, 2, c->stream) : PeerArgs();
+    const bool fused = !sharded || pa.world > 1;
     if (profile) prof_begin(c, 2);
-    const int nb = launch_k4_k<KIND>(c, a, b, s, y, y_reg, !sharded);
-    if (profile) prof_end(c, 2);                      // K4 alone: the exchange between ranks is not part of its time
-    if (sharded) return launch_pair_finalize(c, nb, c->hb_dev->pair);
+    const int nb = launch_k4_k<KIND>(c, a, b, s, y, y_reg, fused, pa);
+    if (profile) prof_end(c, 2);
+    if (!fused) return launch_pair_finalize(c, nb, c->hb_dev->pair);
     return 0;
 }
 

@@ -70,11 +70,19 @@ enum stochqn_b200_option {
     STOCHQN_B200_OPT_ONE_LAUNCH_MAX_N = 5,
     /* stochqn_b200_fit_batch / fit_batches: largest n for which the request loop of a mini-batch runs on the device
        (csrc/kernels_loop.cuh; default 65536, environment: STOCHQN_B200_LOOP_MAX_N); 0: always the host-driven loop. */
-    STOCHQN_B200_OPT_DEVICE_LOOP_MAX_N = 6
+    STOCHQN_B200_OPT_DEVICE_LOOP_MAX_N = 6,
+    /* stochqn_b200_fit_batch / fit_batches, two-class models (0, 1), oLBFGS and the ordinary steps of SQN, n <= 5120:
+       1 (default; environment STOCHQN_B200_FUSED_FIT): a whole RUN of consecutive mini-batches is ONE cooperative launch
+       (csrc/kernels_fit.cuh) - the gradient sweeps, the step, the pair and every decision between them, separated by grid
+       barriers instead of launches; 0: one kernel sequence per mini-batch (csrc/kernels_loop.cuh). */
+    STOCHQN_B200_OPT_FUSED_FIT = 7
 };
 int stochqn_b200_set_option(void *ws, int option, long long value);
 /* current value of an option of this workspace (-1: unknown option or workspace) */
 long long stochqn_b200_get_option(void *ws, int option);
+/* development aid (tools/probe_fit.py): a device buffer of 16 * nbatches 64-bit slots in which CTA 0 of the fused fit kernel
+   (STOCHQN_B200_OPT_FUSED_FIT) leaves %globaltimer stamps at the phase boundaries of every mini-batch; NULL turns it off */
+int stochqn_b200_debug_fit_trace(void *ws, unsigned long long *dev_buf);
 
 enum stochqn_b200_stat {
     STOCHQN_B200_STAT_K1_MS = 1, STOCHQN_B200_STAT_K1_COUNT = 2,     /* accumulated device ms / launches (profile mode) */
@@ -86,7 +94,8 @@ enum stochqn_b200_stat {
     /* steps taken by the one-launch kernel used for latency-bound sizes (n <= 2048 unless STOCHQN_B200_SMALL_N
        says otherwise; 0 there disables it): dots, solve and update in one cooperative launch instead of three */
     STOCHQN_B200_STAT_ONE_LAUNCH_STEPS = 11,
-    STOCHQN_B200_STAT_DEVICE_LOOP_STEPS = 12                          /* steps taken by the device-side loop kernels */
+    STOCHQN_B200_STAT_DEVICE_LOOP_STEPS = 12,                         /* steps taken by the device-side loop kernels */
+    STOCHQN_B200_STAT_FUSED_FIT_STEPS = 13                            /* ... of which inside fused runs (kernels_fit.cuh) */
 };
 int stochqn_b200_get_stat(void *ws, int what, double *out);
 

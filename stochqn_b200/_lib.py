@@ -17,7 +17,7 @@ _LIBS = {}
 
 EXT_SYMBOLS = (
     "stochqn_b200_version", "stochqn_b200_real_bytes", "stochqn_b200_last_error", "stochqn_b200_launch_count",
-    "stochqn_b200_set_stream", "stochqn_b200_set_option", "stochqn_b200_get_option", "stochqn_b200_get_stat", "stochqn_b200_row_stride",
+    "stochqn_b200_set_stream", "stochqn_b200_set_option", "stochqn_b200_get_option", "stochqn_b200_debug_fit_trace", "stochqn_b200_get_stat", "stochqn_b200_row_stride",
     "stochqn_b200_comm_unique_id", "stochqn_b200_comm_init", "stochqn_b200_comm_destroy", "stochqn_b200_comm_uses_p2p",
     "stochqn_b200_set_comm",
     "stochqn_b200_allreduce_f64", "stochqn_b200_allreduce_real", "stochqn_b200_reduce_scatter_real", "stochqn_b200_all_gather_real",
@@ -37,11 +37,13 @@ OPT_PROFILE = 3
 OPT_SYNC_RETURN = 4
 OPT_ONE_LAUNCH_MAX_N = 5
 OPT_DEVICE_LOOP_MAX_N = 6
+OPT_FUSED_FIT = 7
 STAT_K1_MS, STAT_K1_COUNT, STAT_K3_MS, STAT_K3_COUNT, STAT_K4_MS, STAT_K4_COUNT, STAT_LAST_BOUND = 1, 2, 3, 4, 5, 6, 7
 STAT_EXACT_NORM_STEPS = 8
 STAT_KA2_MS, STAT_KA2_COUNT = 9, 10
 STAT_ONE_LAUNCH_STEPS = 11
 STAT_DEVICE_LOOP_STEPS = 12
+STAT_FUSED_FIT_STEPS = 13
 
 
 def lib_path(dtype) -> str:
@@ -97,6 +99,7 @@ def load(dtype=np.float64) -> StochqnABI:
     lib.stochqn_b200_set_option.argtypes = [vp, ci, ll]
     lib.stochqn_b200_get_option.argtypes = [vp, ci]
     lib.stochqn_b200_get_option.restype = ll
+    lib.stochqn_b200_debug_fit_trace.argtypes = [vp, vp]
     lib.stochqn_b200_get_stat.argtypes = [vp, ci, C.POINTER(C.c_double)]
     lib.stochqn_b200_row_stride.argtypes = [vp]
     lib.stochqn_b200_row_stride.restype = sz

@@ -13,6 +13,7 @@
 #include "stochqn_b200.h"
 #include "vecio.cuh"
 #include "p2p.cuh"
+#include "logistic_form.cuh"
 
 // stochqn_b200.cu: PeerArgs of the next exchange on a communicator (world = 0 when the exchange must go through NCCL)
 sqn::PeerArgs stochqn_b200_internal_next_exchange(void* comm, size_t count, int** error_flag, cudaStream_t stream);
@@ -219,31 +220,6 @@ rosen_fun_kernel(const real_t* __restrict__ x, long long n, long long offset, lo
 // pass A: one warp per row: z = x_row'w (and t = x_row'v), r_row written to scratch
 //         grad: r = (sigmoid(z) - y) * sw          hess_vec: r = p(1-p) * sw * t        loss: per-row loss * sw
 // pass B: one thread per column: out[col] = sum_rows r_row X[row][col] / sum(sw) + 2*lambda*u[col]
-enum { LG_GRAD = 0, LG_HVP = 1, LG_LOSS = 2 };
-
-// Two conventions share the kernels:
-//   sk = 0  R/logistic.R:1-37: y in {0,1}, weighted MEANS, penalty lambda*|w|^2 on every coefficient (the intercept is a
-//           column of X);
-//   sk = 1  scikit-learn (<= 1.0) _logistic_loss_and_grad / _logistic_grad_hess, which the reference's Python layer calls
-//           (stochqn/_logistic.py:23-30): y in {-1,+1}, weighted SUMS, penalty alpha/2*|w[:ncols]|^2, and with icpt = 1
-//           an unpenalised intercept stored LAST in w (w has ncols + 1 entries; z = x'w[:ncols] + w[ncols]).
-struct LgForm { int sk; int icpt; };
-
-__device__ __forceinline__ double lg_row_weight(int kind, const LgForm f, double z, double t, double yy, double wt)
-{
-    if (!f.sk) {
-        const double p = 1.0 / (1.0 + exp(-z));
-        if (kind == LG_GRAD) return (p - yy) * wt;
-        if (kind == LG_HVP) return p * (1.0 - p) * wt * t;
-        return -(yy * log(p) + (1.0 - yy) * log(1.0 - p)) * wt;
-    }
-    const double yz = yy * z;
-    const double q = 1.0 / (1.0 + exp(-yz));
-    if (kind == LG_GRAD) return wt * (q - 1.0) * yy;
-    if (kind == LG_HVP) return wt * q * (1.0 - q) * t;
-    return wt * (yz > 0 ? log1p(exp(-yz)) : -yz + log1p(exp(yz)));        // -log sigmoid(yz)
-}
-
 template <int KIND>
 __global__ void __launch_bounds__(kT)
 logistic_rows_kernel(const real_t* __restrict__ X, long long ldx, const real_t* __restrict__ y,
@@ -378,6 +354,7 @@ logistic_fused_kernel(const real_t* __restrict__ X, long long ldx, const real_t*
     const double zc = form.icpt ? (double) w[ncols] : 0.0;
     const double tc = (form.icpt && KIND == LG_HVP) ? (double) v[ncols] : 0.0;
     __shared__ double red[2][2][LT / 32][R];
+    __shared__ double rw[2][R], sc_s[2][R];
     int par = 0;
     // (each thread reads back only the w / v entries it wrote itself: no barrier needed before the loop)
     for (long long row0 = (long long) blockIdx.x * R; row0 < nrows; row0 += (long long) gridDim.x * R) {
@@ -417,19 +394,25 @@ logistic_fused_kernel(const real_t* __restrict__ X, long long ldx, const real_t*
             if (lane == 0) { red[par][0][warp][r] = z; if (KIND == LG_HVP) red[par][1][warp][r] = t; }
         }
         __syncthreads();
-        #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const long long row = row0 + r;
+        // the row weights once per row (thread r < R), not once per thread: the fp64 exp + divide are ~100 issue slots, and
+        // 256 threads each doing all R of them cost as much as streaming a 1000-column row
+        if (tid < R) {
+            const long long row = row0 + tid;
             double z = 0, t = 0;
             #pragma unroll
-            for (int q = 0; q < LT / 32; ++q) { z += red[par][0][q][r]; if (KIND == LG_HVP) t += red[par][1][q][r]; }
+            for (int q = 0; q < LT / 32; ++q) { z += red[par][0][q][tid]; if (KIND == LG_HVP) t += red[par][1][q][tid]; }
             double rr = 0.0;
             if (row < nrows) {
                 const double wt = sw ? (double) sw[row] : 1.0;
                 rr = lg_row_weight(KIND, form, z + zc, t + tc, (double) y[row], wt);
-                if (tid == 0) { sw_sum += wt; r_sum += rr; }
+                sw_sum += wt; r_sum += rr;
             }
-            const real_t rt = (real_t) rr;
+            rw[par][tid] = rr;
+        }
+        __syncthreads();
+        #pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const real_t rt = (real_t) rw[par][r];
             #pragma unroll
             for (int k = 0; k < CPT; ++k) acc[k] = fma(rt, xv[r][k], acc[k]);
         }
@@ -441,7 +424,14 @@ logistic_fused_kernel(const real_t* __restrict__ X, long long ldx, const real_t*
         const long long c = tid + (long long) k * LT;
         if (c < ncols) out[c] = (double) acc[k];
     }
-    if (tid == 0) { out[ncols] = sw_sum; out[ncols + 1] = r_sum; }
+    if (tid < R) { sc_s[0][tid] = sw_sum; sc_s[1][tid] = r_sum; }
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0, b = 0;
+        #pragma unroll
+        for (int r = 0; r < R; ++r) { a += sc_s[0][r]; b += sc_s[1][r]; }
+        out[ncols] = a; out[ncols + 1] = b;
+    }
 }
 
 // 32 columns x 8 record-slices per CTA: thread (tx, ty) adds the records ty, ty+8, ... of column tx (CTA order within

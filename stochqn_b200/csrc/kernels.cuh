@@ -304,7 +304,7 @@ __device__ __forceinline__ int solve_cta(const SolveArgs& A, const double* sums,
     for (int t = threadIdx.x; t < used * used; t += nthreads) {
         const int i = t / used, j = t % used;
         const int pi = ph(i), pj = ph(j);
-        double r = SY[pi * m + pj], yy = YY[pi * m + pj];
+        double r = __ldcg(SY + pi * m + pj), yy = __ldcg(YY + pi * m + pj);      // (L2: another CTA of a persistent grid may have written them)
         if (c >= 0) {
             if (pj == c) { r = sums[2 * m + pi]; yy = sums[3 * m + pi]; }
             else if (pi == c) yy = sums[3 * m + pj];
@@ -316,7 +316,7 @@ __device__ __forceinline__ int solve_cta(const SolveArgs& A, const double* sums,
         const int pi = ph(i);
         sh.pv[i] = sums[pi];
         sh.qv[i] = sums[m + pi];
-        sh.ssv[i] = (pi == c) ? sums[4 * m + 1] : SS[pi];
+        sh.ssv[i] = (pi == c) ? sums[4 * m + 1] : __ldcg(SS + pi);
     }
     for (int j = threadIdx.x; j < 2 * m; j += nthreads) coef_s[j] = 0.0;
     if (write_gram && c >= 0) {              // fold the newest pair's Gram column into the global state
@@ -928,3 +928,4 @@ kf2_combine(const T* __restrict__ F, size_t ld, int k, const double* __restrict_
 #include "kernels_small.cuh"
 #include "kernels_adaqn.cuh"
 #include "kernels_loop.cuh"
+#include "kernels_fit.cuh"

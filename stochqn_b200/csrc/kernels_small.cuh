@@ -68,10 +68,10 @@ __device__ __forceinline__ double slice_dot(const T* __restrict__ a, const T* __
 // d_i = (gamma*g_i + sum_j a_j s_ji) + sum_j (gamma b_j) y_ji with K3's FMA order; the row loads are issued eight pairs at
 // a time ahead of the FMA chains (a plain loop over a run-time row count serialises 2*used load latencies)
 template <typename T>
-__device__ __forceinline__ T combine_direction(const T* __restrict__ g, const T* S, const T* __restrict__ Y, size_t ld, long long i,
-                                               int used, int m, T gamma, const double* coef_s)
+__device__ __forceinline__ T combine_direction_at(T gi, const T* S, const T* __restrict__ Y, size_t ld, long long i,
+                                                  int used, int m, T gamma, const double* coef_s)
 {
-    T p0 = gamma * g[i], p1 = (T) 0;
+    T p0 = gamma * gi, p1 = (T) 0;
     for (int r0 = 0; r0 < used; r0 += 8) {
         T sv[8], yv[8];
         #pragma unroll
@@ -89,6 +89,13 @@ __device__ __forceinline__ T combine_direction(const T* __restrict__ g, const T*
         }
     }
     return p0 + p1;
+}
+
+template <typename T>
+__device__ __forceinline__ T combine_direction(const T* __restrict__ g, const T* S, const T* __restrict__ Y, size_t ld, long long i,
+                                               int used, int m, T gamma, const double* coef_s)
+{
+    return combine_direction_at<T>(g[i], S, Y, ld, i, used, m, gamma, coef_s);
 }
 
 // Launched either as ONE CTA of 1024 threads with an ordinary launch (n <= kOneCtaN = 2048: no grid barrier at all) or as a

@@ -189,6 +189,12 @@ struct Ctx {
     double* rec2 = nullptr;             // 2-value partial records of the loop kernels
     long long loop_max_n = 0;           // largest n served by the loop kernels (0: never)
     double loop_steps = 0;              // steps taken by them
+    // fused runs of mini-batches (kernels_fit.cuh)
+    int fused_fit = 1;                  // 0: never (option FUSED_FIT)
+    unsigned long long* fit_bar = nullptr;    // its grid-barrier counter
+    void* fit_work = nullptr;           // the model's scratch buffer (partial column records)
+    double fit_steps = 0;               // mini-batches served by it
+    unsigned long long* fit_trace = nullptr;   // development aid (stochqn_b200_debug_fit_trace)
     Comm* comm = nullptr;
     long long n_global = 0;
     // host-pointer compatibility mode
@@ -650,7 +656,7 @@ void free_ctx(Ctx* c)
     for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_out) cudaEventDestroy(e);
     if (c->ev_x) cudaEventDestroy(c->ev_x);
-    cudaFree(c->loop_dev); cudaFree(c->loop_bar); cudaFree(c->rec2);
+    cudaFree(c->loop_dev); cudaFree(c->loop_bar); cudaFree(c->rec2); cudaFree(c->fit_bar);
     if (c->loop_host) cudaFreeHost(c->loop_host);
     if (c->copy_in) cudaStreamDestroy(c->copy_in);
     if (c->copy_out) cudaStreamDestroy(c->copy_out);
@@ -703,6 +709,8 @@ Ctx* make_ctx(Kind kind, long long n, int msize, int fisher_size)
         const char* e2 = getenv("STOCHQN_B200_LOOP_MAX_N");
         c->loop_max_n = e2 ? atoll(e2) : (1ll << 16);
         if (!coop && c->loop_max_n > kOneCtaN) c->loop_max_n = kOneCtaN;
+        const char* e3 = getenv("STOCHQN_B200_FUSED_FIT");
+        c->fused_fit = (coop && !(e3 && atoi(e3) == 0)) ? 1 : 0;
     }
     ok = ok && cudaHostAlloc((void**) &c->hb, sizeof(HostBlock), cudaHostAllocMapped) == cudaSuccess;
     if (ok) {

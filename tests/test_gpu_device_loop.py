@@ -23,13 +23,26 @@ def _problem(torch, nrows, n, seed):
     return X, y
 
 
-def _run(kind, n, batch, nbatches, min_curv, loop_max_n, chunk, step=0.1, L=4, mem=5):
+def _run(kind, n, batch, nbatches, min_curv, loop_max_n, chunk, step=0.1, L=4, mem=5, fused=1, model=0, weights=False, short_tail=0,
+         dtype=np.float64):
+    """model 0: R conventions (the intercept is column 0 of X); model 1: scikit-learn conventions with an unpenalised
+    intercept stored last (n - 1 columns, labels +-1).  short_tail: rows missing from the last mini-batch."""
     import torch
-    abi = _lib.load(np.float64)
+    abi = _lib.load(dtype)
     lib = abi.lib
-    nrows = batch * nbatches
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    nrows = batch * nbatches - short_tail
     X, y = _problem(torch, nrows, n, 11)
-    x = torch.zeros(n, device="cuda", dtype=torch.float64)
+    sw = None
+    if weights:
+        sw = (0.5 + torch.rand(nrows, device="cuda", dtype=torch.float64, generator=torch.Generator(device="cuda").manual_seed(5))).to(tdt)
+    ncols = n
+    if model == 1:
+        X = X[:, 1:].contiguous()
+        y = 2.0 * y - 1.0
+        ncols = n - 1
+    X, y = X.to(tdt), y.to(tdt)
+    x = torch.zeros(n, device="cuda", dtype=tdt)
     big = batch * L
     work = torch.empty(lib.stochqn_b200_logistic_work_size(max(batch, big), n), device="cuda", dtype=torch.uint8)
     if kind == "oLBFGS":
@@ -38,15 +51,16 @@ def _run(kind, n, batch, nbatches, min_curv, loop_max_n, chunk, step=0.1, L=4, m
         ws = lib.initialize_SQN(n, mem, L, min_curv, 0, 0.0, 1, 1)
     assert ws
     assert lib.stochqn_b200_set_option(ws, _lib.OPT_DEVICE_LOOP_MAX_N, loop_max_n) == 0
+    assert lib.stochqn_b200_set_option(ws, _lib.OPT_FUSED_FIT, fused) == 0
     req, req_vec, task, info = C.c_void_p(), C.c_void_p(), C.c_int(), C.c_int()
-    g0 = torch.zeros(n, device="cuda", dtype=torch.float64)
+    g0 = torch.zeros(n, device="cuda", dtype=tdt)
     if kind == "oLBFGS":
         lib.run_oLBFGS(step, x.data_ptr(), g0.data_ptr(), C.byref(req), C.byref(task), ws, C.byref(info))
     else:
         lib.run_SQN(step, x.data_ptr(), g0.data_ptr(), g0.data_ptr(), C.byref(req), C.byref(req_vec), C.byref(task), ws, C.byref(info))
     assert task.value == 101
-    M = abi.Model(0, 0, n, 0, 1e-5, work.data_ptr())
-    data = _lib.Rows(X.data_ptr(), n, y.data_ptr(), 1, None, nrows)
+    M = abi.Model(model, 1 if model == 1 else 0, ncols, 0, 1e-5 if model == 0 else 1e-2, work.data_ptr())
+    data = _lib.Rows(X.data_ptr(), ncols, y.data_ptr(), 1, sw.data_ptr() if sw is not None else None, nrows)
     tally = dict(calls=0, n_info=[0, 0, 0, 0], x_changed=0)
     rep = _lib.FitReport()
     b = 0
@@ -70,22 +84,25 @@ def _run(kind, n, batch, nbatches, min_curv, loop_max_n, chunk, step=0.1, L=4, m
     w = ws.contents
     m = w.bfgs_memory.contents
     out = dict(tally, niter=int(w.niter), section=int(w.section), mem_used=int(m.mem_used), mem_st_ix=int(m.mem_st_ix),
-               loop_steps=_lib.get_stat(abi, ws, _lib.STAT_DEVICE_LOOP_STEPS), x=x.cpu().numpy())
+               loop_steps=_lib.get_stat(abi, ws, _lib.STAT_DEVICE_LOOP_STEPS), fit_steps=_lib.get_stat(abi, ws, _lib.STAT_FUSED_FIT_STEPS),
+               x=x.double().cpu().numpy())
     {"oLBFGS": lib.dealloc_oLBFGS, "SQN": lib.dealloc_SQN}[kind](ws)
     return out
 
 
+@pytest.mark.parametrize("fused", [0, 1])                    # 0: one kernel sequence per mini-batch (kernels_loop.cuh); 1: one launch per run (kernels_fit.cuh)
 @pytest.mark.parametrize("kind", ["oLBFGS", "SQN"])
 @pytest.mark.parametrize("n", [37, 1001, 2049, 5000])        # one 1024-thread CTA up to 2048, a cooperative grid above
 @pytest.mark.parametrize("factor", [0.0, 0.8, 3.0])
-def test_device_loop_matches_the_host_driven_loop(kind, n, factor):
+def test_device_loop_matches_the_host_driven_loop(kind, n, factor, fused):
     # curvature of a pair on a 64-row batch is about 0.2 * max(1, n / 64) (sigmoid'(z) ~ 0.2, |x_i|^2 ~ n): a threshold at
     # 0.8 of that rejects some pairs, at 3 times that every pair (quirk Q1: the slot is zeroed, with a full memory the
     # next direction is NaN and the memory is flushed)
     min_curv = 1e-4 if factor == 0 else factor * 0.2 * max(1.0, n / 64.0)
-    a = _run(kind, n, 64, 45, min_curv, loop_max_n=1 << 16, chunk=7)
-    b = _run(kind, n, 64, 45, min_curv, loop_max_n=0, chunk=7)
+    a = _run(kind, n, 64, 45, min_curv, loop_max_n=1 << 16, chunk=7, fused=fused)
+    b = _run(kind, n, 64, 45, min_curv, loop_max_n=0, chunk=7, fused=fused)
     assert a["loop_steps"] > 0 and b["loop_steps"] == 0
+    assert (a["fit_steps"] > 0) == bool(fused) and b["fit_steps"] == 0
     for k in ("calls", "n_info", "niter", "section", "mem_used", "mem_st_ix"):
         assert a[k] == b[k], (k, a[k], b[k])
     if factor > 2:
@@ -94,7 +111,36 @@ def test_device_loop_matches_the_host_driven_loop(kind, n, factor):
     assert np.max(np.abs(a["x"] - b["x"])) <= 1e-10 * max(np.max(np.abs(b["x"])), 1e-300)
 
 
-def test_chunking_of_the_calls_does_not_matter():
-    a = _run("oLBFGS", 1001, 64, 40, 1e-4, loop_max_n=1 << 16, chunk=40)
-    b = _run("oLBFGS", 1001, 64, 40, 1e-4, loop_max_n=1 << 16, chunk=1)
+@pytest.mark.parametrize("fused", [0, 1])
+def test_chunking_of_the_calls_does_not_matter(fused):
+    a = _run("oLBFGS", 1001, 64, 40, 1e-4, loop_max_n=1 << 16, chunk=40, fused=fused)
+    b = _run("oLBFGS", 1001, 64, 40, 1e-4, loop_max_n=1 << 16, chunk=1, fused=fused)
     assert np.array_equal(a["x"], b["x"]) and a["n_info"] == b["n_info"] and a["mem_st_ix"] == b["mem_st_ix"]
+
+
+@pytest.mark.parametrize("kind", ["oLBFGS", "SQN"])
+@pytest.mark.parametrize("model,weights,short_tail,batch,n", [
+    (0, True, 0, 1000, 1001),      # BASELINE config-1 shape with sample weights
+    (1, False, 0, 300, 777),       # scikit-learn conventions: labels +-1, sums, unpenalised intercept stored last
+    (1, True, 17, 129, 4097),      # widest register layout, ragged last mini-batch
+    (0, False, 5, 64, 5120),       # the largest n the fused kernel takes
+    (0, False, 0, 7, 3),           # fewer rows and variables than CTAs
+])
+def test_fused_runs_on_other_models_and_shapes(kind, model, weights, short_tail, batch, n):
+    kw = dict(model=model, weights=weights, short_tail=short_tail)
+    a = _run(kind, n, batch, 23, 1e-4, loop_max_n=1 << 16, chunk=9, fused=1, **kw)
+    b = _run(kind, n, batch, 23, 1e-4, loop_max_n=0, chunk=9, fused=0, **kw)
+    assert a["fit_steps"] == 23 - (23 // 4 if kind == "SQN" else 0) and b["loop_steps"] == 0
+    for k in ("calls", "n_info", "niter", "section", "mem_used", "mem_st_ix"):
+        assert a[k] == b[k], (k, a[k], b[k])
+    assert np.all(np.isfinite(a["x"]))
+    assert np.max(np.abs(a["x"] - b["x"])) <= 1e-10 * max(np.max(np.abs(b["x"])), 1e-300)
+
+
+def test_fused_run_in_single_precision():
+    a = _run("oLBFGS", 1001, 500, 20, 1e-4, loop_max_n=1 << 16, chunk=20, fused=1, dtype=np.float32)
+    b = _run("oLBFGS", 1001, 500, 20, 1e-4, loop_max_n=0, chunk=20, fused=0, dtype=np.float32)
+    assert a["fit_steps"] == 20
+    for k in ("calls", "n_info", "niter", "mem_used", "mem_st_ix"):
+        assert a[k] == b[k], (k, a[k], b[k])
+    assert np.max(np.abs(a["x"] - b["x"])) <= 1e-4 * np.max(np.abs(b["x"]))

@@ -374,7 +374,8 @@ struct MnPlan {
     int splits;
     long long bpad;                   // leading dimension of DT / XT (samples, padded to 16 bytes)
     long long dpad;                   // leading dimension of the packed coefficient copies (features, padded to 16 bytes)
-    size_t off_zp, off_rp, off_dt, off_xt, off_terms, off_stats, off_bvec, off_wp, off_vp, total;
+    size_t off_zp, off_rp, off_dt, off_xt, off_terms, off_stats, off_bvec, off_wp, off_vp, off_small, off_small_bar, total;
+    bool small_ok;                    // the work buffer holds the partial products of the one-launch small-batch gradient
 };
 
 // Wp[K x ldp] = W[:, :d]  (coefficient block without the intercept column, rows 16-byte aligned: what TMA needs)
@@ -432,6 +433,240 @@ mn_rs_reduce(const T* __restrict__ slots, long long blk, int world, T* __restric
     }
 }
 
+MnPlan mn_plan(long long B, long long d, long long K);
+
+// ---- small batches: the whole gradient in ONE cooperative launch -----------------------------------------------------
+// At the reference's own multinomial sizes (BibTeX: 50 samples x 1836 features x 159 classes, n = 292 083) the five
+// launches above are 91 us of launch gaps around ~10 us of work.  mn_grad_small runs the same three products on one
+// persistent grid (one 512-thread CTA per SM) with two grid barriers:
+//   1  CTA c owns a chunk of <= 16 FEATURES: it loads its columns of X and of W once (they stay in shared memory for
+//      phase 3), forms its partial Z_c = X[:, chunk] W[:, chunk]' (B x K, 4 x 8 register tiles) and stores it   -- barrier
+//   2  CTA b (b < B) owns SAMPLE b: adds the G partial rows in CTA order (+ intercepts), log-sum-exp, and writes the
+//      row D[b][:] = sw_b (softmax(z_b) - y_b)                                                                -- barrier
+//   3  every CTA loads D (B x K) and forms its chunk of the gradient G[:, chunk] = D' X[:, chunk] + alpha W[:, chunk]; the
+//      last CTA adds the intercept column (column sums of D)
+// W and X are read from L2 / HBM exactly once; the only extra traffic is the G partial Z (G x B x K values).
+// Restates scikit-learn (<= 1.0) _multinomial_loss_grad as mn_rows / mn_finish above (stochqn/_logistic.py:7-13).
+constexpr int MS_T = 512;
+constexpr int MS_CW = 16;
+constexpr int MS_MAX_BK = 12288, MS_MAX_B = 128, MS_MAX_K = 512, MS_MAX_GRID = 160;
+
+__device__ __forceinline__ void ms_barrier(unsigned long long* bar)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long old = atomicAdd(bar, 1ull);
+        const unsigned long long gen = old / gridDim.x + 1ull;
+        unsigned long long* flag = bar + 32;
+        if ((old + 1ull) % gridDim.x == 0) {
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(flag), "l"(gen) : "memory");
+        } else {
+            unsigned long long v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+            } while (v < gen);
+        }
+    }
+    __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(MS_T, 1)
+mn_grad_small(const T* __restrict__ X, long long ldx, const T* __restrict__ Y, long long ldy, const int* __restrict__ labels,
+              const T* __restrict__ sw, int B, int d, int K, int icpt, const T* __restrict__ W, T alpha, T* __restrict__ Gout,
+              T* Zp, T* Dg, unsigned long long* bar)
+{
+    extern __shared__ __align__(16) unsigned char ms_smem[];
+    const int G = (int) gridDim.x, c = (int) blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cw = (d + G - 1) / G;
+    const int j0 = c * cw < d ? c * cw : d;
+    const int j1 = j0 + cw < d ? j0 + cw : d;
+    const int w = j1 - j0;
+    const long long ldw = (long long) d + (icpt ? 1 : 0);
+    T* Xc = reinterpret_cast<T*>(ms_smem);                   // [cw][B]   (sample index contiguous)
+    T* Wc = Xc + (size_t) cw * B;                            // [cw][K]   (class index contiguous)
+    T* Ds = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(Wc + (size_t) cw * K) + 15) & ~(uintptr_t) 15);      // [B][K]
+    __shared__ double red_s[MS_T / 32];
+    __shared__ double bc_s[2];
+
+    // ---- phase 1: the chunk of X and W, partial Z ----
+    for (int t = tid; t < B * cw; t += MS_T) {
+        const int b = t / cw, jj = t % cw;
+        Xc[jj * B + b] = jj < w ? __ldg(X + (long long) b * ldx + j0 + jj) : (T) 0;
+    }
+    for (int t = tid; t < K * cw; t += MS_T) {
+        const int k = t / cw, jj = t % cw;
+        Wc[jj * K + k] = jj < w ? __ldg(W + (long long) k * ldw + j0 + jj) : (T) 0;
+    }
+    __syncthreads();
+    {
+        const int BT = (B + 3) / 4, KT = (K + 7) / 8;        // thread tile: b in {bt + BT*ib}, k in {kt + KT*ik}: lanes walk kt -> conflict-free
+        T* zout = Zp + (size_t) c * (size_t) B * K;
+        for (int t = tid; t < BT * KT; t += MS_T) {
+            const int bt = t / KT, kt = t % KT;
+            T acc[4][8];
+            #pragma unroll
+            for (int ib = 0; ib < 4; ++ib)
+                #pragma unroll
+                for (int ik = 0; ik < 8; ++ik) acc[ib][ik] = (T) 0;
+            for (int jj = 0; jj < w; ++jj) {
+                T xa[4], wa[8];
+                #pragma unroll
+                for (int ib = 0; ib < 4; ++ib) { const int b = bt + BT * ib; xa[ib] = b < B ? Xc[jj * B + b] : (T) 0; }
+                #pragma unroll
+                for (int ik = 0; ik < 8; ++ik) { const int k = kt + KT * ik; wa[ik] = k < K ? Wc[jj * K + k] : (T) 0; }
+                #pragma unroll
+                for (int ib = 0; ib < 4; ++ib)
+                    #pragma unroll
+                    for (int ik = 0; ik < 8; ++ik) acc[ib][ik] = fma(xa[ib], wa[ik], acc[ib][ik]);
+            }
+            #pragma unroll
+            for (int ib = 0; ib < 4; ++ib) {
+                const int b = bt + BT * ib;
+                #pragma unroll
+                for (int ik = 0; ik < 8; ++ik) {
+                    const int k = kt + KT * ik;
+                    if (b < B && k < K) zout[(size_t) b * K + k] = acc[ib][ik];
+                }
+            }
+        }
+    }
+    ms_barrier(bar);
+
+    // ---- phase 2: one CTA per sample: sum the partial rows, softmax, D row ----
+    {
+        const int KP = (K + 31) / 32 * 32;
+        const int NQ = MS_T / KP;                            // record slices (K <= 512: at least one)
+        double* zrow = reinterpret_cast<double*>(Ds);         // (Ds is not in use yet) [NQ][KP] partial sums, then the finished row in slice 0
+        for (int b = c; b < B; b += G) {
+            const int k = tid % KP, q = tid / KP;
+            if (q < NQ) {
+                double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                if (k < K) {
+                    const T* pz = Zp + (size_t) b * K + k;
+                    const size_t rs = (size_t) B * K;
+                    int r = q;
+                    for (; r + 3 * NQ < G; r += 4 * NQ) {
+                        const T v0 = __ldcg(pz + (size_t) r * rs), v1 = __ldcg(pz + (size_t) (r + NQ) * rs);
+                        const T v2 = __ldcg(pz + (size_t) (r + 2 * NQ) * rs), v3 = __ldcg(pz + (size_t) (r + 3 * NQ) * rs);
+                        a0 += (double) v0; a1 += (double) v1; a2 += (double) v2; a3 += (double) v3;
+                    }
+                    for (; r < G; r += NQ) a0 += (double) __ldcg(pz + (size_t) r * rs);
+                }
+                zrow[q * KP + k] = (a0 + a1) + (a2 + a3);
+            }
+            __syncthreads();
+            double z = -INFINITY;
+            if (tid < K) {
+                z = icpt ? (double) __ldg(W + (long long) tid * ldw + d) : 0.0;
+                for (int q2 = 0; q2 < NQ; ++q2) z += zrow[q2 * KP + tid];
+            }
+            // CTA max
+            double mx = z;
+            for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if (lane == 0) red_s[warp] = mx;
+            __syncthreads();
+            if (tid == 0) { double v = red_s[0]; for (int q2 = 1; q2 < MS_T / 32; ++q2) v = fmax(v, red_s[q2]); bc_s[0] = v; }
+            __syncthreads();
+            mx = bc_s[0];
+            const double ez = tid < K ? exp(z - mx) : 0.0;
+            double se = ez;
+            for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+            if (lane == 0) red_s[warp] = se;
+            __syncthreads();
+            if (tid == 0) { double v = 0; for (int q2 = 0; q2 < MS_T / 32; ++q2) v += red_s[q2]; bc_s[1] = v; }
+            __syncthreads();
+            if (tid < K) {
+                const double lse = mx + log(bc_s[1]);
+                const double p = exp(z - lse);                                   // as mn_rows: exp(z - lse)
+                const double wt = sw ? (double) sw[b] : 1.0;
+                const double yk = labels ? (labels[b] == tid ? 1.0 : 0.0) : (double) Y[(long long) b * ldy + tid];
+                Dg[(size_t) b * K + tid] = (T) (wt * (p - yk));
+            }
+            __syncthreads();
+        }
+    }
+    ms_barrier(bar);
+
+    // ---- phase 3: G[:, chunk] = D' X[:, chunk] + alpha W[:, chunk]; the intercept column by the last CTA ----
+    for (int t = tid; t < B * K; t += MS_T) Ds[t] = __ldcg(Dg + t);
+    __syncthreads();
+    {
+        const int KP = (K + 31) / 32 * 32;
+        const int NH = MS_T / KP;                            // feature interleave: thread (k, h) owns jj = h, h + NH, ...
+        const int k = tid % KP, h = tid / KP;
+        if (k < K && h < NH) {
+            T acc[MS_CW];
+            #pragma unroll
+            for (int u = 0; u < MS_CW; ++u) acc[u] = (T) 0;
+            for (int b = 0; b < B; ++b) {
+                const T dv = Ds[b * K + k];
+                #pragma unroll
+                for (int u = 0; u < MS_CW; ++u) {
+                    const int jj = h + u * NH;
+                    if (jj < w) acc[u] = fma(dv, Xc[jj * B + b], acc[u]);
+                }
+            }
+            #pragma unroll
+            for (int u = 0; u < MS_CW; ++u) {
+                const int jj = h + u * NH;
+                if (jj < w) Gout[(long long) k * ldw + j0 + jj] = fma(alpha, Wc[jj * K + k], acc[u]);
+            }
+        }
+        if (icpt && c == G - 1 && tid < K) {
+            double sacc = 0.0;
+            for (int b = 0; b < B; ++b) sacc += (double) Ds[b * K + tid];
+            Gout[(long long) tid * ldw + d] = (T) sacc;
+        }
+    }
+}
+
+size_t mn_small_smem(long long B, long long d, long long K, int grid)
+{
+    const long long cw = (d + grid - 1) / grid;
+    size_t ds = sizeof(real_t) * (size_t) (B * K);
+    if (ds < 512 * sizeof(double)) ds = 512 * sizeof(double);          // phase 2 stages its partial sums there
+    return sizeof(real_t) * (size_t) (cw * B + cw * K) + ds + 16;
+}
+
+// 0: launched; 1: not applicable (the caller takes the multi-launch route); < 0: error
+int mn_try_small(const real_t* X, long long ldx, const real_t* Y, long long ldy, const int* labels, const real_t* sw,
+                 long long B, long long d, long long K, int fit_intercept, const real_t* w, real_t alpha, real_t* out,
+                 unsigned char* base, const MnPlan& p, cudaStream_t st)
+{
+    static int enabled = -1, sms = 0, coop = 0;
+    if (enabled < 0) {
+        const char* e = getenv("STOCHQN_B200_MN_SMALL");
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        enabled = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    if (!enabled || !coop || sms < 1 || sms > MS_MAX_GRID || !p.small_ok) return 1;
+    if (B > MS_MAX_B || K > MS_MAX_K || B * K > MS_MAX_BK || (d + sms - 1) / sms > MS_CW) return 1;
+    const size_t smem = mn_small_smem(B, d, K, sms);
+    if (smem > 200 * 1024) return 1;
+    auto kern = mn_grad_small<real_t>;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (200 * 1024)) != cudaSuccess) { cudaGetLastError(); return 1; }
+        smem_set = 200 * 1024;
+    }
+    real_t* Zp = (real_t*) (base + p.off_small);
+    real_t* Dg = (real_t*) (base + p.off_dt);
+    unsigned long long* bar = (unsigned long long*) (base + p.off_small_bar);
+    if (cudaMemsetAsync(bar, 0, 64 * sizeof(unsigned long long), st) != cudaSuccess) return -2;
+    int Bi = (int) B, di = (int) d, Ki = (int) K, ic = fit_intercept ? 1 : 0;
+    void* args[] = {&X, &ldx, &Y, &ldy, &labels, &sw, &Bi, &di, &Ki, &ic, &w, &alpha, &out, &Zp, &Dg, &bar};
+    if (cudaLaunchCooperativeKernel((const void*) kern, dim3((unsigned) sms), dim3(MS_T), args, smem, st) != cudaSuccess) {
+        fprintf(stderr, "stochqn_b200: mn_grad_small launch failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        return -2;
+    }
+    return mn_check("mn_grad_small", 1);
+}
+
 MnPlan mn_plan(long long B, long long d, long long K)
 {
     MnPlan p;
@@ -459,6 +694,18 @@ MnPlan mn_plan(long long B, long long d, long long K)
     p.off_wp = off; off = al(off + sizeof(real_t) * (size_t) (K * p.dpad));      // packed W / V for the tensor-core path
     p.off_vp = off; off = al(off + sizeof(real_t) * (size_t) (K * p.dpad));
 #endif
+    // one-launch small-batch gradient (mn_grad_small): one partial Z per CTA + the barrier words.  Reserved for every
+    // batch size (capped at its largest applicable one), so a buffer sized for a long batch also serves the mini-batches.
+    p.small_ok = K <= MS_MAX_K;
+    p.off_small = off; p.off_small_bar = off;
+    if (p.small_ok) {
+        long long bk = (B < MS_MAX_B ? B : MS_MAX_B) * K;
+        if (bk > MS_MAX_BK) bk = MS_MAX_BK;
+        const size_t dt_need = sizeof(real_t) * (size_t) bk;                 // D is kept where DT lives: K * bpad >= B * K
+        (void) dt_need;
+        off = al(off + sizeof(real_t) * (size_t) (MS_MAX_GRID * bk));
+        p.off_small_bar = off; off = al(off + 64 * sizeof(unsigned long long));
+    }
     p.total = off;
     return p;
 }
@@ -526,6 +773,10 @@ int mn_common(int kind, const real_t* X, long long ldx, const real_t* Y, long lo
         if (int r = mn_check("multinomial pack", packed)) return r;
     }
 #endif
+    if (kind == MN_GRAD && need_out && !loss_dev && !scatter) {          // small batches: the whole gradient in one launch
+        const int r = mn_try_small(X, ldx, Y, ldy, labels, sw, B, d, K, fit_intercept, w, alpha, out, base, p, st);
+        if (r <= 0) return r;
+    }
     // GEMM 1: Z = X W'   (and R = X V')
     if (int r = launch_gemm(X, ldx, w1, ld1, Zp, K, zstride, (int) B, (int) K, (int) d, p.splits, st)) return r;
     if (kind == MN_HVP) { if (int r = launch_gemm(X, ldx, v1, ld1, Rp, K, zstride, (int) B, (int) K, (int) d, p.splits, st)) return r; }

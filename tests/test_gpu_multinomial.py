@@ -72,6 +72,49 @@ def test_multinomial_cuda_cores(dtype, tol, shape, fit_intercept, use_labels, we
     assert abs(loss - lr) <= max(tol, 1e-12) * abs(lr)
 
 
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-11), (np.float32, 3e-5)])
+@pytest.mark.parametrize("shape", [(1, 1, 2), (20, 7, 5), (50, 1836, 159), (128, 96, 96), (64, 2300, 130), (24, 33, 512), (3, 2368, 17)])
+@pytest.mark.parametrize("fit_intercept,use_labels,weighted", [(True, False, False), (False, True, True), (True, True, True)])
+def test_small_batch_gradient_in_one_launch(dtype, tol, shape, fit_intercept, use_labels, weighted):
+    """Gradient-only requests on small batches take mn_grad_small (one cooperative launch, csrc/multinomial.cu): same result as
+    the oracle and as the five-launch route (which the loss + gradient call takes)."""
+    import torch
+    B, d, K = shape
+    abi = _lib.load(dtype)
+    lib = abi.lib
+    rng = np.random.default_rng(5 + B + 3 * d + 7 * K)
+    X = (rng.standard_normal((B, d)) / np.sqrt(d)).astype(dtype)
+    lab = rng.integers(0, K, B).astype(np.int32)
+    Y = np.eye(K)[lab].astype(dtype)
+    w = (rng.standard_normal(K * (d + int(fit_intercept))) * 0.5).astype(dtype)
+    sw = (rng.random(B) + 0.5).astype(dtype) if weighted else None
+    alpha = 1e-2
+    Xd, wd = _t(X, dtype), _t(w, dtype)
+    Yd = None if use_labels else _t(Y, dtype)
+    labd = torch.tensor(lab, device="cuda") if use_labels else None
+    swd = _t(sw, dtype) if weighted else None
+    work = torch.empty(lib.stochqn_b200_multinomial_work_size(B, d, K), device="cuda", dtype=torch.uint8)
+    g1, g5 = torch.zeros_like(wd), torch.zeros_like(wd)
+    loss = torch.zeros(1, device="cuda", dtype=torch.float64)
+    yp = Yd.data_ptr() if Yd is not None else None
+    lp = labd.data_ptr() if labd is not None else None
+    sp = swd.data_ptr() if swd is not None else None
+    n0 = _lib.launch_count()
+    for _ in range(3):                         # (the barrier words are re-armed by every call)
+        assert lib.stochqn_b200_multinomial_loss_grad(Xd.data_ptr(), d, yp, K, lp, sp, B, d, K, int(fit_intercept), wd.data_ptr(), alpha,
+                                                      g1.data_ptr(), None, work.data_ptr(), None) == 0
+    n1 = _lib.launch_count()
+    assert n1 - n0 == 3, "the gradient-only call did not take the one-launch route"
+    assert lib.stochqn_b200_multinomial_loss_grad(Xd.data_ptr(), d, yp, K, lp, sp, B, d, K, int(fit_intercept), wd.data_ptr(), alpha,
+                                                  g5.data_ptr(), loss.data_ptr(), work.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    _, gr, _ = M.multinomial_loss_grad(w.astype(np.float64), X.astype(np.float64), Y.astype(np.float64), alpha,
+                                       None if sw is None else sw.astype(np.float64))
+    scale = max(np.max(np.abs(gr)), 1e-3)
+    assert np.max(np.abs(g1.cpu().numpy().astype(np.float64) - gr)) <= tol * scale
+    assert np.max(np.abs(g1.cpu().numpy().astype(np.float64) - g5.cpu().numpy().astype(np.float64))) <= tol * scale
+
+
 @pytest.mark.parametrize("shape", [(512, 1024, 512), (1000, 1032, 520), (256, 2048, 1030)])
 @pytest.mark.parametrize("fit_intercept", [True, False])
 def test_multinomial_tensor_cores_fp32(shape, fit_intercept):

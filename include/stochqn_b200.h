@@ -69,7 +69,8 @@ enum stochqn_b200_option {
        Not used when the optimizer is sharded. */
     STOCHQN_B200_OPT_ONE_LAUNCH_MAX_N = 5,
     /* stochqn_b200_fit_batch / fit_batches: largest n for which the request loop of a mini-batch runs on the device
-       (csrc/kernels_loop.cuh; default 65536, environment: STOCHQN_B200_LOOP_MAX_N); 0: always the host-driven loop. */
+       (csrc/kernels_loop.cuh; default 65536 for oLBFGS / SQN and 524288 for adaQN, whose ordinary steps then are ONE launch -
+       kl_ada - for mem_size <= 20; environment: STOCHQN_B200_LOOP_MAX_N); 0: always the host-driven loop. */
     STOCHQN_B200_OPT_DEVICE_LOOP_MAX_N = 6,
     /* stochqn_b200_fit_batch / fit_batches, two-class models (0, 1), oLBFGS and the ordinary steps of SQN, n <= 5120:
        1 (default; environment STOCHQN_B200_FUSED_FIT): a whole RUN of consecutive mini-batches is ONE cooperative launch

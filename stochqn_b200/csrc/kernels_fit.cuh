@@ -54,32 +54,6 @@ struct FitArgs {
     unsigned long long* trace;  // development aid: CTA 0 stamps %globaltimer at the phase boundaries of every mini-batch (16 slots each), or nullptr
 };
 
-// Grid barrier (cooperative launch: all CTAs resident).  bar[0] counts arrivals and only ever grows; it is a multiple of
-// gridDim.x whenever no barrier is in progress (every launch that uses it has the same grid), so the generation a CTA
-// waits for follows from its ticket and the host need not know how many barriers a launch executes (rejections and the
-// exact-norm route change it).  The CTA that arrives last publishes the generation in bar[32] - another 128-byte line,
-// so the waiters' polling does not queue up behind the arrivals at the same L2 atomic unit.
-constexpr int kFitBarWords = 64;
-__device__ __forceinline__ void fit_barrier(unsigned long long* bar)
-{
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned long long old = atomicAdd(bar, 1ull);
-        const unsigned long long gen = old / gridDim.x + 1ull;
-        unsigned long long* flag = bar + 32;
-        if ((old + 1ull) % gridDim.x == 0) {
-            asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(flag), "l"(gen) : "memory");
-        } else {
-            unsigned long long v;
-            do {
-                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
-            } while (v < gen);
-        }
-    }
-    __syncthreads();
-}
-
 template <typename T, int MODE, int CPT, int R>
 __global__ void __launch_bounds__(kFitThreads, 1)
 kl_fit_logistic(const FitArgs<T> F, const LoopArgs A, LoopState* __restrict__ st, T* x, T* x_sum, T* S, T* Y, const T step,

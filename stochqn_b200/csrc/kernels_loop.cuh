@@ -14,9 +14,9 @@
 //             on rejection, ring advance on acceptance; a no-op when the step before it was rejected (the reference
 //             then asks for a gradient on a NEW batch instead, stochqn.c:1010-1020)
 //   kl_ada    adaQN take_step (stochqn.c:802-840 with 720-783) in ONE launch: accumulator update, Fisher ring write,
-//             the two reduction phases of the compact form with a diagonal H0 (kernels_adaqn.cuh), update
+//             the two reduction phases of the compact form with a diagonal H0 (kernels_adaqn.cuh), update (512-thread CTAs)
 //
-// All three are cooperative grids of 256-thread CTAs (or one 1024-thread CTA for n <= 2048) in which every CTA owns a
+// kl_step / kl_pair are cooperative grids of 256-thread CTAs (or one 1024-thread CTA for n <= 2048) in which every CTA owns a
 // contiguous slice of the elements; partial records are summed by every CTA in the same fixed order, and every CTA
 // solves the m x m system redundantly in its own shared memory, so no broadcast is needed after a grid barrier.
 // Arithmetic of the update is that of K3 / KA3 (same FMA order), so the iterates agree with the host-driven routes to
@@ -261,6 +261,351 @@ kl_pair(LoopArgs A, LoopState* __restrict__ st, const T* __restrict__ g, const T
             st->st_ix = (slot + 1) % m;                 // incr_bfgs_counters (stochqn.c:569-573)
             st->used = used + 1 >= m ? m : used + 1;
             st->pend = slot;
+        }
+    }
+}
+
+// Grid barrier (cooperative launch: all CTAs resident).  bar[0] counts arrivals and only ever grows; it is a multiple of
+// gridDim.x whenever no barrier is in progress (every launch that uses it has the same grid), so the generation a CTA
+// waits for follows from its ticket and the host need not know how many barriers a launch executes (rejections and the
+// exact-norm route change it).  The CTA that arrives last publishes the generation in bar[32] - another 128-byte line,
+// so the waiters' polling does not queue up behind the arrivals at the same L2 atomic unit.
+constexpr int kFitBarWords = 64;
+__device__ __forceinline__ void fit_barrier(unsigned long long* bar)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long old = atomicAdd(bar, 1ull);
+        const unsigned long long gen = old / gridDim.x + 1ull;
+        unsigned long long* flag = bar + 32;
+        if ((old + 1ull) % gridDim.x == 0) {
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(flag), "l"(gen) : "memory");
+        } else {
+            unsigned long long v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+            } while (v < gen);
+        }
+    }
+    __syncthreads();
+}
+
+// =========================================================================================
+// kl_ada: the adaQN take_step (stochqn.c:802-840 with 720-783; kernels_adaqn.cuh for the compact form with the
+// diagonal H0 = diag(h)) in ONE cooperative launch, decisions on the device.  KA1 -> KAu -> KA2 -> KAa -> KA3 become
+// three sweeps of a CTA's own contiguous slice of the elements separated by two grid barriers; every CTA sums the
+// partial records in the same order and performs both small solves redundantly in its own shared memory.
+//   A  G <- accumulate(g), Fisher ring row <- g, p = S'g, pending Gram column, sum h^2          -- barrier
+//   B  u = R^-1 p ;  w = Y'[h.(Yu - g)], sum (h.(Yu-g))^2                                       -- barrier
+//   C  a = R^-T (D u + w), bound on ||d||, accept / reject (exact-norm route: + one barrier);
+//      d = h.(g + Y b) + S a ;  x -= step*d ;  x_sum += x       (rejected: x_sum += x, flush; quirk Q7)
+// Element arithmetic is that of ka1_dots / ka2_wdots / ka3_combine (same FMA order).
+// =========================================================================================
+constexpr int kAdaThreads = 512;
+
+struct AdaLoopArgs {
+    int msize, check_nan, fisher_size, pad;
+    long long n;
+    size_t ld;
+    double limit;                                // 1e3 * n
+    double scal_reg, rmsprop_weight;
+};
+
+struct AdaShared {
+    double Rm[kMaxMem][kMaxMem + 1];
+    double pv[kMaxMem], u[kMaxMem], w[kMaxMem], ssv[kMaxMem];
+    int status;
+};
+
+// sum entry-major records: entry p of CTA b is rec[p * G + b]; one warp per entry (three at a time), lanes over CTAs
+__device__ __forceinline__ void reduce_entry_major(const double* __restrict__ rec, int P, int G, double* __restrict__ sums, int nwarps)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int p0 = 0; p0 < P; p0 += 3 * nwarps) {
+        double acc[3] = {0.0, 0.0, 0.0};
+        #pragma unroll 5
+        for (int r = lane; r < G; r += 32) {
+            #pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int p = p0 + warp + q * nwarps;
+                if (p < P) acc[q] += __ldcg(rec + (size_t) p * G + r);
+            }
+        }
+        #pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int p = p0 + warp + q * nwarps;
+            if (p < P) {
+                const double v = warp_sum(acc[q]);
+                if (lane == 0) sums[p] = v;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+template <typename T, int MMAX>
+__global__ void __launch_bounds__(kAdaThreads, 1)
+kl_ada(const AdaLoopArgs A, LoopState* __restrict__ st, const T* g, T* gout, T* __restrict__ Gacc,
+       const T* __restrict__ S, const T* __restrict__ Y, T* __restrict__ F, T* __restrict__ x, T* __restrict__ x_sum, const T step,
+       double* partials, double* rec2, double* SY, double* YY, double* SS, unsigned long long* bar)
+{
+    const int m = A.msize;
+    const int used = st->used, slot = st->st_ix, c = st->pend;
+    const int f_used = st->fisher_used, f_st = st->fisher_st;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = (int) gridDim.x, b = (int) blockIdx.x;
+    constexpr int NW = kAdaThreads / 32;
+    const long long per = (A.n + G - 1) / G;
+    const long long e0 = (long long) b * per < A.n ? (long long) b * per : A.n;
+    const long long e1 = e0 + per < A.n ? e0 + per : A.n;
+    const T scal_reg = (T) A.scal_reg, rmsw = (T) A.rmsprop_weight;
+    const bool rms = (rmsw > (T) 0 && rmsw < (T) 1);
+    const T w_new = (T) 1 - rmsw;
+    const int oldest = (slot == used) ? 0 : slot;
+    auto ph = [&](int i) { int s2 = oldest + i; return s2 >= m ? s2 - m : s2; };
+    T* frow = A.fisher_size > 0 ? F + (size_t) f_st * A.ld : nullptr;
+    const T* yc = c >= 0 ? Y + (size_t) c * A.ld : nullptr;
+    const T* sc = c >= 0 ? S + (size_t) c * A.ld : nullptr;
+
+    __shared__ double sums1[2 * kMaxMem + 4], sums2[kMaxMem + 1], coef_s[2 * kMaxMem + 3], two_s[2];
+    __shared__ double red[NW][2 * MMAX + 4];
+    __shared__ AdaShared sh;
+    const int P1 = 2 * m + 4, P2 = m + 1;
+
+    // ---- A: accumulator, Fisher row, p, pending column ----
+    {
+        double a_p[MMAX], a_c[MMAX], a_hh = 0, a_ss = 0, a_yy = 0;
+        #pragma unroll
+        for (int r = 0; r < MMAX; ++r) { a_p[r] = 0; a_c[r] = 0; }
+        for (long long i = e0 + tid; i < e1; i += kAdaThreads) {
+            T rv[MMAX];
+            const T gv = g[i];
+            T Gv = Gacc[i];
+            #pragma unroll
+            for (int r = 0; r < MMAX; ++r) rv[r] = r < used ? S[(size_t) r * A.ld + i] : (T) 0;
+            T ycv = (T) 0, scv = (T) 0;
+            if (c >= 0) { ycv = yc[i]; scv = sc[i]; }
+            Gv = ada_accumulate<T>(gv, Gv, rmsw, w_new, rms);
+            Gacc[i] = Gv;
+            if (frow) frow[i] = gv;
+            const T h = gv / sqrt(Gv + scal_reg);
+            a_hh = fma((double) h, (double) h, a_hh);
+            if (c >= 0) { a_ss = fma((double) scv, (double) scv, a_ss); a_yy = fma((double) ycv, (double) ycv, a_yy); }
+            #pragma unroll
+            for (int r = 0; r < MMAX; ++r) {
+                if (r < used) {
+                    a_p[r] = fma((double) rv[r], (double) gv, a_p[r]);
+                    if (c >= 0) a_c[r] = fma((double) rv[r], (double) ycv, a_c[r]);
+                }
+            }
+        }
+        #pragma unroll
+        for (int q = 0; q < 2 * MMAX + 3; ++q) {
+            double v = q < MMAX ? a_p[q < MMAX ? q : 0] : q < 2 * MMAX ? a_c[(q - MMAX) < MMAX ? (q - MMAX) : 0]
+                     : q == 2 * MMAX ? a_hh : q == 2 * MMAX + 1 ? a_ss : a_yy;
+            const bool need = q < MMAX ? q < used : q < 2 * MMAX ? (c >= 0 && q - MMAX < used) : true;
+            if (need) {                                      // block-uniform
+                v = warp_sum(v);
+                if (lane == 0) red[warp][q] = v;
+            }
+        }
+        __syncthreads();
+        for (int p = tid; p < P1; p += kAdaThreads) {        // record layout of ka1_dots: [0,m) p, [m,2m) s_j'y_c, 2m: sum h^2, 2m+1: s_c's_c, 2m+2: y_c'y_c
+            const int q = p < m ? p : p < 2 * m ? MMAX + (p - m) : 2 * MMAX + (p - 2 * m);
+            const bool have = p < m ? p < used : p < 2 * m ? (c >= 0 && p - m < used) : p < 2 * m + 3;
+            double v = 0;
+            if (have) { for (int w2 = 0; w2 < NW; ++w2) v += red[w2][q]; }
+            partials[(size_t) p * G + b] = v;
+        }
+    }
+    fit_barrier(bar);
+
+    // ---- B: u, then w = Y'[h.(Yu - g)] ----
+    reduce_entry_major(partials, P1, G, sums1, NW);
+    if (b == 0 && c >= 0) {                                  // fold the pending pair's Gram column into the global state
+        for (int j = tid; j < used; j += kAdaThreads) SY[j * m + c] = sums1[m + j];
+        if (tid == 0) { SS[c] = sums1[2 * m + 1]; YY[c * m + c] = sums1[2 * m + 2]; }
+    }
+    for (int t = tid; t < used * used; t += kAdaThreads) {
+        const int i = t / used, j = t % used;
+        const int pi = ph(i), pj = ph(j);
+        sh.Rm[i][j] = (pj == c) ? sums1[m + pi] : __ldcg(SY + pi * m + pj);
+    }
+    for (int i = tid; i < used; i += kAdaThreads) {
+        const int pi = ph(i);
+        sh.pv[i] = sums1[pi];
+        sh.ssv[i] = (pi == c) ? sums1[2 * m + 1] : __ldcg(SS + pi);
+    }
+    for (int j = tid; j < 2 * m + 3; j += kAdaThreads) coef_s[j] = 0.0;
+    __syncthreads();
+    if (tid < 32) {                                          // u = R^-1 p, lane i owns row i (ada_stage_and_solve_u)
+        const bool live = tid < used;
+        const double inv = 1.0 / (live ? sh.Rm[tid][tid] : 1.0);
+        double t = live ? sh.pv[tid] : 0.0;
+        for (int j = used - 1; j >= 0; --j) {
+            const double uj = __shfl_sync(0xffffffffu, t * inv, j);
+            if (tid == j) sh.u[tid] = uj;
+            if (tid < j) t = fma(-sh.Rm[tid][j], uj, t);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < used; i += kAdaThreads) coef_s[m + ph(i)] = -sh.u[i];
+    __syncthreads();
+
+    int status = ST_ACCEPT;
+    if (used == 0) {                                         // d = h: its norm is exact (stochqn.c:808-812, 825-835)
+        const double hh = sums1[2 * m];
+        if (A.check_nan && (!isfinite(hh) || !(sqrt(hh) <= A.limit))) status = ST_REJECT_NONFINITE;
+    } else {
+        T cu[MMAX];
+        #pragma unroll
+        for (int j = 0; j < MMAX; ++j) cu[j] = (j < used) ? (T) (-coef_s[m + j]) : (T) 0;
+        double acc[MMAX], a_tt = 0;
+        #pragma unroll
+        for (int j = 0; j < MMAX; ++j) acc[j] = 0;
+        for (long long i = e0 + tid; i < e1; i += kAdaThreads) {
+            T yv[MMAX];
+            const T gv = g[i], Gv = Gacc[i];
+            #pragma unroll
+            for (int j = 0; j < MMAX; ++j) yv[j] = j < used ? Y[(size_t) j * A.ld + i] : (T) 0;
+            T t = -gv;
+            #pragma unroll
+            for (int j = 0; j < MMAX; ++j) if (j < used) t = fma(cu[j], yv[j], t);
+            const T h = gv / sqrt(Gv + scal_reg);
+            const double ht = (double) (h * t);
+            a_tt = fma(ht, ht, a_tt);
+            #pragma unroll
+            for (int j = 0; j < MMAX; ++j) if (j < used) acc[j] = fma((double) yv[j], ht, acc[j]);
+        }
+        #pragma unroll
+        for (int q = 0; q <= MMAX; ++q) {
+            if (q < used || q == MMAX) {
+                double v = q < MMAX ? acc[q < MMAX ? q : 0] : a_tt;
+                v = warp_sum(v);
+                if (lane == 0) red[warp][q] = v;
+            }
+        }
+        __syncthreads();
+        for (int p = tid; p < P2; p += kAdaThreads) {        // record of ka2_wdots: [0,m) w, [m] sum (h.(Yu-g))^2
+            const int q = p < m ? p : MMAX;
+            double v = 0;
+            if (p == m || p < used) { for (int w2 = 0; w2 < NW; ++w2) v += red[w2][q]; }
+            rec2[(size_t) p * G + b] = v;
+        }
+        fit_barrier(bar);
+
+        // ---- C: a = R^-T (D u + w), bound, decision ----
+        reduce_entry_major(rec2, P2, G, sums2, NW);
+        for (int i = tid; i < used; i += kAdaThreads) sh.w[i] = sh.Rm[i][i] * sh.u[i] + sums2[ph(i)];
+        __syncthreads();
+        if (tid < 32) {
+            const unsigned full = 0xffffffffu;
+            const bool live = tid < used;
+            const double tt = sums2[m];
+            double U = sqrt(tt);
+            bool ok = isfinite(tt);
+            const double inv = 1.0 / (live ? sh.Rm[tid][tid] : 1.0);
+            double t = live ? sh.w[tid] : 0.0, ai = 0.0;
+            for (int j = 0; j < used; ++j) {
+                const double aj = __shfl_sync(full, t * inv, j);
+                if (tid == j) ai = aj;
+                if (live && tid > j) t = fma(-sh.Rm[j][tid], aj, t);
+            }
+            double term = 0.0;
+            bool fin = true;
+            if (live) {
+                coef_s[ph(tid)] = ai;
+                term = fabs(ai) * sqrt(sh.ssv[tid]);
+                fin = isfinite(ai) && isfinite(sh.u[tid]);
+            }
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(full, term, o);
+            U += term;
+            ok = ok && __all_sync(full, fin) && isfinite(U);
+            if (tid == 0) {
+                int s2 = ST_ACCEPT;
+                if (A.check_nan) {
+                    if (!ok) s2 = ST_REJECT_NONFINITE;
+                    else if (!(U <= 0.99 * A.limit)) s2 = ST_NEED_EXACT_NORM;
+                }
+                sh.status = s2;
+            }
+        }
+        __syncthreads();
+        status = sh.status;
+    }
+
+    // d on the slice (ka3_combine): part0 = sum_r a_r s_r ; part1 = h.(g + sum_r b_r y_r)
+    T cfS[MMAX], cfY[MMAX];
+    #pragma unroll
+    for (int r = 0; r < MMAX; ++r) { cfS[r] = r < used ? (T) coef_s[r] : (T) 0; cfY[r] = r < used ? (T) coef_s[m + r] : (T) 0; }
+    auto direction = [&](long long i) -> T {
+        T sv[MMAX], yv[MMAX];
+        const T gv = g[i], Gv = Gacc[i];
+        #pragma unroll
+        for (int r = 0; r < MMAX; ++r) { sv[r] = r < used ? S[(size_t) r * A.ld + i] : (T) 0; yv[r] = r < used ? Y[(size_t) r * A.ld + i] : (T) 0; }
+        T p0 = (T) 0, p1 = gv;
+        #pragma unroll
+        for (int r = 0; r < MMAX; ++r) {
+            if (r < used) { p0 = fma(cfS[r], sv[r], p0); p1 = fma(cfY[r], yv[r], p1); }
+        }
+        const T h = gv / sqrt(Gv + scal_reg);
+        p1 = used > 0 ? h * p1 : h;
+        return p1 + p0;
+    };
+
+    bool d_in_g = false;
+    if (status == ST_NEED_EXACT_NORM) {                      // measure ||d|| exactly before touching x (stochqn.c:825-838)
+        double a_dd = 0, a_bad = 0;
+        T* gw = const_cast<T*>(g);
+        for (long long i = e0 + tid; i < e1; i += kAdaThreads) {
+            const T d = direction(i);
+            const double de = (double) d;
+            a_dd = fma(de, de, a_dd);
+            if (!isfinite(de)) a_bad += 1.0;
+            gw[i] = d;
+        }
+        a_dd = warp_sum(a_dd); a_bad = warp_sum(a_bad);
+        __syncthreads();
+        if (lane == 0) { red[warp][0] = a_dd; red[warp][1] = a_bad; }
+        __syncthreads();
+        if (tid < 2) { double v = 0; for (int w2 = 0; w2 < NW; ++w2) v += red[w2][tid]; partials[(size_t) tid * G + b] = v; }
+        fit_barrier(bar);
+        reduce_entry_major(partials, 2, G, two_s, NW);
+        status = (two_s[1] > 0 || !(sqrt(two_s[0]) <= A.limit)) ? ST_REJECT_NONFINITE : ST_ACCEPT;
+        d_in_g = true;
+    }
+
+    const T nstep = -step;
+    if (status == ST_ACCEPT) {
+        for (long long i = e0 + tid; i < e1; i += kAdaThreads) {
+            const T d = d_in_g ? g[i] : direction(i);
+            const T xv = fma(nstep, d, x[i]);
+            x[i] = xv;
+            x_sum[i] = x_sum[i] + xv;
+            if (gout) gout[i] = d;
+        }
+    } else {
+        for (long long i = e0 + tid; i < e1; i += kAdaThreads) x_sum[i] = x_sum[i] + x[i];      // quirk Q7 (stochqn.c:1191)
+    }
+
+    if (b == 0 && tid == 0) {
+        st->last_status = status;
+        st->calls += 1;
+        if (A.fisher_size > 0) {                             // add_to_fisher_mem (stochqn.c:581-587)
+            st->fisher_st = (f_st + 1) % A.fisher_size;
+            st->fisher_used = f_used + 1 >= A.fisher_size ? A.fisher_size : f_used + 1;
+        }
+        if (status == ST_ACCEPT) {
+            st->pend = -1;
+            st->n_info[0] += 1;
+            st->x_changed += 1;
+            st->last_info = 200;
+        } else {
+            st->used = 0; st->st_ix = 0; st->pend = -1;
+            st->n_info[3] += 1;
+            st->last_info = 203;
         }
     }
 }

@@ -192,6 +192,7 @@ struct Ctx {
     // fused runs of mini-batches (kernels_fit.cuh)
     int fused_fit = 1;                  // 0: never (option FUSED_FIT)
     unsigned long long* fit_bar = nullptr;    // its grid-barrier counter
+    unsigned long long* ada_bar = nullptr;    // grid-barrier words of kl_ada (its grid depends on n)
     void* fit_work = nullptr;           // the model's scratch buffer (partial column records)
     double fit_steps = 0;               // mini-batches served by it
     unsigned long long* fit_trace = nullptr;   // development aid (stochqn_b200_debug_fit_trace)
@@ -656,7 +657,7 @@ void free_ctx(Ctx* c)
     for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_out) cudaEventDestroy(e);
     if (c->ev_x) cudaEventDestroy(c->ev_x);
-    cudaFree(c->loop_dev); cudaFree(c->loop_bar); cudaFree(c->rec2); cudaFree(c->fit_bar);
+    cudaFree(c->loop_dev); cudaFree(c->loop_bar); cudaFree(c->rec2); cudaFree(c->fit_bar); cudaFree(c->ada_bar);
     if (c->loop_host) cudaFreeHost(c->loop_host);
     if (c->copy_in) cudaStreamDestroy(c->copy_in);
     if (c->copy_out) cudaStreamDestroy(c->copy_out);
@@ -707,7 +708,7 @@ Ctx* make_ctx(Kind kind, long long n, int msize, int fisher_size)
         if (e1) c->one_cta_n = atoll(e1);
         if (!coop && c->small_n > c->one_cta_n) c->small_n = c->one_cta_n;       // the multi-CTA form needs a cooperative launch
         const char* e2 = getenv("STOCHQN_B200_LOOP_MAX_N");
-        c->loop_max_n = e2 ? atoll(e2) : (1ll << 16);
+        c->loop_max_n = e2 ? atoll(e2) : (kind == K_ADAQN ? (1ll << 19) : (1ll << 16));     // adaQN: its one-launch step (kl_ada) pays up to L2-sized states
         if (!coop && c->loop_max_n > kOneCtaN) c->loop_max_n = kOneCtaN;
         const char* e3 = getenv("STOCHQN_B200_FUSED_FIT");
         c->fused_fit = (coop && !(e3 && atoi(e3) == 0)) ? 1 : 0;

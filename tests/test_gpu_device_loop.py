@@ -47,8 +47,12 @@ def _run(kind, n, batch, nbatches, min_curv, loop_max_n, chunk, step=0.1, L=4, m
     work = torch.empty(lib.stochqn_b200_logistic_work_size(max(batch, big), n), device="cuda", dtype=torch.uint8)
     if kind == "oLBFGS":
         ws = lib.initialize_oLBFGS(n, mem, 0.0, 0.0, min_curv, 1, 1)
-    else:
+    elif kind == "SQN":
         ws = lib.initialize_SQN(n, mem, L, min_curv, 0, 0.0, 1, 1)
+    else:       # adaQN_fisher: AdaGrad + empirical Fisher pairs; adaQN_gd: RMSProp + gradient differences; adaQN_incr: Fisher + max_incr
+        fisher = 0 if kind == "adaQN_gd" else 7
+        ws = lib.initialize_adaQN(n, mem, max(fisher, 1) if fisher else 1, L, 1.01 if kind == "adaQN_incr" else 0.0, min_curv, 1e-4,
+                                  0.9 if kind == "adaQN_gd" else 0.0, 1 if kind == "adaQN_gd" else 0, 0.0, 1, 1)
     assert ws
     assert lib.stochqn_b200_set_option(ws, _lib.OPT_DEVICE_LOOP_MAX_N, loop_max_n) == 0
     assert lib.stochqn_b200_set_option(ws, _lib.OPT_FUSED_FIT, fused) == 0
@@ -56,8 +60,10 @@ def _run(kind, n, batch, nbatches, min_curv, loop_max_n, chunk, step=0.1, L=4, m
     g0 = torch.zeros(n, device="cuda", dtype=tdt)
     if kind == "oLBFGS":
         lib.run_oLBFGS(step, x.data_ptr(), g0.data_ptr(), C.byref(req), C.byref(task), ws, C.byref(info))
-    else:
+    elif kind == "SQN":
         lib.run_SQN(step, x.data_ptr(), g0.data_ptr(), g0.data_ptr(), C.byref(req), C.byref(req_vec), C.byref(task), ws, C.byref(info))
+    else:
+        lib.run_adaQN(step, x.data_ptr(), 0.0, g0.data_ptr(), C.byref(req), C.byref(task), ws, C.byref(info))
     assert task.value == 101
     M = abi.Model(model, 1 if model == 1 else 0, ncols, 0, 1e-5 if model == 0 else 1e-2, work.data_ptr())
     data = _lib.Rows(X.data_ptr(), ncols, y.data_ptr(), 1, sw.data_ptr() if sw is not None else None, nrows)
@@ -83,10 +89,13 @@ def _run(kind, n, batch, nbatches, min_curv, loop_max_n, chunk, step=0.1, L=4, m
         b += cnt
     w = ws.contents
     m = w.bfgs_memory.contents
-    out = dict(tally, niter=int(w.niter), section=int(w.section), mem_used=int(m.mem_used), mem_st_ix=int(m.mem_st_ix),
+    fisher = (0, 0)
+    if kind.startswith("adaQN") and w.fisher_memory:
+        fisher = (int(w.fisher_memory.contents.mem_used), int(w.fisher_memory.contents.mem_st_ix))
+    out = dict(tally, niter=int(w.niter), section=int(w.section), mem_used=int(m.mem_used), mem_st_ix=int(m.mem_st_ix), fisher=fisher,
                loop_steps=_lib.get_stat(abi, ws, _lib.STAT_DEVICE_LOOP_STEPS), fit_steps=_lib.get_stat(abi, ws, _lib.STAT_FUSED_FIT_STEPS),
                x=x.double().cpu().numpy())
-    {"oLBFGS": lib.dealloc_oLBFGS, "SQN": lib.dealloc_SQN}[kind](ws)
+    {"oLBFGS": lib.dealloc_oLBFGS, "SQN": lib.dealloc_SQN}.get(kind, lib.dealloc_adaQN)(ws)
     return out
 
 
@@ -144,3 +153,22 @@ def test_fused_run_in_single_precision():
     for k in ("calls", "n_info", "niter", "mem_used", "mem_st_ix"):
         assert a[k] == b[k], (k, a[k], b[k])
     assert np.max(np.abs(a["x"] - b["x"])) <= 1e-4 * np.max(np.abs(b["x"]))
+
+
+@pytest.mark.parametrize("kind", ["adaQN_fisher", "adaQN_gd", "adaQN_incr"])
+@pytest.mark.parametrize("n,batch,nbatches,mem", [(37, 64, 45, 5), (1001, 64, 45, 5), (5000, 32, 45, 12), (30011, 16, 26, 14)])
+@pytest.mark.parametrize("factor", [0.0, 3.0])
+def test_adaqn_one_launch_steps_match_the_host_driven_loop(kind, n, batch, nbatches, mem, factor):
+    """The ordinary steps of adaQN as ONE launch each (kl_ada, csrc/kernels_loop.cuh: stochqn.c:802-840 with 720-783) inside
+    stochqn_b200_fit_batches, against the five-launch host-driven route: same tallies, ring and Fisher counters, iterate.
+    factor 3: a curvature threshold that rejects every pair (Fisher pairs have curvature ~ |g's|^2/|s|^2, grad-diff pairs
+    as in the oLBFGS test above)."""
+    min_curv = 1e-4 if factor == 0 else factor * 0.2 * max(1.0, n / float(batch))
+    step = 0.05
+    a = _run(kind, n, batch, nbatches, min_curv, loop_max_n=1 << 19, chunk=7, step=step, mem=mem)
+    b = _run(kind, n, batch, nbatches, min_curv, loop_max_n=0, chunk=7, step=step, mem=mem)
+    assert a["loop_steps"] > 0 and b["loop_steps"] == 0
+    for k in ("calls", "n_info", "niter", "section", "mem_used", "mem_st_ix", "fisher"):
+        assert a[k] == b[k], (k, a[k], b[k])
+    assert np.all(np.isfinite(a["x"]))
+    assert np.max(np.abs(a["x"] - b["x"])) <= 1e-10 * max(np.max(np.abs(b["x"])), 1e-300)

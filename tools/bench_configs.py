@@ -174,7 +174,7 @@ def run_logistic(name, kind, nrows, d, batch, steps, L=10, big=20000, native=Fal
 
 
 def run_multinomial(name, dtype, d, K, batch, nrows, steps, L, fisher, use_grad_diff, max_incr, rms, step, quiet=False, cpu_fn=None,
-                    profile=None, fixed_big=False):
+                    profile=None, fixed_big=False, native=False):
     """profile "bibtex": the shape AND the set-up of the reference's notebook (example/example_stochqn.ipynb: BibTeX, 1836 binary
     bag-of-words features at 3.75 % density, 159 classes): weights of one per sample (summed loss), reg_param 0.1, start point
     ~ N(0,1) - with these the correction-pair memory fills and stays full (checked with the reference library on the CPU:
@@ -249,8 +249,40 @@ def run_multinomial(name, dtype, d, K, batch, nrows, steps, L, fisher, use_grad_
     call()
     niter = lambda: int(ws.contents.niter)
     warm = 12 * L                 # mem_size + 2 correction pairs: the timed steps run with the memory full
-    while niter() < warm:
+
+    def serve_call():
         serve(); call()
+    if native:
+        # the request loop inside the library (stochqn_b200_fit_batches): `chunk` consecutive mini-batches per call; the ordinary
+        # steps are two launches each (mn_grad_small + kl_ada) with no host wait, the pair iterations take the host-driven loop
+        assert profile == "bibtex" and not fixed_big, "one weight array must serve every batch size"
+        chunk = 50
+        Yoh = torch.zeros(nrows, K, device="cuda", dtype=tdt)
+        Yoh[torch.arange(nrows, device="cuda"), lab.long()] = 1.0
+        swall = torch.ones(nrows, device="cuda", dtype=tdt)
+        M = abi.Model(2, 1, d, K, alpha, work.data_ptr())
+        data = _lib.Rows(X.data_ptr(), d, Yoh.data_ptr(), K, swall.data_ptr(), nrows)
+        val = _lib.Rows(X.data_ptr(), d, Yoh.data_ptr(), K, swall.data_ptr(), nval)
+        rep = _lib.FitReport()
+        LL = C.c_longlong * chunk
+        lf, lr = LL(), LL()
+        req_vec = C.c_void_p()
+
+        def serve_call():
+            b0 = (state["b"] + 1) % nb
+            cnt_b = min(chunk, nb - b0)
+            for i in range(cnt_b):
+                e = (b0 + i + 1) * batch
+                lr[i] = min(big, e)
+                lf[i] = e - lr[i]
+            rc = lib.stochqn_b200_fit_batches(ws, x.data_ptr(), step, C.byref(M), C.byref(data), b0 * batch, batch, cnt_b, lf, lr, C.byref(val),
+                                              C.byref(task), C.byref(req), C.byref(req_vec), C.byref(rep))
+            assert rc == 0, (rc, _lib.last_error(abi))
+            state["b"] = b0 + cnt_b - 1
+            for i in range(4):
+                infos[200 + i] = infos.get(200 + i, 0) + rep.n_info[i]
+    while niter() < warm:
+        serve_call()
     torch.cuda.synchronize()
     tasks.clear(); infos.clear()
     launches0 = _lib.launch_count()
@@ -258,13 +290,15 @@ def run_multinomial(name, dtype, d, K, batch, nrows, steps, L, fisher, use_grad_
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     while niter() < it0 + steps:
-        serve(); call()
+        serve_call()
     e1.record()
     torch.cuda.synchronize()
+    steps = niter() - it0
     ms = e0.elapsed_time(e1) / steps
     req.value = x.data_ptr()
     grad_on(0, nval, want_loss=True)
-    out = dict(config=name, optimizer="adaQN", dtype="f64" if esz == 8 else "f32", n=n, features=d, classes=K, batch=batch, steps=steps,
+    out = dict(config=name, optimizer="adaQN", loop="device (stochqn_b200_fit_batches)" if native else "python (one call per request)",
+               device_loop_steps=_lib.get_stat(abi, ws, _lib.STAT_DEVICE_LOOP_STEPS), dtype="f64" if esz == 8 else "f32", n=n, features=d, classes=K, batch=batch, steps=steps,
                ms_per_step=ms, steps_per_s=1e3 / ms, tasks=tasks, infos=infos, mem_used=int(ws.contents.bfgs_memory.contents.mem_used),
                launches_per_step=(_lib.launch_count() - launches0) / steps, loss_after=float(loss.item()), loss_at_zero=float(np.log(K)))
     lib.dealloc_adaQN(ws)
@@ -471,6 +505,8 @@ def main():
         run_logistic("cfg2", "SQN", a.rows_cfg2, 4096, 2000, a.steps, L=10, big=20000, native=True, step=1e-2)
     if "cfg3" in a.configs:
         run_multinomial("cfg3", np.float64, 1836, 159, 50, 6655, a.steps, 20, 100, 0, 1.01, 0.0, 1e-2, profile="bibtex")
+    if "cfg3d" in a.configs:
+        run_multinomial("cfg3", np.float64, 1836, 159, 50, 6655, a.steps, 20, 100, 0, 1.01, 0.0, 1e-2, profile="bibtex", native=True)
     if "cfg5" in a.configs:
         run_multinomial("cfg5", np.float32, 8192, 4096, 1024, 16384, min(a.steps, 100), 10, 0, 1, 0.0, 0.9, 1e-3, fixed_big=True)
 

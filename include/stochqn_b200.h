@@ -84,6 +84,9 @@ long long stochqn_b200_get_option(void *ws, int option);
 /* development aid (tools/probe_fit.py): a device buffer of 16 * nbatches 64-bit slots in which CTA 0 of the fused fit kernel
    (STOCHQN_B200_OPT_FUSED_FIT) leaves %globaltimer stamps at the phase boundaries of every mini-batch; NULL turns it off */
 int stochqn_b200_debug_fit_trace(void *ws, unsigned long long *dev_buf);
+/* the same for the one-launch small-batch multinomial gradient (8 slots, process-wide) and - through stochqn_b200_debug_fit_trace -
+   for the one-launch adaQN step (16 slots per call, overwritten by every call) */
+int stochqn_b200_debug_mn_trace(unsigned long long *dev_buf);
 
 enum stochqn_b200_stat {
     STOCHQN_B200_STAT_K1_MS = 1, STOCHQN_B200_STAT_K1_COUNT = 2,     /* accumulated device ms / launches (profile mode) */

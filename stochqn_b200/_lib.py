@@ -17,7 +17,7 @@ _LIBS = {}
 
 EXT_SYMBOLS = (
     "stochqn_b200_version", "stochqn_b200_real_bytes", "stochqn_b200_last_error", "stochqn_b200_launch_count",
-    "stochqn_b200_set_stream", "stochqn_b200_set_option", "stochqn_b200_get_option", "stochqn_b200_debug_fit_trace", "stochqn_b200_get_stat", "stochqn_b200_row_stride",
+    "stochqn_b200_set_stream", "stochqn_b200_set_option", "stochqn_b200_get_option", "stochqn_b200_debug_fit_trace", "stochqn_b200_debug_mn_trace", "stochqn_b200_get_stat", "stochqn_b200_row_stride",
     "stochqn_b200_comm_unique_id", "stochqn_b200_comm_init", "stochqn_b200_comm_destroy", "stochqn_b200_comm_uses_p2p",
     "stochqn_b200_set_comm",
     "stochqn_b200_allreduce_f64", "stochqn_b200_allreduce_real", "stochqn_b200_reduce_scatter_real", "stochqn_b200_all_gather_real",
@@ -100,6 +100,7 @@ def load(dtype=np.float64) -> StochqnABI:
     lib.stochqn_b200_get_option.argtypes = [vp, ci]
     lib.stochqn_b200_get_option.restype = ll
     lib.stochqn_b200_debug_fit_trace.argtypes = [vp, vp]
+    lib.stochqn_b200_debug_mn_trace.argtypes = [vp]
     lib.stochqn_b200_get_stat.argtypes = [vp, ci, C.POINTER(C.c_double)]
     lib.stochqn_b200_row_stride.argtypes = [vp]
     lib.stochqn_b200_row_stride.restype = sz

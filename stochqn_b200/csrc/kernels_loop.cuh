@@ -304,6 +304,31 @@ __device__ __forceinline__ void fit_barrier(unsigned long long* bar)
 // =========================================================================================
 constexpr int kAdaThreads = 512;
 
+// Sum N (a power of two <= 32) per-lane values over the warp with N - 1 + log2(32 / N) shuffles of doubles instead of 5 N: at
+// every step a lane keeps the half of the values its lane bit selects and hands the other half to its partner.  Afterwards
+// lane l holds, in the return value, the warp total of value number l / (32 / N).  Fixed order: deterministic.
+template <int N>
+__device__ __forceinline__ double warp_reduce_multi(double (&v)[N])
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    int o = 16;
+    #pragma unroll
+    for (int half = N / 2; half >= 1; half >>= 1, o >>= 1) {
+        const bool upper = (lane & o) != 0;
+        #pragma unroll
+        for (int j = 0; j < half; ++j) {
+            const double send = upper ? v[j] : v[j + half];
+            const double keep = upper ? v[j + half] : v[j];
+            v[j] = keep + __shfl_xor_sync(full, send, o);
+        }
+    }
+    double r = v[0];
+    #pragma unroll
+    for (; o >= 1; o >>= 1) r += __shfl_xor_sync(full, r, o);
+    return r;
+}
+
 struct AdaLoopArgs {
     int msize, check_nan, fisher_size, pad;
     long long n;
@@ -348,10 +373,14 @@ template <typename T, int MMAX>
 __global__ void __launch_bounds__(kAdaThreads, 1)
 kl_ada(const AdaLoopArgs A, LoopState* __restrict__ st, const T* g, T* gout, T* __restrict__ Gacc,
        const T* __restrict__ S, const T* __restrict__ Y, T* __restrict__ F, T* __restrict__ x, T* __restrict__ x_sum, const T step,
-       double* partials, double* rec2, double* SY, double* YY, double* SS, unsigned long long* bar)
+       double* partials, double* rec2, double* SY, double* YY, double* SS, unsigned long long* bar, unsigned long long* trace)
 {
     const int m = A.msize;
     const int used = st->used, slot = st->st_ix, c = st->pend;
+    auto stamp = [&](int k) {                                // development aid (stochqn_b200_debug_fit_trace)
+        if (trace && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[k] = t; }
+    };
+    stamp(0);
     const int f_used = st->fisher_used, f_st = st->fisher_st;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = (int) gridDim.x, b = (int) blockIdx.x;
@@ -368,6 +397,9 @@ kl_ada(const AdaLoopArgs A, LoopState* __restrict__ st, const T* g, T* gout, T* 
     const T* yc = c >= 0 ? Y + (size_t) c * A.ld : nullptr;
     const T* sc = c >= 0 ? S + (size_t) c * A.ld : nullptr;
 
+    extern __shared__ __align__(16) unsigned char ada_smem[];
+    T* g_s = reinterpret_cast<T*>(ada_smem);                  // this CTA's slice of g and of h = g / sqrt(G + eps): computed once in
+    T* h_s = g_s + per;                                        // phase A, read by B and C (the divide + square root are ~100 fp64 issue slots)
     __shared__ double sums1[2 * kMaxMem + 4], sums2[kMaxMem + 1], coef_s[2 * kMaxMem + 3], two_s[2];
     __shared__ double red[NW][2 * MMAX + 4];
     __shared__ AdaShared sh;
@@ -390,6 +422,8 @@ kl_ada(const AdaLoopArgs A, LoopState* __restrict__ st, const T* g, T* gout, T* 
             Gacc[i] = Gv;
             if (frow) frow[i] = gv;
             const T h = gv / sqrt(Gv + scal_reg);
+            g_s[i - e0] = gv;
+            h_s[i - e0] = h;
             a_hh = fma((double) h, (double) h, a_hh);
             if (c >= 0) { a_ss = fma((double) scv, (double) scv, a_ss); a_yy = fma((double) ycv, (double) ycv, a_yy); }
             #pragma unroll
@@ -400,14 +434,20 @@ kl_ada(const AdaLoopArgs A, LoopState* __restrict__ st, const T* g, T* gout, T* 
                 }
             }
         }
-        #pragma unroll
-        for (int q = 0; q < 2 * MMAX + 3; ++q) {
-            double v = q < MMAX ? a_p[q < MMAX ? q : 0] : q < 2 * MMAX ? a_c[(q - MMAX) < MMAX ? (q - MMAX) : 0]
-                     : q == 2 * MMAX ? a_hh : q == 2 * MMAX + 1 ? a_ss : a_yy;
-            const bool need = q < MMAX ? q < used : q < 2 * MMAX ? (c >= 0 && q - MMAX < used) : true;
-            if (need) {                                      // block-uniform
-                v = warp_sum(v);
-                if (lane == 0) red[warp][q] = v;
+        {                                                    // warp totals: value q lands in lane q of its group of (up to) 32
+            constexpr int NV = 2 * MMAX + 3;
+            #pragma unroll
+            for (int q0 = 0; q0 < NV; q0 += 32) {
+                constexpr int NG = 32;
+                double v[NG];
+                #pragma unroll
+                for (int j = 0; j < NG; ++j) {
+                    const int q = q0 + j;
+                    v[j] = q < MMAX ? a_p[q < MMAX ? q : 0] : q < 2 * MMAX ? a_c[(q - MMAX) < MMAX && q >= MMAX ? (q - MMAX) : 0]
+                         : q == 2 * MMAX ? a_hh : q == 2 * MMAX + 1 ? a_ss : q == 2 * MMAX + 2 ? a_yy : 0.0;
+                }
+                const double r = warp_reduce_multi<NG>(v);
+                if (q0 + lane < NV) red[warp][q0 + lane] = r;
             }
         }
         __syncthreads();
@@ -416,13 +456,16 @@ kl_ada(const AdaLoopArgs A, LoopState* __restrict__ st, const T* g, T* gout, T* 
             const bool have = p < m ? p < used : p < 2 * m ? (c >= 0 && p - m < used) : p < 2 * m + 3;
             double v = 0;
             if (have) { for (int w2 = 0; w2 < NW; ++w2) v += red[w2][q]; }
-            partials[(size_t) p * G + b] = v;
+            partials[(size_t) p * G + b] = v;          // (values nobody asked for were summed too: they are zeros or unused)
         }
     }
+    stamp(1);
     fit_barrier(bar);
+    stamp(2);
 
     // ---- B: u, then w = Y'[h.(Yu - g)] ----
     reduce_entry_major(partials, P1, G, sums1, NW);
+    stamp(3);
     if (b == 0 && c >= 0) {                                  // fold the pending pair's Gram column into the global state
         for (int j = tid; j < used; j += kAdaThreads) SY[j * m + c] = sums1[m + j];
         if (tid == 0) { SS[c] = sums1[2 * m + 1]; YY[c * m + c] = sums1[2 * m + 2]; }
@@ -452,6 +495,7 @@ kl_ada(const AdaLoopArgs A, LoopState* __restrict__ st, const T* g, T* gout, T* 
     __syncthreads();
     for (int i = tid; i < used; i += kAdaThreads) coef_s[m + ph(i)] = -sh.u[i];
     __syncthreads();
+    stamp(4);
 
     int status = ST_ACCEPT;
     if (used == 0) {                                         // d = h: its norm is exact (stochqn.c:808-812, 825-835)
@@ -466,25 +510,25 @@ kl_ada(const AdaLoopArgs A, LoopState* __restrict__ st, const T* g, T* gout, T* 
         for (int j = 0; j < MMAX; ++j) acc[j] = 0;
         for (long long i = e0 + tid; i < e1; i += kAdaThreads) {
             T yv[MMAX];
-            const T gv = g[i], Gv = Gacc[i];
             #pragma unroll
             for (int j = 0; j < MMAX; ++j) yv[j] = j < used ? Y[(size_t) j * A.ld + i] : (T) 0;
+            const T gv = g_s[i - e0], h = h_s[i - e0];
             T t = -gv;
             #pragma unroll
             for (int j = 0; j < MMAX; ++j) if (j < used) t = fma(cu[j], yv[j], t);
-            const T h = gv / sqrt(Gv + scal_reg);
             const double ht = (double) (h * t);
             a_tt = fma(ht, ht, a_tt);
             #pragma unroll
             for (int j = 0; j < MMAX; ++j) if (j < used) acc[j] = fma((double) yv[j], ht, acc[j]);
         }
-        #pragma unroll
-        for (int q = 0; q <= MMAX; ++q) {
-            if (q < used || q == MMAX) {
-                double v = q < MMAX ? acc[q < MMAX ? q : 0] : a_tt;
-                v = warp_sum(v);
-                if (lane == 0) red[warp][q] = v;
-            }
+        {
+            constexpr int NG = MMAX + 1 <= 16 ? 16 : 32;
+            double v[NG];
+            #pragma unroll
+            for (int j = 0; j < NG; ++j) v[j] = j < MMAX ? acc[j < MMAX ? j : 0] : j == MMAX ? a_tt : 0.0;
+            const double r = warp_reduce_multi<NG>(v);
+            constexpr int SH = NG == 16 ? 1 : 0;              // lane l holds value l >> SH
+            if ((lane & ((1 << SH) - 1)) == 0 && (lane >> SH) <= MMAX) red[warp][lane >> SH] = r;
         }
         __syncthreads();
         for (int p = tid; p < P2; p += kAdaThreads) {        // record of ka2_wdots: [0,m) w, [m] sum (h.(Yu-g))^2
@@ -493,7 +537,9 @@ kl_ada(const AdaLoopArgs A, LoopState* __restrict__ st, const T* g, T* gout, T* 
             if (p == m || p < used) { for (int w2 = 0; w2 < NW; ++w2) v += red[w2][q]; }
             rec2[(size_t) p * G + b] = v;
         }
+        stamp(5);
         fit_barrier(bar);
+        stamp(6);
 
         // ---- C: a = R^-T (D u + w), bound, decision ----
         reduce_entry_major(rec2, P2, G, sums2, NW);
@@ -535,6 +581,7 @@ kl_ada(const AdaLoopArgs A, LoopState* __restrict__ st, const T* g, T* gout, T* 
         __syncthreads();
         status = sh.status;
     }
+    stamp(7);
 
     // d on the slice (ka3_combine): part0 = sum_r a_r s_r ; part1 = h.(g + sum_r b_r y_r)
     T cfS[MMAX], cfY[MMAX];
@@ -542,15 +589,14 @@ kl_ada(const AdaLoopArgs A, LoopState* __restrict__ st, const T* g, T* gout, T* 
     for (int r = 0; r < MMAX; ++r) { cfS[r] = r < used ? (T) coef_s[r] : (T) 0; cfY[r] = r < used ? (T) coef_s[m + r] : (T) 0; }
     auto direction = [&](long long i) -> T {
         T sv[MMAX], yv[MMAX];
-        const T gv = g[i], Gv = Gacc[i];
         #pragma unroll
         for (int r = 0; r < MMAX; ++r) { sv[r] = r < used ? S[(size_t) r * A.ld + i] : (T) 0; yv[r] = r < used ? Y[(size_t) r * A.ld + i] : (T) 0; }
+        const T gv = g_s[i - e0], h = h_s[i - e0];
         T p0 = (T) 0, p1 = gv;
         #pragma unroll
         for (int r = 0; r < MMAX; ++r) {
             if (r < used) { p0 = fma(cfS[r], sv[r], p0); p1 = fma(cfY[r], yv[r], p1); }
         }
-        const T h = gv / sqrt(Gv + scal_reg);
         p1 = used > 0 ? h * p1 : h;
         return p1 + p0;
     };
@@ -590,6 +636,7 @@ kl_ada(const AdaLoopArgs A, LoopState* __restrict__ st, const T* g, T* gout, T* 
         for (long long i = e0 + tid; i < e1; i += kAdaThreads) x_sum[i] = x_sum[i] + x[i];      // quirk Q7 (stochqn.c:1191)
     }
 
+    if (trace) { __syncthreads(); stamp(8); }
     if (b == 0 && tid == 0) {
         st->last_status = status;
         st->calls += 1;

@@ -451,6 +451,24 @@ constexpr int MS_T = 512;
 constexpr int MS_CW = 16;
 constexpr int MS_MAX_BK = 12288, MS_MAX_B = 128, MS_MAX_K = 512, MS_MAX_GRID = 160;
 
+
+// 16-byte L2 load (ld.global.cg.v4 / v2) of VE = 16 / sizeof(T) elements
+template <typename T> struct Pack16 {
+    T v[16 / sizeof(T)];
+    __device__ static Pack16 zero() { Pack16 p; for (int e = 0; e < (int) (16 / sizeof(T)); ++e) p.v[e] = (T) 0; return p; }
+};
+template <typename T> __device__ __forceinline__ Pack16<T> ld_cg16(const T* p);
+template <> __device__ __forceinline__ Pack16<double> ld_cg16<double>(const double* p)
+{
+    const double2 t = __ldcg(reinterpret_cast<const double2*>(p));
+    Pack16<double> r; r.v[0] = t.x; r.v[1] = t.y; return r;
+}
+template <> __device__ __forceinline__ Pack16<float> ld_cg16<float>(const float* p)
+{
+    const float4 t = __ldcg(reinterpret_cast<const float4*>(p));
+    Pack16<float> r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
+}
+
 __device__ __forceinline__ void ms_barrier(unsigned long long* bar)
 {
     __syncthreads();
@@ -475,7 +493,7 @@ template <typename T>
 __global__ void __launch_bounds__(MS_T, 1)
 mn_grad_small(const T* __restrict__ X, long long ldx, const T* __restrict__ Y, long long ldy, const int* __restrict__ labels,
               const T* __restrict__ sw, int B, int d, int K, int icpt, const T* __restrict__ W, T alpha, T* __restrict__ Gout,
-              T* Zp, T* Dg, unsigned long long* bar)
+              T* Zp, T* Dg, unsigned long long* bar, unsigned long long* trace)
 {
     extern __shared__ __align__(16) unsigned char ms_smem[];
     const int G = (int) gridDim.x, c = (int) blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -489,8 +507,14 @@ mn_grad_small(const T* __restrict__ X, long long ldx, const T* __restrict__ Y, l
     T* Ds = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(Wc + (size_t) cw * K) + 15) & ~(uintptr_t) 15);      // [B][K]
     __shared__ double red_s[MS_T / 32];
     __shared__ double bc_s[2];
+    auto stamp = [&](int k) {                                // development aid (stochqn_b200_debug_mn_trace)
+        if (trace && c == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[k] = t; }
+    };
+    stamp(0);
 
     // ---- phase 1: the chunk of X and W, partial Z ----
+    constexpr int VE = 16 / (int) sizeof(T);                 // elements of a 16-byte vector
+    const int KZ = (K + VE - 1) / VE * VE;                   // row pitch of the partial Z records (16-byte aligned rows)
     for (int t = tid; t < B * cw; t += MS_T) {
         const int b = t / cw, jj = t % cw;
         Xc[jj * B + b] = jj < w ? __ldg(X + (long long) b * ldx + j0 + jj) : (T) 0;
@@ -501,73 +525,79 @@ mn_grad_small(const T* __restrict__ X, long long ldx, const T* __restrict__ Y, l
     }
     __syncthreads();
     {
-        const int BT = (B + 3) / 4, KT = (K + 7) / 8;        // thread tile: b in {bt + BT*ib}, k in {kt + KT*ik}: lanes walk kt -> conflict-free
-        T* zout = Zp + (size_t) c * (size_t) B * K;
+        const int BT = (B + 1) / 2, KT = (K + 7) / 8;        // thread tile: b in {bt, bt + BT}, k in {kt + KT*ik}: lanes walk kt -> conflict-free
+        T* zout = Zp + (size_t) c * (size_t) B * KZ;
         for (int t = tid; t < BT * KT; t += MS_T) {
             const int bt = t / KT, kt = t % KT;
-            T acc[4][8];
+            const int b0 = bt, b1 = bt + BT;
+            T acc[2][8];
             #pragma unroll
-            for (int ib = 0; ib < 4; ++ib)
-                #pragma unroll
-                for (int ik = 0; ik < 8; ++ik) acc[ib][ik] = (T) 0;
+            for (int ik = 0; ik < 8; ++ik) { acc[0][ik] = (T) 0; acc[1][ik] = (T) 0; }
             for (int jj = 0; jj < w; ++jj) {
-                T xa[4], wa[8];
-                #pragma unroll
-                for (int ib = 0; ib < 4; ++ib) { const int b = bt + BT * ib; xa[ib] = b < B ? Xc[jj * B + b] : (T) 0; }
+                T wa[8];
+                const T x0 = Xc[jj * B + b0], x1 = b1 < B ? Xc[jj * B + b1] : (T) 0;
                 #pragma unroll
                 for (int ik = 0; ik < 8; ++ik) { const int k = kt + KT * ik; wa[ik] = k < K ? Wc[jj * K + k] : (T) 0; }
                 #pragma unroll
-                for (int ib = 0; ib < 4; ++ib)
-                    #pragma unroll
-                    for (int ik = 0; ik < 8; ++ik) acc[ib][ik] = fma(xa[ib], wa[ik], acc[ib][ik]);
+                for (int ik = 0; ik < 8; ++ik) { acc[0][ik] = fma(x0, wa[ik], acc[0][ik]); acc[1][ik] = fma(x1, wa[ik], acc[1][ik]); }
             }
             #pragma unroll
-            for (int ib = 0; ib < 4; ++ib) {
-                const int b = bt + BT * ib;
-                #pragma unroll
-                for (int ik = 0; ik < 8; ++ik) {
-                    const int k = kt + KT * ik;
-                    if (b < B && k < K) zout[(size_t) b * K + k] = acc[ib][ik];
+            for (int ik = 0; ik < 8; ++ik) {
+                const int k = kt + KT * ik;
+                if (k < K) {
+                    zout[(size_t) b0 * KZ + k] = acc[0][ik];
+                    if (b1 < B) zout[(size_t) b1 * KZ + k] = acc[1][ik];
                 }
             }
         }
+        if (KZ > K) {                                        // the padding of every row is read (as part of a vector) by phase 2
+            for (int t = tid; t < B * (KZ - K); t += MS_T) zout[(size_t) (t / (KZ - K)) * KZ + K + t % (KZ - K)] = (T) 0;
+        }
     }
+    stamp(1);
     ms_barrier(bar);
+    stamp(2);
 
-    // ---- phase 2: one CTA per sample: sum the partial rows, softmax, D row ----
+    // ---- phase 2: one CTA per sample: sum the partial rows (16-byte loads, 8 records in flight per thread), softmax, D row ----
     {
-        const int KP = (K + 31) / 32 * 32;
-        const int NQ = MS_T / KP;                            // record slices (K <= 512: at least one)
-        double* zrow = reinterpret_cast<double*>(Ds);         // (Ds is not in use yet) [NQ][KP] partial sums, then the finished row in slice 0
+        const int NV = KZ / VE;                              // vectors per row
+        const int NVP = (NV + 31) / 32 * 32;
+        const int NQ = MS_T / NVP;                           // record slices (K <= 512: at least one)
+        double* zrow = reinterpret_cast<double*>(Ds);         // (Ds is not in use yet) [NQ][NVP * VE] partial sums
+        const size_t rs = (size_t) B * KZ;
         for (int b = c; b < B; b += G) {
-            const int k = tid % KP, q = tid / KP;
-            if (q < NQ) {
-                double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-                if (k < K) {
-                    const T* pz = Zp + (size_t) b * K + k;
-                    const size_t rs = (size_t) B * K;
-                    int r = q;
-                    for (; r + 3 * NQ < G; r += 4 * NQ) {
-                        const T v0 = __ldcg(pz + (size_t) r * rs), v1 = __ldcg(pz + (size_t) (r + NQ) * rs);
-                        const T v2 = __ldcg(pz + (size_t) (r + 2 * NQ) * rs), v3 = __ldcg(pz + (size_t) (r + 3 * NQ) * rs);
-                        a0 += (double) v0; a1 += (double) v1; a2 += (double) v2; a3 += (double) v3;
+            const int v = tid % NVP, q = tid / NVP;
+            if (q < NQ && v < NV) {
+                double a[VE];
+                #pragma unroll
+                for (int e = 0; e < VE; ++e) a[e] = 0.0;
+                const T* pz = Zp + (size_t) b * KZ + (size_t) v * VE;
+                for (int r0 = q; r0 < G; r0 += 8 * NQ) {
+                    Pack16<T> pv[8];
+                    #pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int r = r0 + u * NQ;
+                        if (r < G) pv[u] = ld_cg16<T>(pz + (size_t) r * rs); else pv[u] = Pack16<T>::zero();
                     }
-                    for (; r < G; r += NQ) a0 += (double) __ldcg(pz + (size_t) r * rs);
+                    #pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        #pragma unroll
+                        for (int e = 0; e < VE; ++e) a[e] += (double) pv[u].v[e];
                 }
-                zrow[q * KP + k] = (a0 + a1) + (a2 + a3);
+                #pragma unroll
+                for (int e = 0; e < VE; ++e) zrow[(size_t) q * NVP * VE + v * VE + e] = a[e];
             }
             __syncthreads();
             double z = -INFINITY;
             if (tid < K) {
                 z = icpt ? (double) __ldg(W + (long long) tid * ldw + d) : 0.0;
-                for (int q2 = 0; q2 < NQ; ++q2) z += zrow[q2 * KP + tid];
+                for (int q2 = 0; q2 < NQ; ++q2) z += zrow[(size_t) q2 * NVP * VE + tid];
             }
-            // CTA max
             double mx = z;
             for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             if (lane == 0) red_s[warp] = mx;
             __syncthreads();
-            if (tid == 0) { double v = red_s[0]; for (int q2 = 1; q2 < MS_T / 32; ++q2) v = fmax(v, red_s[q2]); bc_s[0] = v; }
+            if (tid == 0) { double v2 = red_s[0]; for (int q2 = 1; q2 < MS_T / 32; ++q2) v2 = fmax(v2, red_s[q2]); bc_s[0] = v2; }
             __syncthreads();
             mx = bc_s[0];
             const double ez = tid < K ? exp(z - mx) : 0.0;
@@ -575,43 +605,61 @@ mn_grad_small(const T* __restrict__ X, long long ldx, const T* __restrict__ Y, l
             for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
             if (lane == 0) red_s[warp] = se;
             __syncthreads();
-            if (tid == 0) { double v = 0; for (int q2 = 0; q2 < MS_T / 32; ++q2) v += red_s[q2]; bc_s[1] = v; }
+            if (tid == 0) { double v2 = 0; for (int q2 = 0; q2 < MS_T / 32; ++q2) v2 += red_s[q2]; bc_s[1] = v2; }
             __syncthreads();
             if (tid < K) {
                 const double lse = mx + log(bc_s[1]);
-                const double p = exp(z - lse);                                   // as mn_rows: exp(z - lse)
+                const double pk = exp(z - lse);                                  // as mn_rows: exp(z - lse)
                 const double wt = sw ? (double) sw[b] : 1.0;
                 const double yk = labels ? (labels[b] == tid ? 1.0 : 0.0) : (double) Y[(long long) b * ldy + tid];
-                Dg[(size_t) b * K + tid] = (T) (wt * (p - yk));
+                Dg[(size_t) b * K + tid] = (T) (wt * (pk - yk));
             }
             __syncthreads();
         }
     }
+    stamp(3);
     ms_barrier(bar);
+    stamp(4);
 
     // ---- phase 3: G[:, chunk] = D' X[:, chunk] + alpha W[:, chunk]; the intercept column by the last CTA ----
-    for (int t = tid; t < B * K; t += MS_T) Ds[t] = __ldcg(Dg + t);
+    {
+        const int total = B * K;
+        for (int t0 = tid; t0 < total; t0 += 8 * MS_T) {     // eight loads in flight per thread
+            T dv[8];
+            #pragma unroll
+            for (int u = 0; u < 8; ++u) { const int t = t0 + u * MS_T; dv[u] = t < total ? __ldcg(Dg + t) : (T) 0; }
+            #pragma unroll
+            for (int u = 0; u < 8; ++u) { const int t = t0 + u * MS_T; if (t < total) Ds[t] = dv[u]; }
+        }
+    }
     __syncthreads();
+    stamp(5);
     {
         const int KP = (K + 31) / 32 * 32;
-        const int NH = MS_T / KP;                            // feature interleave: thread (k, h) owns jj = h, h + NH, ...
+        const int NH = MS_T / KP;                            // feature interleave: thread (k, h) owns jj = h, h + NH, ... (h is warp-uniform)
         const int k = tid % KP, h = tid / KP;
         if (k < K && h < NH) {
-            T acc[MS_CW];
             #pragma unroll
-            for (int u = 0; u < MS_CW; ++u) acc[u] = (T) 0;
-            for (int b = 0; b < B; ++b) {
-                const T dv = Ds[b * K + k];
-                #pragma unroll
-                for (int u = 0; u < MS_CW; ++u) {
-                    const int jj = h + u * NH;
-                    if (jj < w) acc[u] = fma(dv, Xc[jj * B + b], acc[u]);
+            for (int ug = 0; ug < MS_CW / 4; ++ug) {         // four features at a time; groups beyond the chunk are skipped (warp-uniform)
+                const int jb = h + 4 * ug * NH;
+                if (jb < w) {
+                    const int j1 = jb + NH, j2 = jb + 2 * NH, j3 = jb + 3 * NH;
+                    const T* x0 = Xc + jb * B;
+                    const T* x1 = Xc + (j1 < w ? j1 : jb) * B;
+                    const T* x2 = Xc + (j2 < w ? j2 : jb) * B;
+                    const T* x3 = Xc + (j3 < w ? j3 : jb) * B;
+                    T a0 = (T) 0, a1 = (T) 0, a2 = (T) 0, a3 = (T) 0;
+                    #pragma unroll 5
+                    for (int b = 0; b < B; ++b) {
+                        const T dv = Ds[b * K + k];
+                        a0 = fma(dv, x0[b], a0); a1 = fma(dv, x1[b], a1); a2 = fma(dv, x2[b], a2); a3 = fma(dv, x3[b], a3);
+                    }
+                    T* go = Gout + (long long) k * ldw + j0;
+                    go[jb] = fma(alpha, Wc[jb * K + k], a0);
+                    if (j1 < w) go[j1] = fma(alpha, Wc[j1 * K + k], a1);
+                    if (j2 < w) go[j2] = fma(alpha, Wc[j2 * K + k], a2);
+                    if (j3 < w) go[j3] = fma(alpha, Wc[j3 * K + k], a3);
                 }
-            }
-            #pragma unroll
-            for (int u = 0; u < MS_CW; ++u) {
-                const int jj = h + u * NH;
-                if (jj < w) Gout[(long long) k * ldw + j0 + jj] = fma(alpha, Wc[jj * K + k], acc[u]);
             }
         }
         if (icpt && c == G - 1 && tid < K) {
@@ -620,13 +668,16 @@ mn_grad_small(const T* __restrict__ X, long long ldx, const T* __restrict__ Y, l
             Gout[(long long) tid * ldw + d] = (T) sacc;
         }
     }
+    if (trace) { __syncthreads(); stamp(6); }
 }
+
+unsigned long long* g_mn_trace = nullptr;
 
 size_t mn_small_smem(long long B, long long d, long long K, int grid)
 {
     const long long cw = (d + grid - 1) / grid;
     size_t ds = sizeof(real_t) * (size_t) (B * K);
-    if (ds < 512 * sizeof(double)) ds = 512 * sizeof(double);          // phase 2 stages its partial sums there
+    if (ds < 2048 * sizeof(double)) ds = 2048 * sizeof(double);        // phase 2 stages its partial sums there ([slices][padded row])
     return sizeof(real_t) * (size_t) (cw * B + cw * K) + ds + 16;
 }
 
@@ -659,7 +710,8 @@ int mn_try_small(const real_t* X, long long ldx, const real_t* Y, long long ldy,
     unsigned long long* bar = (unsigned long long*) (base + p.off_small_bar);
     if (cudaMemsetAsync(bar, 0, 64 * sizeof(unsigned long long), st) != cudaSuccess) return -2;
     int Bi = (int) B, di = (int) d, Ki = (int) K, ic = fit_intercept ? 1 : 0;
-    void* args[] = {&X, &ldx, &Y, &ldy, &labels, &sw, &Bi, &di, &Ki, &ic, &w, &alpha, &out, &Zp, &Dg, &bar};
+    unsigned long long* trace = g_mn_trace;
+    void* args[] = {&X, &ldx, &Y, &ldy, &labels, &sw, &Bi, &di, &Ki, &ic, &w, &alpha, &out, &Zp, &Dg, &bar, &trace};
     if (cudaLaunchCooperativeKernel((const void*) kern, dim3((unsigned) sms), dim3(MS_T), args, smem, st) != cudaSuccess) {
         fprintf(stderr, "stochqn_b200: mn_grad_small launch failed: %s\n", cudaGetErrorString(cudaGetLastError()));
         return -2;
@@ -703,7 +755,7 @@ MnPlan mn_plan(long long B, long long d, long long K)
         if (bk > MS_MAX_BK) bk = MS_MAX_BK;
         const size_t dt_need = sizeof(real_t) * (size_t) bk;                 // D is kept where DT lives: K * bpad >= B * K
         (void) dt_need;
-        off = al(off + sizeof(real_t) * (size_t) (MS_MAX_GRID * bk));
+        off = al(off + sizeof(real_t) * (size_t) (MS_MAX_GRID * (bk + 3 * MS_MAX_B)));      // rows padded to 16 bytes
         p.off_small_bar = off; off = al(off + 64 * sizeof(unsigned long long));
     }
     p.total = off;
@@ -848,6 +900,12 @@ int stochqn_b200_gemm_tn(const real_t* A, long long lda, const real_t* B, long l
 {
     if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return -1;
     return launch_gemm(A, lda, B, ldb, C, ldc, 0, M, N, K, 1, (cudaStream_t) stream);
+}
+
+int stochqn_b200_debug_mn_trace(unsigned long long* dev_buf)
+{
+    g_mn_trace = dev_buf;
+    return 0;
 }
 
 size_t stochqn_b200_multinomial_work_size(long long nrows, long long nfeat, long long nclasses)

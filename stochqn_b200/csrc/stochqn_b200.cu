@@ -193,6 +193,7 @@ struct Ctx {
     int fused_fit = 1;                  // 0: never (option FUSED_FIT)
     unsigned long long* fit_bar = nullptr;    // its grid-barrier counter
     unsigned long long* ada_bar = nullptr;    // grid-barrier words of kl_ada (its grid depends on n)
+    bool ada_attr_set = false;
     void* fit_work = nullptr;           // the model's scratch buffer (partial column records)
     double fit_steps = 0;               // mini-batches served by it
     unsigned long long* fit_trace = nullptr;   // development aid (stochqn_b200_debug_fit_trace)

@@ -1,8 +1,9 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 400 python -m pytest --timeout=60 tests/test_gpu_device_loop.py tests/test_gpu_logistic_estimator.py tests/test_gpu_guided.py -x -q > gpurun_out/pytest_ada.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/pytest_ada.log
-timeout 300 python tools/bench_configs.py cfg3 cfg3d --steps 1000 2>&1 | python -c "
+timeout 500 python -m pytest --timeout=60 tests/test_gpu_device_loop.py tests/test_gpu_multinomial.py tests/test_gpu_logistic_estimator.py tests/test_gpu_guided.py -x -q > gpurun_out/pytest_ada.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_ada.log
+timeout 200 python tools/probe_cfg3.py
+timeout 300 python tools/bench_configs.py cfg3d --steps 1000 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):

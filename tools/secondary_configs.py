@@ -52,7 +52,7 @@ def _cfg1(peaks, cpu):
             out = dict(r, **keep)
     # per step: two gradients, each ONE sweep of the batch (B x n), + the optimizer's (4m + 10) n-vectors
     b = 2 * B * n * 8 + (4 * MEM + 10) * n * 8
-    out["dominant_kernel"] = "logistic_fused (one-sweep gradient) - latency-bound: 8 KB vectors"
+    out["dominant_kernel"] = "kl_fit_logistic (one launch per run of mini-batches: gradient sweeps + step + pair) - latency-bound: 8 KB vectors"
     out["roofline"] = _roof(b, 0, out["ms_per_step"], peaks)
     return out
 
@@ -84,13 +84,23 @@ def _cfg3(peaks, cpu):
             return CC.best_of_threads(CC.multinomial_reference, dtype=np.float64, X=X.cpu().numpy(), lab=lab.cpu().numpy().astype(np.int64), K=K,
                                       batch=B, steps=40, warm=12 * L, L=L, fisher=k, use_grad_diff=0, max_incr=1.01, rms=0.0, step=1e-2, max_s=4.0,
                                       alpha=1e-1, wsum=True, x0=x0)
-    out = BC.run_multinomial("cfg3", np.float64, d, K, B, 6655, 1000, L, k, 0, 1.01, 0.0, 1e-2, quiet=True, cpu_fn=cpu_fn, profile="bibtex")
+    out = None
+    for native in (True, False):        # the request loop inside the library (two launches per ordinary step) and the caller's Python loop
+        r = BC.run_multinomial("cfg3", np.float64, d, K, B, 6655, 1000, L, k, 0, 1.01, 0.0, 1e-2, quiet=True, cpu_fn=cpu_fn if out is None else None,
+                               profile="bibtex", native=native)
+        if out is None:
+            out = r
+            out["loops"] = {}
+        out["loops"][r["loop"]] = r["steps_per_s"]
+        if r["steps_per_s"] > out["steps_per_s"]:
+            keep = {k2: out[k2] for k2 in ("loops", "cpu_reference") if k2 in out}
+            out = dict(r, **keep)
     out["workload"] = ("BibTeX-shaped as in example/example_stochqn.ipynb: 1836 binary features (3.75 % dense), 159 classes, batch 50, summed loss, "
                        "reg_param 0.1, x0 ~ N(0,1), step 1e-2, AdaGrad, Fisher 100, L 20, max_incr 1.01")
     # per step: optimizer 4m + 10 = 50 n-vectors (Fisher ring write included), gradient reads W, alpha*W and writes G (3 vectors)
     # + the batch; per L steps the Fisher product 2k + 4 vectors
     b = (4 * MEM + 10 + 3 + (2 * k + 4) / float(L)) * n * 8 + B * d * 8
-    out["dominant_kernel"] = "ka3_combine / ka1_dots (n = %d: 2.3 MB vectors, launch-latency-bound)" % n
+    out["dominant_kernel"] = "kl_ada (one-launch adaQN step) + mn_grad_small (one-launch gradient); n = %d: 2.3 MB vectors, latency-bound" % n
     out["roofline"] = _roof(b, 4.0 * B * d * K * 0, out["ms_per_step"], peaks)      # fp64 build: GEMMs on the CUDA cores, not counted
     return out
 

@@ -170,6 +170,13 @@ int stochqn_b200_rosenbrock_halo(const real_t *x, long long n_local, int rank, i
      loss     = -sum(sw .* (y log p + (1-y) log(1-p))) / sum(sw) + lambda*|w|^2   (logistic.R:1-10)
    `work` is device scratch of at least stochqn_b200_logistic_work_size(nrows, ncols) bytes. */
 size_t stochqn_b200_logistic_work_size(long long nrows, long long ncols);
+
+/* Sparse model matrices (stochqn/_logistic.py:155 keeps scipy CSR inputs): rows [row0, row0 + nrows) of a device-resident
+   canonical CSR matrix (indptr / indices as 64-bit integers, no duplicate column within a row) expanded into dense rows
+   out[r][0..ncols), leading dimension ldo - the layout the bundled callbacks stream.  *bad_index_flag (device int, may be
+   NULL) is set to 1 if a column index lies outside [0, ncols). */
+int stochqn_b200_csr_to_dense(const long long *indptr, const long long *indices, const real_t *data, long long row0, long long nrows,
+                              long long ncols, real_t *out, long long ldo, int *bad_index_flag, void *stream);
 int stochqn_b200_logistic_grad(const real_t *X, long long ldx, const real_t *y, const real_t *sw,
                                long long nrows, long long ncols, const real_t *w, real_t lambda,
                                real_t *grad, void *work, void *stream);

@@ -23,7 +23,7 @@ EXT_SYMBOLS = (
     "stochqn_b200_allreduce_f64", "stochqn_b200_allreduce_real", "stochqn_b200_reduce_scatter_real", "stochqn_b200_all_gather_real",
     "stochqn_b200_rosenbrock_x0", "stochqn_b200_rosenbrock_grad", "stochqn_b200_rosenbrock_fun", "stochqn_b200_rosenbrock_halo",
     "stochqn_b200_rosenbrock_grad_sharded",
-    "stochqn_b200_logistic_work_size", "stochqn_b200_logistic_grad", "stochqn_b200_logistic_hess_vec",
+    "stochqn_b200_logistic_work_size", "stochqn_b200_csr_to_dense", "stochqn_b200_logistic_grad", "stochqn_b200_logistic_hess_vec",
     "stochqn_b200_logistic_loss", "stochqn_b200_export", "stochqn_b200_import",
     "stochqn_b200_logistic_sk_grad", "stochqn_b200_logistic_sk_hess_vec", "stochqn_b200_logistic_sk_loss",
     "stochqn_b200_multinomial_work_size", "stochqn_b200_multinomial_loss_grad", "stochqn_b200_multinomial_hess_vec",
@@ -120,6 +120,7 @@ def load(dtype=np.float64) -> StochqnABI:
     lib.stochqn_b200_rosenbrock_grad_sharded.argtypes = [vp, vp, ll, ll, ll, ci, ci, vp, vp, vp, vp]
     lib.stochqn_b200_logistic_work_size.argtypes = [ll, ll]
     lib.stochqn_b200_logistic_work_size.restype = sz
+    lib.stochqn_b200_csr_to_dense.argtypes = [vp, vp, vp, ll, ll, ll, vp, ll, vp, vp]
     lib.stochqn_b200_logistic_grad.argtypes = [vp, ll, vp, vp, ll, ll, vp, real, vp, vp, vp]
     lib.stochqn_b200_logistic_hess_vec.argtypes = [vp, ll, vp, vp, ll, ll, vp, vp, real, vp, vp, vp]
     lib.stochqn_b200_logistic_loss.argtypes = [vp, ll, vp, vp, ll, ll, vp, real, vp, vp, vp]

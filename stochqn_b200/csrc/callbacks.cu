@@ -466,6 +466,32 @@ logistic_fused_finish(const double* __restrict__ colpart, int nparts, long long 
     if (form.icpt && blockIdx.x == 0 && tx == 0) out[ncols] = (real_t) rst;      // intercept: sum of the row weights
 }
 
+
+// ---- CSR rows -> dense rows (sparse model matrices for the bundled callbacks) ---------------------------------------
+// The reference's Python estimator keeps a scipy CSR matrix and hands it to scikit-learn's sparse-aware arithmetic
+// (stochqn/_logistic.py:155).  The device callbacks are dense one-sweep kernels, so a CSR model matrix is expanded once, on the
+// device, into the resident dense matrix they stream (stochqn_b200/logistic.py): one warp per row zero-fills it and scatters
+// the stored entries (canonical CSR: no duplicate column in a row).
+__global__ void __launch_bounds__(kT)
+csr_rows_to_dense_kernel(const long long* __restrict__ indptr, const long long* __restrict__ indices, const real_t* __restrict__ data,
+                         long long row0, long long nrows, long long ncols, real_t* __restrict__ out, long long ldo, int* __restrict__ bad)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long) gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp; r < nrows; r += nwarps) {
+        real_t* o = out + r * ldo;
+        for (long long j = lane; j < ncols; j += 32) o[j] = (real_t) 0;
+        __syncwarp();
+        const long long p0 = indptr[row0 + r], p1 = indptr[row0 + r + 1];
+        for (long long p = p0 + lane; p < p1; p += 32) {
+            const long long j = indices[p];
+            if (j >= 0 && j < ncols) o[j] = data[p];
+            else if (bad) *bad = 1;
+        }
+    }
+}
+
 template <int C, int KIND, int R, int MINB>
 void launch_logistic_fused_t(const real_t* X, long long ldx, const real_t* y, const real_t* sw, long long nrows, long long ncols,
                              const real_t* w, const real_t* v, double* colpart, int* nparts, int sms, cudaStream_t st, LgForm form)
@@ -597,6 +623,16 @@ int stochqn_b200_rosenbrock_halo(const real_t* x, long long n_local, int rank, i
     if (int r = stochqn_b200_allreduce_f64(comm, scratch, (size_t) 2 * world_size, stream)) return r;
     rosen_halo_unpack<<<1, 32, 0, (cudaStream_t) stream>>>(scratch, rank, world_size, halo);
     return check_launch("rosenbrock_halo", 2);
+}
+
+int stochqn_b200_csr_to_dense(const long long* indptr, const long long* indices, const real_t* data, long long row0, long long nrows,
+                              long long ncols, real_t* out, long long ldo, int* bad_index_flag, void* stream)
+{
+    if (!indptr || !out || nrows < 0 || ncols <= 0 || ldo < ncols || row0 < 0) return -1;
+    if (nrows == 0) return 0;
+    csr_rows_to_dense_kernel<<<grid_1d(nrows * 32, 148 * 16), kT, 0, (cudaStream_t) stream>>>(indptr, indices, data, row0, nrows, ncols, out, ldo,
+                                                                                              bad_index_flag);
+    return check_launch("csr_to_dense");
 }
 
 size_t stochqn_b200_logistic_work_size(long long nrows, long long ncols)

@@ -69,6 +69,39 @@ def _rows(X):
     return X, (X.stride(0) if X.shape[0] > 1 else X.shape[1])
 
 
+def _csr_to_dense_on_device(a, dev, dt):
+    """A sparse model matrix (scipy sparse, any format, or a torch sparse-CSR tensor - stochqn/_logistic.py:155 keeps CSR inputs)
+    expanded ON THE DEVICE into the dense row-major matrix the bundled kernels stream: the three CSR arrays are uploaded and
+    one kernel (stochqn_b200_csr_to_dense) zero-fills and scatters every row.  The dense copy must fit in device memory."""
+    torch = _torch()
+    if _is_torch(a):
+        indptr, indices, data = a.crow_indices(), a.col_indices(), a.values()
+        nrows, ncols = a.shape
+    else:
+        from scipy.sparse import csr_matrix
+        a = csr_matrix(a)
+        a.sum_duplicates()
+        indptr, indices, data = torch.as_tensor(a.indptr.astype(np.int64)), torch.as_tensor(a.indices.astype(np.int64)), torch.as_tensor(a.data)
+        nrows, ncols = a.shape
+    need = int(nrows) * int(ncols) * (8 if dt == torch.float64 else 4)
+    free, _total = torch.cuda.mem_get_info(dev)
+    if need > 0.9 * free:
+        raise MemoryError("the dense copy of the sparse model matrix (%d x %d, %.1f GB) does not fit in device memory (%.1f GB free); "
+                          "the bundled device callbacks are dense kernels" % (nrows, ncols, need / 1e9, free / 1e9))
+    indptr = indptr.to(device=dev, dtype=torch.int64).contiguous()
+    indices = indices.to(device=dev, dtype=torch.int64).contiguous()
+    data = data.to(device=dev, dtype=dt).contiguous()
+    out = torch.empty((int(nrows), int(ncols)), device=dev, dtype=dt)
+    bad = torch.zeros(1, device=dev, dtype=torch.int32)
+    abi = _lib.load(np.float64 if dt == torch.float64 else np.float32)
+    with torch.cuda.device(dev):
+        _check(abi.lib.stochqn_b200_csr_to_dense(indptr.data_ptr(), indices.data_ptr(), data.data_ptr() if data.numel() else None, 0, int(nrows),
+                                                 int(ncols), out.data_ptr(), int(ncols), bad.data_ptr(), _stream()), abi, "csr_to_dense")
+    if int(bad.item()):
+        raise ValueError("the sparse matrix holds a column index outside [0, %d)" % ncols)
+    return out
+
+
 def _vec(a, like, name):
     if a is None:
         return None
@@ -453,11 +486,11 @@ class StochasticLogisticRegression:
     # ---- predictions ----------------------------------------------------------------------------------------
     def _to_dev(self, a, dtype=None):
         torch = _torch()
-        if _is_sparse(a):
-            raise TypeError("sparse inputs are not supported by the device callbacks; pass a dense array")
         x = self.optimizer.x if self.optimizer is not None else None
         dev = x.device if x is not None else torch.device(self.device if self.device is not None else "cuda")
         dt = dtype if dtype is not None else (x.dtype if x is not None else None)
+        if _is_sparse(a) or (_is_torch(a) and a.layout == torch.sparse_csr):
+            return _csr_to_dense_on_device(a, dev, dt if dt is not None else torch.float64)
         if not _is_torch(a):
             a = torch.as_tensor(np.ascontiguousarray(a))
         return a.to(device=dev, dtype=dt)

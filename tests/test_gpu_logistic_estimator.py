@@ -124,3 +124,40 @@ def test_estimator_partial_fit_and_float():
     assert m.is_fitted and m.optimizer.niter == 9 and m.optimizer.x.dtype == torch.float32
     assert bool(torch.isfinite(m.optimizer.x).all())
     assert m.predict(Xd).shape == (X.shape[0],) and m.predict_proba(Xd).shape == (X.shape[0], 2)
+
+
+@pytest.mark.parametrize("fmt", ["scipy_csr", "scipy_coo", "torch_csr"])
+@pytest.mark.parametrize("mult,optimizer", [(False, "oLBFGS"), (True, "adaQN")])
+def test_sparse_model_matrix_is_expanded_on_the_device(fmt, mult, optimizer):
+    """The reference's estimator keeps scipy CSR inputs (stochqn/_logistic.py:155).  Here a sparse model matrix is expanded once, on
+    the device (stochqn_b200_csr_to_dense), into the dense matrix the bundled kernels stream: same kernels, same batches, so the fit
+    is bit-identical to the one on the dense array - also for a BibTeX-like 4 %-dense matrix with empty rows and columns."""
+    import scipy.sparse as sp
+    import torch
+    from stochqn_b200.logistic import StochasticLogisticRegression, _csr_to_dense_on_device
+
+    rng = np.random.default_rng(7)
+    n, d, K = 700, 83, 5
+    Xd = rng.standard_normal((n, d)) * (rng.random((n, d)) < 0.04)
+    Xd[17] = 0.0
+    Xd[:, 5] = 0.0
+    if mult:
+        lab = rng.integers(0, K, n)
+        y = np.eye(K)[lab]
+    else:
+        y = np.where(rng.random(n) < 0.5, 1.0, -1.0)
+    Xs = {"scipy_csr": sp.csr_matrix(Xd), "scipy_coo": sp.coo_matrix(Xd), "torch_csr": torch.tensor(Xd, device="cuda").to_sparse_csr()}[fmt]
+    dense = _csr_to_dense_on_device(Xs, torch.device("cuda"), torch.float64)
+    assert dense.shape == (n, d) and np.array_equal(dense.cpu().numpy(), Xd)
+    kw = dict(reg_param=1e-3, random_state=1, optimizer=optimizer, step_size=5e-2, valset_frac=None, verbose=False, batches_per_epoch=7, nepochs=2,
+              mem_size=4)
+    if optimizer == "adaQN":
+        kw.update(bfgs_upd_freq=3, fisher_size=6, max_incr=None)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = StochasticLogisticRegression(**kw).fit(Xs, y)
+        b = StochasticLogisticRegression(**kw).fit(Xd, y)
+    assert a.optimizer.niter == b.optimizer.niter
+    assert torch.equal(a.optimizer.x, b.optimizer.x)
+    pa, pb = a.predict(Xs), b.predict(Xd)
+    assert np.array_equal(np.asarray(pa.cpu() if hasattr(pa, "cpu") else pa), np.asarray(pb))

@@ -21,7 +21,7 @@ LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 
 SOURCES = ["stochqn_b200.cu", "callbacks.cu", "multinomial.cu"]
-DEPS = ["kernels.cuh", "kernels_small.cuh", "kernels_adaqn.cuh", "kernels_loop.cuh", "kernels_fit.cuh", "logistic_form.cuh", "p2p.cuh", "gemm_tf32_sm100.cuh", "vecio.cuh", "adaqn_impl.inc", "ext_impl.inc", "guided_impl.inc", "internal_rs.h",
+DEPS = ["kernels.cuh", "kernels_small.cuh", "kernels_adaqn.cuh", "kernels_loop.cuh", "kernels_fit.cuh", "mn_small.cuh", "logistic_form.cuh", "p2p.cuh", "gemm_tf32_sm100.cuh", "vecio.cuh", "adaqn_impl.inc", "ext_impl.inc", "guided_impl.inc", "internal_rs.h",
         os.path.join(REPO, "include", "stochqn.h"), os.path.join(REPO, "include", "stochqn_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-I" + os.path.join(REPO, "include"), "-I" + CSRC]

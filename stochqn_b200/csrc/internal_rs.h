@@ -12,3 +12,11 @@ struct StochqnRsPlan {
 int stochqn_b200_internal_rs_begin(void* comm, long long blk, StochqnRsPlan* out);
 // rank barrier on `st` (peer-memory flags; ncclAllReduce of one value as fallback)
 int stochqn_b200_internal_barrier(void* comm, cudaStream_t st);
+
+// multinomial.cu: where the one-launch small-batch gradient (mn_small.cuh) keeps its scratch inside a caller's `work` buffer for a
+// batch of B rows, and whether the shape qualifies on a grid of `grid` CTAs (ok = 1); smem = dynamic shared memory it needs
+struct StochqnMnSmallPlan {
+    size_t off_zp, off_dg, smem;
+    int ok;
+};
+void stochqn_b200_internal_mn_small_plan(long long B, long long d, long long K, int grid, StochqnMnSmallPlan* out);

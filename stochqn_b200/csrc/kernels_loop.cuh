@@ -23,6 +23,8 @@
 // the last bit given the same coefficients.
 #pragma once
 
+#include "mn_small.cuh"
+
 namespace sqn {
 
 struct LoopState {
@@ -369,19 +371,44 @@ __device__ __forceinline__ void reduce_entry_major(const double* __restrict__ re
     __syncthreads();
 }
 
+// the ring / Fisher counters and the tallies of a device-side adaQN loop, carried in registers by every CTA
+struct AdaRing {
+    int used, slot, pend, f_used, f_st;
+    int last_status, last_info;
+    unsigned long long n_ok, n_nan, calls, x_changed;
+};
+
+__device__ __forceinline__ AdaRing ada_ring_load(const LoopState* st)
+{
+    AdaRing R;
+    R.used = st->used; R.slot = st->st_ix; R.pend = st->pend; R.f_used = st->fisher_used; R.f_st = st->fisher_st;
+    R.last_status = st->last_status; R.last_info = st->last_info;
+    R.n_ok = 0; R.n_nan = 0; R.calls = 0; R.x_changed = 0;
+    return R;
+}
+
+__device__ __forceinline__ void ada_ring_store(LoopState* st, const AdaRing& R)       // one thread of one CTA, after the last barrier
+{
+    st->used = R.used; st->st_ix = R.slot; st->pend = R.pend; st->fisher_used = R.f_used; st->fisher_st = R.f_st;
+    st->last_status = R.last_status; st->last_info = R.last_info;
+    st->n_info[0] += R.n_ok; st->n_info[3] += R.n_nan; st->calls += R.calls; st->x_changed += R.x_changed;
+}
+
+// Whole-grid function: every CTA of a cooperative grid of kAdaThreads-thread CTAs calls it with the same arguments and the same
+// ring state `R` (updated in place, identically everywhere).  `ada_smem`: dynamic shared memory, 2 * ceil(n / grid) elements.
 template <typename T, int MMAX>
-__global__ void __launch_bounds__(kAdaThreads, 1)
-kl_ada(const AdaLoopArgs A, LoopState* __restrict__ st, const T* g, T* gout, T* __restrict__ Gacc,
+__device__ __forceinline__ void kl_ada_body(const AdaLoopArgs& A, AdaRing& R, const T* g, T* gout, T* __restrict__ Gacc,
        const T* __restrict__ S, const T* __restrict__ Y, T* __restrict__ F, T* __restrict__ x, T* __restrict__ x_sum, const T step,
-       double* partials, double* rec2, double* SY, double* YY, double* SS, unsigned long long* bar, unsigned long long* trace)
+       double* partials, double* rec2, double* SY, double* YY, double* SS, unsigned long long* bar, unsigned long long* trace,
+       unsigned char* ada_smem)
 {
     const int m = A.msize;
-    const int used = st->used, slot = st->st_ix, c = st->pend;
+    const int used = R.used, slot = R.slot, c = R.pend;
     auto stamp = [&](int k) {                                // development aid (stochqn_b200_debug_fit_trace)
         if (trace && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[k] = t; }
     };
     stamp(0);
-    const int f_used = st->fisher_used, f_st = st->fisher_st;
+    const int f_used = R.f_used, f_st = R.f_st;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = (int) gridDim.x, b = (int) blockIdx.x;
     constexpr int NW = kAdaThreads / 32;
@@ -397,7 +424,6 @@ kl_ada(const AdaLoopArgs A, LoopState* __restrict__ st, const T* g, T* gout, T* 
     const T* yc = c >= 0 ? Y + (size_t) c * A.ld : nullptr;
     const T* sc = c >= 0 ? S + (size_t) c * A.ld : nullptr;
 
-    extern __shared__ __align__(16) unsigned char ada_smem[];
     T* g_s = reinterpret_cast<T*>(ada_smem);                  // this CTA's slice of g and of h = g / sqrt(G + eps): computed once in
     T* h_s = g_s + per;                                        // phase A, read by B and C (the divide + square root are ~100 fp64 issue slots)
     __shared__ double sums1[2 * kMaxMem + 4], sums2[kMaxMem + 1], coef_s[2 * kMaxMem + 3], two_s[2];
@@ -412,7 +438,7 @@ kl_ada(const AdaLoopArgs A, LoopState* __restrict__ st, const T* g, T* gout, T* 
         for (int r = 0; r < MMAX; ++r) { a_p[r] = 0; a_c[r] = 0; }
         for (long long i = e0 + tid; i < e1; i += kAdaThreads) {
             T rv[MMAX];
-            const T gv = g[i];
+            const T gv = __ldcg(g + i);                  // (other CTAs of a persistent grid may have written it: L2, not a stale L1 line)
             T Gv = Gacc[i];
             #pragma unroll
             for (int r = 0; r < MMAX; ++r) rv[r] = r < used ? S[(size_t) r * A.ld + i] : (T) 0;
@@ -637,24 +663,73 @@ kl_ada(const AdaLoopArgs A, LoopState* __restrict__ st, const T* g, T* gout, T* 
     }
 
     if (trace) { __syncthreads(); stamp(8); }
-    if (b == 0 && tid == 0) {
-        st->last_status = status;
-        st->calls += 1;
-        if (A.fisher_size > 0) {                             // add_to_fisher_mem (stochqn.c:581-587)
-            st->fisher_st = (f_st + 1) % A.fisher_size;
-            st->fisher_used = f_used + 1 >= A.fisher_size ? A.fisher_size : f_used + 1;
-        }
-        if (status == ST_ACCEPT) {
-            st->pend = -1;
-            st->n_info[0] += 1;
-            st->x_changed += 1;
-            st->last_info = 200;
-        } else {
-            st->used = 0; st->st_ix = 0; st->pend = -1;
-            st->n_info[3] += 1;
-            st->last_info = 203;
-        }
+    R.last_status = status;
+    R.calls += 1;
+    if (A.fisher_size > 0) {                                 // add_to_fisher_mem (stochqn.c:581-587)
+        R.f_st = (f_st + 1) % A.fisher_size;
+        R.f_used = f_used + 1 >= A.fisher_size ? A.fisher_size : f_used + 1;
     }
+    if (status == ST_ACCEPT) {
+        R.pend = -1;
+        R.n_ok += 1; R.x_changed += 1; R.last_info = 200;
+    } else {
+        R.used = 0; R.slot = 0; R.pend = -1;                 // flush_bfgs_mem (stochqn.c:554-558)
+        R.n_nan += 1; R.last_info = 203;
+    }
+}
+
+template <typename T, int MMAX>
+__global__ void __launch_bounds__(kAdaThreads, 1)
+kl_ada(const AdaLoopArgs A, LoopState* __restrict__ st, const T* g, T* gout, T* __restrict__ Gacc,
+       const T* __restrict__ S, const T* __restrict__ Y, T* __restrict__ F, T* __restrict__ x, T* __restrict__ x_sum, const T step,
+       double* partials, double* rec2, double* SY, double* YY, double* SS, unsigned long long* bar, unsigned long long* trace)
+{
+    extern __shared__ __align__(16) unsigned char ada_dyn_smem[];
+    AdaRing R = ada_ring_load(st);
+    kl_ada_body<T, MMAX>(A, R, g, gout, Gacc, S, Y, F, x, x_sum, step, partials, rec2, SY, YY, SS, bar, trace, ada_dyn_smem);
+    // (every CTA passed at least one grid barrier after reading the record)
+    if (blockIdx.x == 0 && threadIdx.x == 0) ada_ring_store(st, R);
+}
+
+// ---- adaQN + multinomial model: a RUN of ordinary mini-batches in one persistent launch --------------------------------------
+// gradient of mini-batch ib (mn_grad_small_body, mn_small.cuh) -> barrier -> adaQN step (kl_ada_body) -> barrier -> next.
+// The two bodies use the dynamic shared memory one after the other.  stochqn/_optimizers.py:339-382 for the common path.
+template <typename T>
+struct MnFitArgs {
+    const T* X; long long ldx;          // first row of the first mini-batch
+    const T* Y; long long ldy;          // one-hot labels
+    const T* sw;                        // or nullptr
+    long long batch_rows, rows_total;
+    int nbatches, d, K, icpt;
+    T alpha;
+    T* Zp; T* Dg;                       // scratch of mn_grad_small
+};
+
+template <typename T, int MMAX>
+__global__ void __launch_bounds__(kAdaThreads, 1)
+kl_fit_mn_ada(const MnFitArgs<T> F, const AdaLoopArgs A, LoopState* __restrict__ st, T* g, T* __restrict__ Gacc,
+              const T* __restrict__ S, const T* __restrict__ Y, T* __restrict__ Fm, T* x, T* __restrict__ x_sum, const T step,
+              double* partials, double* rec2, double* SY, double* YY, double* SS, unsigned long long* bar, unsigned long long* trace)
+{
+    extern __shared__ __align__(16) unsigned char fit_dyn_smem[];
+    AdaRing R = ada_ring_load(st);
+    for (int ib = 0; ib < F.nbatches; ++ib) {
+        const long long r0 = (long long) ib * F.batch_rows;
+        const long long rows = F.rows_total - r0 < F.batch_rows ? F.rows_total - r0 : F.batch_rows;
+        mnsmall::MnSmallArgs<T> ma;
+        ma.X = F.X + (size_t) r0 * (size_t) F.ldx; ma.ldx = F.ldx;
+        ma.Y = F.Y + (size_t) r0 * (size_t) F.ldy; ma.ldy = F.ldy;
+        ma.labels = nullptr;
+        ma.sw = F.sw ? F.sw + r0 : nullptr;
+        ma.B = (int) rows; ma.d = F.d; ma.K = F.K; ma.icpt = F.icpt;
+        ma.W = x; ma.alpha = F.alpha; ma.Gout = g; ma.Zp = F.Zp; ma.Dg = F.Dg;
+        mnsmall::mn_grad_small_body<T>(ma, fit_dyn_smem, [&]() { fit_barrier(bar); }, nullptr);
+        fit_barrier(bar);                                    // the gradient is complete
+        kl_ada_body<T, MMAX>(A, R, g, (T*) nullptr, Gacc, S, Y, Fm, x, x_sum, step, partials, rec2, SY, YY, SS, bar,
+                             ib == F.nbatches - 1 ? trace : nullptr, fit_dyn_smem);
+        fit_barrier(bar);                                    // x is complete
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) ada_ring_store(st, R);
 }
 
 }  // namespace sqn

@@ -193,7 +193,11 @@ struct Ctx {
     int fused_fit = 1;                  // 0: never (option FUSED_FIT)
     unsigned long long* fit_bar = nullptr;    // its grid-barrier counter
     unsigned long long* ada_bar = nullptr;    // grid-barrier words of kl_ada (its grid depends on n)
-    bool ada_attr_set = false;
+    bool ada_attr_set = false, mnfit_attr_set = false;
+    // run_adaQN: the step of the pending call (take_step, Fisher ring write, niter) was already taken by a device-loop kernel;
+    // only what follows it at a pair boundary (stochqn.c:1196-1239) is left to do.  Set by stochqn_b200_fit_batches.
+    bool ada_step_done = false;
+    int ada_step_changed_x = 0;
     void* fit_work = nullptr;           // the model's scratch buffer (partial column records)
     double fit_steps = 0;               // mini-batches served by it
     unsigned long long* fit_trace = nullptr;   // development aid (stochqn_b200_debug_fit_trace)
@@ -539,6 +543,9 @@ int launch_finalize(Ctx* c, int nblocks, int count, volatile double* host_dst, i
         COUNT_LAUNCH();
         if (int r = allreduce_sums(c, c->sums, (size_t) count)) return r;
         if (host_dst) { k_publish<<<1, 32, 0, c->stream>>>(c->sums, count, host_dst, seq_dst, seq); COUNT_LAUNCH(); }
+    } else if (!sharded && !host_dst && count > 2 * kWarps) {
+        k_finalize_wide<<<(unsigned) ((count + kWarps - 1) / kWarps), kThreads, 0, c->stream>>>(c->partials, nblocks, count, c->sums);
+        COUNT_LAUNCH();
     } else {
         k_finalize<<<1, kThreads, 0, c->stream>>>(c->partials, nblocks, count, c->sums, pa, host_dst, seq_dst, seq);
         COUNT_LAUNCH();

@@ -172,3 +172,79 @@ def test_adaqn_one_launch_steps_match_the_host_driven_loop(kind, n, batch, nbatc
         assert a[k] == b[k], (k, a[k], b[k])
     assert np.all(np.isfinite(a["x"]))
     assert np.max(np.abs(a["x"] - b["x"])) <= 1e-10 * max(np.max(np.abs(b["x"])), 1e-300)
+
+
+def _run_multinomial(kind, d, K, batch, nbatches, loop_max_n, fused, chunk, mem=5, L=4, short_tail=0, weights=True):
+    """adaQN on the multinomial model (model 2: one-hot labels, intercept last) through stochqn_b200_fit_batches."""
+    import torch
+    abi = _lib.load(np.float64)
+    lib = abi.lib
+    n = K * (d + 1)
+    nrows = batch * nbatches - short_tail
+    g = torch.Generator(device="cuda").manual_seed(21)
+    X = torch.randn(nrows, d, device="cuda", dtype=torch.float64, generator=g) / d ** 0.5
+    lab = torch.randint(0, K, (nrows,), device="cuda", generator=g)
+    Y = torch.zeros(nrows, K, device="cuda", dtype=torch.float64)
+    Y[torch.arange(nrows, device="cuda"), lab] = 1.0
+    sw = (0.5 + torch.rand(nrows, device="cuda", dtype=torch.float64, generator=g)) / batch if weights else None
+    x = torch.randn(n, device="cuda", dtype=torch.float64, generator=g) * 0.1
+    big = batch * L
+    work = torch.empty(lib.stochqn_b200_multinomial_work_size(max(batch, big), d, K), device="cuda", dtype=torch.uint8)
+    fisher = 0 if kind == "adaQN_gd" else 7
+    ws = lib.initialize_adaQN(n, mem, fisher if fisher else 1, L, 0.0, 1e-4, 1e-4, 0.9 if kind == "adaQN_gd" else 0.0, 1 if kind == "adaQN_gd" else 0,
+                              0.0, 1, 1)
+    assert ws
+    assert lib.stochqn_b200_set_option(ws, _lib.OPT_DEVICE_LOOP_MAX_N, loop_max_n) == 0
+    assert lib.stochqn_b200_set_option(ws, _lib.OPT_FUSED_FIT, fused) == 0
+    req, req_vec, task, info = C.c_void_p(), C.c_void_p(), C.c_int(), C.c_int()
+    g0 = torch.zeros(n, device="cuda", dtype=torch.float64)
+    lib.run_adaQN(0.05, x.data_ptr(), 0.0, g0.data_ptr(), C.byref(req), C.byref(task), ws, C.byref(info))
+    M = abi.Model(2, 1, d, K, 1e-2, work.data_ptr())
+    data = _lib.Rows(X.data_ptr(), d, Y.data_ptr(), K, sw.data_ptr() if sw is not None else None, nrows)
+    rep = _lib.FitReport()
+    tally = dict(calls=0, n_info=[0, 0, 0, 0])
+    launches0 = _lib.launch_count()
+    b = 0
+    while b < nbatches:
+        cnt = min(chunk, nbatches - b)
+        LL = C.c_longlong * cnt
+        lf, lr = LL(), LL()
+        for i in range(cnt):
+            e = min((b + i + 1) * batch, nrows)
+            lr[i] = min(big, e)
+            lf[i] = e - lr[i]
+        rc = lib.stochqn_b200_fit_batches(ws, x.data_ptr(), 0.05, C.byref(M), C.byref(data), b * batch, batch, cnt, lf, lr, None,
+                                          C.byref(task), C.byref(req), C.byref(req_vec), C.byref(rep))
+        assert rc == 0, _lib.last_error(abi)
+        tally["calls"] += rep.calls
+        for i in range(4):
+            tally["n_info"][i] += rep.n_info[i]
+        b += cnt
+    torch.cuda.synchronize()
+    w = ws.contents
+    m = w.bfgs_memory.contents
+    fm = (int(w.fisher_memory.contents.mem_used), int(w.fisher_memory.contents.mem_st_ix)) if w.fisher_memory else (0, 0)
+    out = dict(tally, niter=int(w.niter), section=int(w.section), mem_used=int(m.mem_used), mem_st_ix=int(m.mem_st_ix), fisher=fm,
+               loop_steps=_lib.get_stat(abi, ws, _lib.STAT_DEVICE_LOOP_STEPS), fit_steps=_lib.get_stat(abi, ws, _lib.STAT_FUSED_FIT_STEPS),
+               launches=_lib.launch_count() - launches0, x=x.cpu().numpy())
+    lib.dealloc_adaQN(ws)
+    return out
+
+
+@pytest.mark.parametrize("kind", ["adaQN_fisher", "adaQN_gd"])
+@pytest.mark.parametrize("d,K,batch,short_tail", [(600, 130, 40, 0), (1836, 159, 50, 13), (333, 250, 17, 0)])
+def test_adaqn_multinomial_runs_in_one_launch(kind, d, K, batch, short_tail):
+    """adaQN + multinomial model: a run of ordinary mini-batches is ONE persistent launch (kl_fit_mn_ada = mn_grad_small + kl_ada
+    per mini-batch, csrc/kernels_loop.cuh), against two launches per mini-batch (FUSED_FIT off) and against the host-driven loop."""
+    a = _run_multinomial(kind, d, K, batch, 26, loop_max_n=1 << 19, fused=1, chunk=9, short_tail=short_tail)
+    b = _run_multinomial(kind, d, K, batch, 26, loop_max_n=1 << 19, fused=0, chunk=9, short_tail=short_tail)
+    c = _run_multinomial(kind, d, K, batch, 26, loop_max_n=0, fused=0, chunk=9, short_tail=short_tail)
+    # (the STEP of a boundary mini-batch is taken on the device too; what follows it - averaging, pair - is host work)
+    assert a["fit_steps"] == 26 and b["fit_steps"] == 0 and b["loop_steps"] == 26 and c["loop_steps"] == 0
+    assert a["launches"] < b["launches"] < c["launches"]
+    for k in ("calls", "n_info", "niter", "section", "mem_used", "mem_st_ix", "fisher"):
+        assert a[k] == c[k] and b[k] == c[k], (k, a[k], b[k], c[k])
+    assert a["mem_used"] > 0 and np.all(np.isfinite(a["x"]))
+    scale = max(np.max(np.abs(c["x"])), 1e-300)
+    assert np.max(np.abs(a["x"] - c["x"])) <= 1e-10 * scale
+    assert np.max(np.abs(b["x"] - c["x"])) <= 1e-10 * scale

@@ -44,6 +44,7 @@ def main():
     tr_ada = torch.zeros(16, device="cuda", dtype=torch.int64)
     mn_d, ada_d, step_us = [], [], []
     b0 = 0
+    assert lib.stochqn_b200_set_option(ws, _lib.OPT_FUSED_FIT, 0) == 0      # two launches per step: each kernel is traced on its own
     for it in range(16 * L):
         cnt = 1
         LL = C.c_longlong * cnt

@@ -298,10 +298,226 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
 }
 
+// =====================================================================================================================
+// The same product on CTA PAIRS (cta_group::2): two CTAs of a cluster on one TPC work on one 256 x 256 output tile.  Each
+// CTA stages ITS 128 rows of A and ITS 128 rows of B (one half of the tile's N) per k-block - 32 KB instead of 48 KB for the
+// same 128 x 256 share of the output, so a third less operand traffic from L2 (what limits the one-CTA kernel at 76 %
+// tensor-pipe activity) and six pipeline stages instead of four.  The leader CTA (cluster rank 0) issues
+// tcgen05.mma.cta_group::2 (M 256, N 256, K 8): every SM's tensor core multiplies its own A rows by both halves of B, read from
+// both CTAs' shared memory, into its own 128 lanes x 256 columns of tensor memory.
+//   full[s]       lives in the LEADER: both CTAs' TMA copies complete_tx on it (the peer addresses it with mapa)
+//   empty[s]      one per CTA, released by tcgen05.commit.multicast (mask 0b11) once the MMAs have read the stage
+//   acc_full[a]   one per CTA, same multicast commit after the last k-block
+//   acc_empty[a]  lives in the leader, 8 arrivals: the four epilogue warps of each CTA
+// =====================================================================================================================
+constexpr int BN2 = 256;
+constexpr int STAGES2 = 6;
+constexpr uint32_t STAGE2_BYTES = 2 * A_BYTES;                         // A half + B half per CTA and stage
+constexpr int THREADS2 = 384;                                            // warps 0-3: TMA, MMA, TMEM allocation, idle; warps 4-11: epilogue
+constexpr int EPI_WARPS2 = 8;                                            // two warps per TMEM lane quadrant, alternating 32-column chunks
+constexpr size_t SMEM2_BYTES = (size_t) STAGES2 * STAGE2_BYTES + 1024 + 256 + 2 * EPI_BYTES;
+
+__device__ __forceinline__ uint32_t cluster_rank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank)      // shared::cluster address of `smem_addr` in CTA `rank`
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                 :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar)           // arrives on `bar` in BOTH CTAs of the pair
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "h"((uint16_t) 3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(bar_cluster_addr) : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_m(int bm, int bn)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (bn >> 3) << 17) | ((uint32_t) (bm >> 4) << 24);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1)
+gemm_tf32_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     float* __restrict__ C, long long ldc, int M, int N, int K,
+                     const float* __restrict__ addend, long long ld_add, float alpha)
+{
+    constexpr int BN = BN2, STAGES = STAGES2;
+    constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;                           // all 512 columns
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
+    unsigned char* tiles = smem;                                              // [STAGES][A half 16 KB | B half 16 KB]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t) STAGES * STAGE2_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* acc_full = empty + STAGES;
+    uint64_t* acc_empty = acc_full + ACC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+    float* epi = reinterpret_cast<float*>(smem + (size_t) STAGES * STAGE2_BYTES + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    const bool leader = rank == 0;
+    const int pair = (int) (blockIdx.x >> 1), npairs = (int) (gridDim.x >> 1);
+    const int tiles_m = (M + 2 * BM - 1) / (2 * BM), tiles_n = (N + BN - 1) / BN;
+    const int ntiles = tiles_m * tiles_n;
+    const int kblocks = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 2 * EPI_WARPS2); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();                                                       // barriers and tensor memory of BOTH CTAs are ready
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================= TMA producer (both CTAs; the transaction bytes land on the leader's barrier) =================
+            int s = 0; uint32_t ph = 0;
+            for (int t = pair; t < ntiles; t += npairs) {
+                const int m0 = (t / tiles_n) * (2 * BM) + (int) rank * BM;
+                const int n0 = (t % tiles_n) * BN + (int) rank * (BN / 2);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    if (leader) mbar_expect_tx(&full[s], 2 * STAGE2_BYTES);
+                    const uint32_t bar = map_to_cta(smem_u32(&full[s]), 0);
+                    unsigned char* a_dst = tiles + (size_t) s * STAGE2_BYTES;
+                    tma_load_2d_2sm(a_dst, &map_a, bar, kb * BK, m0);
+                    tma_load_2d_2sm(a_dst + A_BYTES, &map_b, bar, kb * BK, n0);
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            // ================= MMA issuer (leader CTA only) =================
+            constexpr uint32_t idesc = make_idesc_m(2 * BM, BN);
+            int s = 0; uint32_t ph = 0;
+            int as = 0; uint32_t aph = 0;
+            for (int t = pair; t < ntiles; t += npairs) {
+                mbar_wait(&acc_empty[as], aph ^ 1u);                 // both CTAs' epilogues have drained this accumulator stage
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t) (as * BN);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(tiles + (size_t) s * STAGE2_BYTES);
+                    const uint32_t b_addr = a_addr + A_BYTES;
+                    #pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t da = make_desc(a_addr + (uint32_t) (k * UMMA_K * 4));
+                        const uint64_t db = make_desc(b_addr + (uint32_t) (k * UMMA_K * 4));
+                        mma_tf32_2sm(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit_2sm(&empty[s]);                      // the stage is free in both CTAs once these MMAs have read it
+                    if (kb == kblocks - 1) umma_commit_2sm(&acc_full[as]);
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
+                }
+                if (++as == ACC_STAGES) { as = 0; aph ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue (each CTA drains its own 128 rows x 256 columns) =================
+        const int q = warp & 3;                                      // TMEM lane quadrant this warp may read
+        const int half = (warp - 4) >> 2;                            // which of the two warps of the quadrant
+        int as = 0; uint32_t aph = 0;
+        const uint32_t acc_empty_leader0 = map_to_cta(smem_u32(&acc_empty[0]), 0);
+        for (int t = pair; t < ntiles; t += npairs) {
+            const int m0 = (t / tiles_n) * (2 * BM) + (int) rank * BM, n0 = (t % tiles_n) * BN;
+            mbar_wait(&acc_full[as], aph);
+            tc_fence_after();
+            float* stage = epi + (size_t) (warp - 4) * 32 * EPI_LD;
+            #pragma unroll 1
+            for (int c = half * 32; c < BN; c += 64) {
+                uint32_t v[32];
+                float ad[32];
+                const int col = n0 + c + lane;
+                if (addend) {
+                    #pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        const int row = m0 + q * 32 + r;
+                        ad[r] = (row < M && col < N) ? __ldg(addend + (long long) row * ld_add + col) : 0.f;
+                    }
+                }
+                const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (as * BN + c);
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                               "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                               "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                             : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                #pragma unroll
+                for (int j = 0; j < 32; ++j) stage[lane * EPI_LD + j] = __uint_as_float(v[j]);
+                __syncwarp();
+                if (addend) {
+                    #pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        const int row = m0 + q * 32 + r;
+                        if (row < M && col < N) C[(long long) row * ldc + col] = fmaf(alpha, ad[r], stage[r * EPI_LD + lane]);
+                    }
+                } else {
+                    #pragma unroll 4
+                    for (int r = 0; r < 32; ++r) {
+                        const int row = m0 + q * 32 + r;
+                        if (row < M && col < N) C[(long long) row * ldc + col] = stage[r * EPI_LD + lane];
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_empty_leader0 + (uint32_t) (as * sizeof(uint64_t)));
+            if (++as == ACC_STAGES) { as = 0; aph ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();                                    // nobody leaves (or frees tensor memory) while the pair still works
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------
 struct Host {
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     int sms = 0;
+    int max_pairs = 0;            // CTA pairs (clusters of 2) of the 2-SM kernel that can be resident at once; 0: kernel not usable
     bool ok = false;
     bool tried = false;
 };
@@ -325,6 +541,16 @@ inline Host& host()
     if (cudaFuncSetAttribute(gemm_tf32_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Cfg<128>::SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(gemm_tf32_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Cfg<256>::SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); return h; }
     h.ok = true;
+    if (cudaFuncSetAttribute(gemm_tf32_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM2_BYTES) == cudaSuccess) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned) (h.sms & ~1)); cfg.blockDim = dim3(THREADS2); cfg.dynamicSmemBytes = SMEM2_BYTES;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, gemm_tf32_2sm_kernel, &cfg) == cudaSuccess && nc > 0) h.max_pairs = nc;
+    }
+    cudaGetLastError();
     return h;
 }
 
@@ -363,6 +589,26 @@ inline int sm100_gemm_tf32(const float* A, long long lda, const float* B, long l
     if (!h.ok) return 1;
     static int force_bn = -1;
     if (force_bn < 0) { const char* e = getenv("STOCHQN_B200_GEMM_BN"); force_bn = e ? atoi(e) : 0; }      // dev switch
+    static int use_2sm = -1;
+    if (use_2sm < 0) { const char* e = getenv("STOCHQN_B200_GEMM_2SM"); use_2sm = e ? atoi(e) : 1; }                 // dev switch
+    const bool no_scatter = !scatter || scatter->world <= 1;
+    if (use_2sm && h.max_pairs > 0 && no_scatter && force_bn == 0 && M >= 256 && N >= 256) {
+        // CTA pairs on 256 x 256 tiles whenever they give most pairs work
+        const long long nt = (long long) ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN2 - 1) / BN2);
+        if (nt * 4 >= (long long) h.max_pairs * 3 || use_2sm == 2) {
+            CUtensorMap ma2, mb2;
+            if (make_map(h, &ma2, A, lda, M, K, BM) && make_map(h, &mb2, B, ldb, N, K, BN2 / 2)) {
+                const int pairs = (int) (nt < h.max_pairs ? nt : h.max_pairs);
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned) (2 * pairs)); cfg.blockDim = dim3(THREADS2); cfg.dynamicSmemBytes = SMEM2_BYTES; cfg.stream = st;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                if (cudaLaunchKernelEx(&cfg, gemm_tf32_2sm_kernel, ma2, mb2, C, ldc, M, N, K, addend, ld_add, alpha) == cudaSuccess) return 0;
+                cudaGetLastError();             // fall through to the one-CTA kernel
+            }
+        }
+    }
     const long long tiles_m = (M + BM - 1) / BM;
     // wide tiles when they still give every SM work (the wide kernel makes the same makespan with less L2 traffic)
     const bool wide = force_bn == 256 || (force_bn != 128 && N >= 256 && tiles_m * ((N + 255) / 256) >= (long long) h.sms * 3 / 4);

@@ -26,7 +26,8 @@
 //                its copy of the ring counters
 //
 // The ring counters live in registers of every CTA (all CTAs take identical decisions from identical sums); CTA 0
-// writes them to the LoopState record once, at the end.  Five grid barriers per oLBFGS iteration, none of them a launch.
+// writes them to the LoopState record once, at the end.  The pair decision P rides on the first barrier of the NEXT
+// mini-batch (whose row sweep does not depend on it): four grid barriers per oLBFGS iteration, none of them a launch.
 // Data written by one CTA and read by another inside the launch (x, the records, the Gram state) is read with
 // ld.global.cg: L1 is not coherent across SMs.  S / Y / x_sum slices are only ever touched by their owner.
 #pragma once
@@ -232,6 +233,39 @@ kl_fit_logistic(const FitArgs<T> F, const LoopArgs A, LoopState* __restrict__ st
         }
     };
 
+    // ---- P: check_min_curvature (stochqn.c:883-900) on the sums of the 2-value records, quirk Q1 on rejection, ring advance.
+    // Every CTA takes the same decision from the same sums; call it after a grid barrier that follows the records.
+    bool pair_pending = false;
+    auto pair_decision = [&]() {
+        if (warp < 2) {
+            double v = 0;
+            for (int r = lane; r < G; r += 32) v += __ldcg(rec2 + (size_t) r * 2 + warp);
+            v = warp_sum(v);
+            if (lane == 0) two_s[warp] = v;
+        }
+        __syncthreads();
+        const bool reject = A.min_curvature > 0 && (two_s[0] / two_s[1]) <= A.min_curvature;
+        calls += 1;
+        if (reject) {                                             // quirk Q1: the slot is zeroed, the counters stay
+            if (tid < ne) { S[(size_t) slot * A.ld + e0 + tid] = (T) 0; Y[(size_t) slot * A.ld + e0 + tid] = (T) 0; }
+            if (b == 0) {
+                for (int j = tid; j < m; j += kFitThreads) {
+                    SY[j * m + slot] = 0; SY[slot * m + j] = 0;
+                    YY[j * m + slot] = 0; YY[slot * m + j] = 0;
+                }
+                if (tid == 0) SS[slot] = 0;
+            }
+            n_curv += 1; last_info = 202;
+        } else {
+            pend = slot;
+            slot = (slot + 1) % m;                                // incr_bfgs_counters (stochqn.c:569-573)
+            used = used + 1 >= m ? m : used + 1;
+            n_ok += 1; last_info = 200;
+        }
+        pair_pending = false;
+        __syncthreads();                                          // two_s is reused
+    };
+
     for (int ib = 0; ib < F.nbatches; ++ib) {
         stamp(ib, 0);
         const long long r0 = (long long) ib * F.batch_rows;
@@ -244,6 +278,7 @@ kl_fit_logistic(const FitArgs<T> F, const LoopArgs A, LoopState* __restrict__ st
         stamp(ib, 1);
         fit_barrier(bar);
         stamp(ib, 2);
+        if (pair_pending) pair_decision();                        // the previous mini-batch's pair
         col_phase();
         stamp(ib, 3);
 
@@ -403,35 +438,14 @@ kl_fit_logistic(const FitArgs<T> F, const LoopArgs A, LoopState* __restrict__ st
             __syncthreads();
             if (tid == 0) { rec2[(size_t) b * 2] = part[0][0] + part[0][1]; rec2[(size_t) b * 2 + 1] = part[1][0] + part[1][1]; }
             stamp(ib, 10);
-            fit_barrier(bar);
-            if (warp < 2) {
-                double v = 0;
-                for (int r = lane; r < G; r += 32) v += __ldcg(rec2 + (size_t) r * 2 + warp);
-                v = warp_sum(v);
-                if (lane == 0) two_s[warp] = v;
-            }
-            __syncthreads();
-            stamp(ib, 11);
-            const bool reject = A.min_curvature > 0 && (two_s[0] / two_s[1]) <= A.min_curvature;
-            calls += 1;
-            if (reject) {                                         // quirk Q1: the slot is zeroed, the counters stay
-                if (tid < ne) { S[(size_t) slot * A.ld + e0 + tid] = (T) 0; Y[(size_t) slot * A.ld + e0 + tid] = (T) 0; }
-                if (b == 0) {
-                    for (int j = tid; j < m; j += kFitThreads) {
-                        SY[j * m + slot] = 0; SY[slot * m + j] = 0;
-                        YY[j * m + slot] = 0; YY[slot * m + j] = 0;
-                    }
-                    if (tid == 0) SS[slot] = 0;
-                }
-                n_curv += 1; last_info = 202;
-            } else {
-                pend = slot;
-                slot = (slot + 1) % m;                            // incr_bfgs_counters (stochqn.c:569-573)
-                used = used + 1 >= m ? m : used + 1;
-                n_ok += 1; last_info = 200;
-            }
-            __syncthreads();                                      // two_s / part are reused by the next mini-batch
+            // The decision needs the sums over all CTAs, but nothing before the NEXT mini-batch's column phase depends on it (its row
+            // sweep only reads x): it rides on that mini-batch's first barrier (pair_decision below) - four barriers per iteration.
+            pair_pending = true;
         }
+    }
+    if (pair_pending) {                                           // the last pair of the run
+        fit_barrier(bar);
+        pair_decision();
     }
 
     if (b == 0 && tid == 0) {

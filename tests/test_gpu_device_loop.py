@@ -157,7 +157,7 @@ def test_fused_run_in_single_precision():
 
 @pytest.mark.parametrize("kind", ["adaQN_fisher", "adaQN_gd", "adaQN_incr"])
 @pytest.mark.parametrize("n,batch,nbatches,mem", [(37, 64, 45, 5), (1001, 64, 45, 5), (5000, 32, 45, 12), (30011, 16, 26, 14)])
-@pytest.mark.parametrize("factor", [0.0, 3.0])
+@pytest.mark.parametrize("factor", [0.0, 0.5, 3.0])
 def test_adaqn_one_launch_steps_match_the_host_driven_loop(kind, n, batch, nbatches, mem, factor):
     """The ordinary steps of adaQN as ONE launch each (kl_ada, csrc/kernels_loop.cuh: stochqn.c:802-840 with 720-783) inside
     stochqn_b200_fit_batches, against the five-launch host-driven route: same tallies, ring and Fisher counters, iterate.
@@ -174,7 +174,7 @@ def test_adaqn_one_launch_steps_match_the_host_driven_loop(kind, n, batch, nbatc
     assert np.max(np.abs(a["x"] - b["x"])) <= 1e-10 * max(np.max(np.abs(b["x"])), 1e-300)
 
 
-def _run_multinomial(kind, d, K, batch, nbatches, loop_max_n, fused, chunk, mem=5, L=4, short_tail=0, weights=True):
+def _run_multinomial(kind, d, K, batch, nbatches, loop_max_n, fused, chunk, mem=5, L=4, short_tail=0, weights=True, min_curv=1e-4):
     """adaQN on the multinomial model (model 2: one-hot labels, intercept last) through stochqn_b200_fit_batches."""
     import torch
     abi = _lib.load(np.float64)
@@ -191,7 +191,7 @@ def _run_multinomial(kind, d, K, batch, nbatches, loop_max_n, fused, chunk, mem=
     big = batch * L
     work = torch.empty(lib.stochqn_b200_multinomial_work_size(max(batch, big), d, K), device="cuda", dtype=torch.uint8)
     fisher = 0 if kind == "adaQN_gd" else 7
-    ws = lib.initialize_adaQN(n, mem, fisher if fisher else 1, L, 0.0, 1e-4, 1e-4, 0.9 if kind == "adaQN_gd" else 0.0, 1 if kind == "adaQN_gd" else 0,
+    ws = lib.initialize_adaQN(n, mem, fisher if fisher else 1, L, 0.0, min_curv, 1e-4, 0.9 if kind == "adaQN_gd" else 0.0, 1 if kind == "adaQN_gd" else 0,
                               0.0, 1, 1)
     assert ws
     assert lib.stochqn_b200_set_option(ws, _lib.OPT_DEVICE_LOOP_MAX_N, loop_max_n) == 0
@@ -248,3 +248,17 @@ def test_adaqn_multinomial_runs_in_one_launch(kind, d, K, batch, short_tail):
     scale = max(np.max(np.abs(c["x"])), 1e-300)
     assert np.max(np.abs(a["x"] - c["x"])) <= 1e-10 * scale
     assert np.max(np.abs(b["x"] - c["x"])) <= 1e-10 * scale
+
+
+def test_adaqn_multinomial_run_with_rejected_pairs():
+    """The same with a curvature threshold nobody passes after the memory filled once: quirk Q1 zeroes slots of the full memory, the next
+    direction is not finite, the kernel rejects it on the device (x_sum += x, flush) and carries on - tallies and iterate as the host-driven loop."""
+    kw = dict(d=600, K=130, batch=40, nbatches=40, chunk=11, mem=3, L=2)
+    a = _run_multinomial("adaQN_gd", loop_max_n=1 << 19, fused=1, min_curv=1e6, **kw)
+    c = _run_multinomial("adaQN_gd", loop_max_n=0, fused=0, min_curv=1e6, **kw)
+    assert a["fit_steps"] == 40 and c["loop_steps"] == 0
+    assert c["n_info"][2] > 0, "the forced curvature rejections did not happen"
+    for k in ("calls", "n_info", "niter", "section", "mem_used", "mem_st_ix"):
+        assert a[k] == c[k], (k, a[k], c[k])
+    assert np.all(np.isfinite(a["x"]))
+    assert np.max(np.abs(a["x"] - c["x"])) <= 1e-10 * max(np.max(np.abs(c["x"])), 1e-300)

@@ -1,16 +1,12 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_device_loop.py tests/test_gpu_logistic_estimator.py tests/test_gpu_guided.py tests/test_gpu_callbacks.py -x -q > gpurun_out/pytest_fit.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_fit.log
-for cfg in cfg1 cfg2; do timeout 120 python tools/probe_fit.py $cfg; done
-for f in 1 0; do
-  echo "== FUSED_FIT=$f"
-  STOCHQN_B200_FUSED_FIT=$f timeout 300 python tools/bench_configs.py cfg1d cfg2d --steps 2000 --rows-cfg2 200000 2>&1 | python -c "
+timeout 600 python -m pytest --timeout=60 tests/test_gpu_device_loop.py tests/test_gpu_logistic_estimator.py tests/test_gpu_guided.py -x -q > gpurun_out/pytest_fit.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_fit.log
+for cfg in cfg1 cfg2; do timeout 120 python tools/probe_fit.py $cfg | cut -c1-700; done
+timeout 300 python tools/bench_configs.py cfg1d cfg2d --steps 2000 --rows-cfg2 200000 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):
         d=json.loads(l); print(d['config'], d['loop'][:30], 'steps/s %.0f'%d['steps_per_s'], 'us/step %.1f'%(d['ms_per_step']*1e3), 'launches/step %.2f'%d['launches_per_step'], 'loss %.5f'%d['loss_after'], d['infos'])
     else: print(l.rstrip()[:300])
 "
-done
-timeout 120 python tools/probe_logistic.py 2>&1 | tail -12

@@ -15,8 +15,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from stochqn_b200 import _lib
 
-NAMES = ["R rows", "barrier 1", "C columns", "dots", "barrier 2", "S reduce+solve+update", "barrier 3", "R' rows", "barrier 4 + C'", "pair partials",
-         "barrier 5 + decision"]
+NAMES = ["R rows", "barrier 1", "pair decision (previous mini-batch) + C columns", "dots", "barrier 2", "S reduce+solve+update", "barrier 3", "R' rows",
+         "barrier 4 + C'", "pair partials"]
 
 
 def main():
@@ -59,7 +59,7 @@ def main():
         assert rc == 0, _lib.last_error(abi)
         ms = e0.elapsed_time(e1)
     t = trace.cpu().numpy().reshape(nb, 16).astype(np.float64)
-    last = 11 if kind == "oLBFGS" else 7
+    last = 10 if kind == "oLBFGS" else 7
     dur = np.diff(t[:, :last + 1], axis=1)
     med = np.median(dur[nb // 4:], axis=0)
     inner = np.median(np.stack([t[:, 12] - t[:, 5], t[:, 13] - t[:, 12], t[:, 14] - t[:, 13], t[:, 6] - t[:, 14]], axis=1)[nb // 4:], axis=0)

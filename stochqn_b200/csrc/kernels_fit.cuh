@@ -244,7 +244,7 @@ kl_fit_logistic(const FitArgs<T> F, const LoopArgs A, LoopState* __restrict__ st
             if (lane == 0) two_s[warp] = v;
         }
         __syncthreads();
-        const bool reject = A.min_curvature > 0 && (two_s[0] / two_s[1]) <= A.min_curvature;
+        const bool reject = A.min_curvature > 0 && ((T) two_s[0] / (T) two_s[1]) <= (T) A.min_curvature;      // the division in T (stochqn.c:892)
         calls += 1;
         if (reject) {                                             // quirk Q1: the slot is zeroed, the counters stay
             if (tid < ne) { S[(size_t) slot * A.ld + e0 + tid] = (T) 0; Y[(size_t) slot * A.ld + e0 + tid] = (T) 0; }

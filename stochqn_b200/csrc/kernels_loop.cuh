@@ -242,8 +242,8 @@ kl_pair(LoopArgs A, LoopState* __restrict__ st, const T* __restrict__ g, const T
     block_sum2_to(a_sy, a_ss, rec2 + (size_t) blockIdx.x * 2);
     grid_barrier_auto(bar);
     reduce2_all(rec2, two_s);
-    // check_min_curvature (stochqn.c:883-900), in the precision the host route uses
-    const bool reject = A.min_curvature > 0 && (two_s[0] / two_s[1]) <= A.min_curvature;
+    // check_min_curvature (stochqn.c:883-900): the division in T, as the reference's (and as the host route)
+    const bool reject = A.min_curvature > 0 && ((T) two_s[0] / (T) two_s[1]) <= (T) A.min_curvature;
     if (reject) {
         for (long long i = e0 + threadIdx.x; i < e1; i += nthr) { s[i] = (T) 0; y[i] = (T) 0; }    // quirk Q1
         if (blockIdx.x == 0) {

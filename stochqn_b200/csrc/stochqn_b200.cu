@@ -874,8 +874,8 @@ int curvature_decision(Ctx* c, bfgs_mem* m, double sy, double ss, info_enum* inf
 {
     const int slot = (int) m->mem_st_ix;
     if (m->min_curvature > 0) {
-        const double curv = sy / ss;
-        if (curv <= (double) m->min_curvature) {
+        const real_t curv = (real_t) sy / (real_t) ss;            // the reference divides in real_t (stochqn.c:892); the sums are fp64
+        if (curv <= m->min_curvature) {
             // rollback_corr_pair copies the never-written (zero) backup over the slot (stochqn.c:597-604)
             CUDA_TRY(cudaMemsetAsync(m->s_mem + (size_t) slot * c->ld, 0, (size_t) c->n * sizeof(real_t), c->stream));
             CUDA_TRY(cudaMemsetAsync(m->y_mem + (size_t) slot * c->ld, 0, (size_t) c->n * sizeof(real_t), c->stream));

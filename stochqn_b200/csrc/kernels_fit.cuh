@@ -86,6 +86,7 @@ kl_fit_logistic(const FitArgs<T> F, const LoopArgs A, LoopState* __restrict__ st
     const T nstep = -step;
     const T y_reg = (T) A.y_reg;
 
+    RunBarrier barrier{bar, 0ull};                             // (the host zeroes the counter before every launch of this kernel)
     int used = st->used, slot = st->st_ix, pend = st->pend;
     int last_info = st->last_info, last_status = st->last_status;
     unsigned long long n_ok = 0, n_curv = 0, n_nan = 0, calls = 0, x_changed = 0;
@@ -276,7 +277,7 @@ kl_fit_logistic(const FitArgs<T> F, const LoopArgs A, LoopState* __restrict__ st
 
         row_phase(Xb, yb, swb, rows);
         stamp(ib, 1);
-        fit_barrier(bar);
+        barrier();
         stamp(ib, 2);
         if (pair_pending) pair_decision();                        // the previous mini-batch's pair
         col_phase();
@@ -330,7 +331,7 @@ kl_fit_logistic(const FitArgs<T> F, const LoopArgs A, LoopState* __restrict__ st
             if (MODE == MODE_OLBFGS && tid < ne) gp_s[tid] = g_s[tid];                  // grad_prev <- grad (stochqn.c:996)
         }
         stamp(ib, 4);
-        fit_barrier(bar);
+        barrier();
         stamp(ib, 5);
 
         // ---- S: every CTA reduces the records in the same order, solves, decides, updates its slice ----
@@ -373,7 +374,7 @@ kl_fit_logistic(const FitArgs<T> F, const LoopArgs A, LoopState* __restrict__ st
             }
             __syncthreads();
             if (tid == 0) { rec2[(size_t) b * 2] = part[0][0] + part[0][1]; rec2[(size_t) b * 2 + 1] = part[1][0] + part[1][1]; }
-            fit_barrier(bar);
+            barrier();
             if (warp < 2) {
                 double v = 0;
                 for (int r = lane; r < G; r += 32) v += __ldcg(rec2 + (size_t) r * 2 + warp);
@@ -409,7 +410,7 @@ kl_fit_logistic(const FitArgs<T> F, const LoopArgs A, LoopState* __restrict__ st
             n_nan += 1; last_info = 203;
         }
         stamp(ib, 6);
-        fit_barrier(bar);                                  // x is complete
+        barrier();                                  // x is complete
         stamp(ib, 7);
 
         if (MODE != MODE_OLBFGS || status != ST_ACCEPT) continue;
@@ -417,7 +418,7 @@ kl_fit_logistic(const FitArgs<T> F, const LoopArgs A, LoopState* __restrict__ st
         // ---- R', C', P: the pair (stochqn.c:915-926, 883-900) ----
         row_phase(Xb, yb, swb, rows);
         stamp(ib, 8);
-        fit_barrier(bar);
+        barrier();
         col_phase();
         stamp(ib, 9);
         {
@@ -444,7 +445,7 @@ kl_fit_logistic(const FitArgs<T> F, const LoopArgs A, LoopState* __restrict__ st
         }
     }
     if (pair_pending) {                                           // the last pair of the run
-        fit_barrier(bar);
+        barrier();
         pair_decision();
     }
 

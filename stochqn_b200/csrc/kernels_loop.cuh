@@ -293,6 +293,27 @@ __device__ __forceinline__ void fit_barrier(unsigned long long* bar)
     __syncthreads();
 }
 
+// The same barrier for PERSISTENT kernels whose counter the host zeroes before the launch: the k-th barrier of a CTA is passed
+// when the counter reaches k * gridDim.x, so the arrival is a fire-and-forget `red` (no ticket to wait for: one L2 round trip
+// less on the critical path of every barrier) and the waiters poll the counter itself.
+struct RunBarrier {
+    unsigned long long* bar;
+    unsigned long long passed;
+    __device__ __forceinline__ void operator()()
+    {
+        __syncthreads();
+        passed += gridDim.x;
+        if (threadIdx.x == 0) {
+            asm volatile("red.release.gpu.global.add.u64 [%0], 1;" :: "l"(bar) : "memory");
+            unsigned long long v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
+            } while (v < passed);
+        }
+        __syncthreads();
+    }
+};
+
 // =========================================================================================
 // kl_ada: the adaQN take_step (stochqn.c:802-840 with 720-783; kernels_adaqn.cuh for the compact form with the
 // diagonal H0 = diag(h)) in ONE cooperative launch, decisions on the device.  KA1 -> KAu -> KA2 -> KAa -> KA3 become
@@ -396,10 +417,10 @@ __device__ __forceinline__ void ada_ring_store(LoopState* st, const AdaRing& R) 
 
 // Whole-grid function: every CTA of a cooperative grid of kAdaThreads-thread CTAs calls it with the same arguments and the same
 // ring state `R` (updated in place, identically everywhere).  `ada_smem`: dynamic shared memory, 2 * ceil(n / grid) elements.
-template <typename T, int MMAX>
+template <typename T, int MMAX, typename Barrier>
 __device__ __forceinline__ void kl_ada_body(const AdaLoopArgs& A, AdaRing& R, const T* g, T* gout, T* __restrict__ Gacc,
        const T* __restrict__ S, const T* __restrict__ Y, T* __restrict__ F, T* __restrict__ x, T* __restrict__ x_sum, const T step,
-       double* partials, double* rec2, double* SY, double* YY, double* SS, unsigned long long* bar, unsigned long long* trace,
+       double* partials, double* rec2, double* SY, double* YY, double* SS, Barrier&& barrier, unsigned long long* trace,
        unsigned char* ada_smem)
 {
     const int m = A.msize;
@@ -486,7 +507,7 @@ __device__ __forceinline__ void kl_ada_body(const AdaLoopArgs& A, AdaRing& R, co
         }
     }
     stamp(1);
-    fit_barrier(bar);
+    barrier();
     stamp(2);
 
     // ---- B: u, then w = Y'[h.(Yu - g)] ----
@@ -564,7 +585,7 @@ __device__ __forceinline__ void kl_ada_body(const AdaLoopArgs& A, AdaRing& R, co
             rec2[(size_t) p * G + b] = v;
         }
         stamp(5);
-        fit_barrier(bar);
+        barrier();
         stamp(6);
 
         // ---- C: a = R^-T (D u + w), bound, decision ----
@@ -643,7 +664,7 @@ __device__ __forceinline__ void kl_ada_body(const AdaLoopArgs& A, AdaRing& R, co
         if (lane == 0) { red[warp][0] = a_dd; red[warp][1] = a_bad; }
         __syncthreads();
         if (tid < 2) { double v = 0; for (int w2 = 0; w2 < NW; ++w2) v += red[w2][tid]; partials[(size_t) tid * G + b] = v; }
-        fit_barrier(bar);
+        barrier();
         reduce_entry_major(partials, 2, G, two_s, NW);
         status = (two_s[1] > 0 || !(sqrt(two_s[0]) <= A.limit)) ? ST_REJECT_NONFINITE : ST_ACCEPT;
         d_in_g = true;
@@ -686,7 +707,7 @@ kl_ada(const AdaLoopArgs A, LoopState* __restrict__ st, const T* g, T* gout, T* 
 {
     extern __shared__ __align__(16) unsigned char ada_dyn_smem[];
     AdaRing R = ada_ring_load(st);
-    kl_ada_body<T, MMAX>(A, R, g, gout, Gacc, S, Y, F, x, x_sum, step, partials, rec2, SY, YY, SS, bar, trace, ada_dyn_smem);
+    kl_ada_body<T, MMAX>(A, R, g, gout, Gacc, S, Y, F, x, x_sum, step, partials, rec2, SY, YY, SS, [&]() { fit_barrier(bar); }, trace, ada_dyn_smem);
     // (every CTA passed at least one grid barrier after reading the record)
     if (blockIdx.x == 0 && threadIdx.x == 0) ada_ring_store(st, R);
 }
@@ -713,6 +734,7 @@ kl_fit_mn_ada(const MnFitArgs<T> F, const AdaLoopArgs A, LoopState* __restrict__
 {
     extern __shared__ __align__(16) unsigned char fit_dyn_smem[];
     AdaRing R = ada_ring_load(st);
+    RunBarrier barrier{bar, 0ull};                           // (the host zeroes the counter before every launch of this kernel)
     for (int ib = 0; ib < F.nbatches; ++ib) {
         const long long r0 = (long long) ib * F.batch_rows;
         const long long rows = F.rows_total - r0 < F.batch_rows ? F.rows_total - r0 : F.batch_rows;
@@ -723,11 +745,11 @@ kl_fit_mn_ada(const MnFitArgs<T> F, const AdaLoopArgs A, LoopState* __restrict__
         ma.sw = F.sw ? F.sw + r0 : nullptr;
         ma.B = (int) rows; ma.d = F.d; ma.K = F.K; ma.icpt = F.icpt;
         ma.W = x; ma.alpha = F.alpha; ma.Gout = g; ma.Zp = F.Zp; ma.Dg = F.Dg;
-        mnsmall::mn_grad_small_body<T>(ma, fit_dyn_smem, [&]() { fit_barrier(bar); }, nullptr);
-        fit_barrier(bar);                                    // the gradient is complete
-        kl_ada_body<T, MMAX>(A, R, g, (T*) nullptr, Gacc, S, Y, Fm, x, x_sum, step, partials, rec2, SY, YY, SS, bar,
+        mnsmall::mn_grad_small_body<T>(ma, fit_dyn_smem, barrier, nullptr);
+        barrier();                                           // the gradient is complete
+        kl_ada_body<T, MMAX>(A, R, g, (T*) nullptr, Gacc, S, Y, Fm, x, x_sum, step, partials, rec2, SY, YY, SS, barrier,
                              ib == F.nbatches - 1 ? trace : nullptr, fit_dyn_smem);
-        fit_barrier(bar);                                    // x is complete
+        barrier();                                           // x is complete
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) ada_ring_store(st, R);
 }

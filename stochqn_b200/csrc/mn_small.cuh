@@ -41,25 +41,25 @@ template <> __device__ __forceinline__ Pack16<float> ld_cg16<float>(const float*
     Pack16<float> r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
 }
 
-__device__ __forceinline__ void ms_barrier(unsigned long long* bar)
-{
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned long long old = atomicAdd(bar, 1ull);
-        const unsigned long long gen = old / gridDim.x + 1ull;
-        unsigned long long* flag = bar + 32;
-        if ((old + 1ull) % gridDim.x == 0) {
-            asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(flag), "l"(gen) : "memory");
-        } else {
+// Grid barrier of the stand-alone kernel: its counter is zeroed by the host before every launch, so the k-th barrier is passed when
+// the counter reaches k * gridDim.x - a fire-and-forget `red` to arrive, no ticket round trip (as RunBarrier, kernels_loop.cuh).
+struct MsBarrier {
+    unsigned long long* bar;
+    unsigned long long passed;
+    __device__ __forceinline__ void operator()()
+    {
+        __syncthreads();
+        passed += gridDim.x;
+        if (threadIdx.x == 0) {
+            asm volatile("red.release.gpu.global.add.u64 [%0], 1;" :: "l"(bar) : "memory");
             unsigned long long v;
             do {
-                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
-            } while (v < gen);
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
+            } while (v < passed);
         }
+        __syncthreads();
     }
-    __syncthreads();
-}
+};
 
 template <typename T>
 struct MnSmallArgs {
@@ -288,7 +288,8 @@ __global__ void __launch_bounds__(MS_T, 1)
 mn_grad_small(const MnSmallArgs<T> a, unsigned long long* bar, unsigned long long* trace)
 {
     extern __shared__ __align__(16) unsigned char ms_dyn_smem[];
-    mn_grad_small_body<T>(a, ms_dyn_smem, [&]() { ms_barrier(bar); }, trace);
+    MsBarrier barrier{bar, 0ull};
+    mn_grad_small_body<T>(a, ms_dyn_smem, barrier, trace);
 }
 
 }  // namespace mnsmall

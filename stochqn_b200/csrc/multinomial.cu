@@ -507,8 +507,12 @@ MnPlan mn_plan(long long B, long long d, long long K)
     p.dpad = (d + q - 1) / q * q;
     auto al = [](size_t v) { return (v + 255) / 256 * 256; };
     size_t off = 0;
-    p.off_zp = off; off = al(off + sizeof(real_t) * (size_t) (s * B * K));
-    p.off_rp = off; off = al(off + sizeof(real_t) * (size_t) (s * B * K));
+    // The split-k partial products take s * B * K elements, and s is not monotone in B (fewer splits once the tiles fill the GPU):
+    // a buffer sized for a long batch must also hold the plan of every shorter one, so the regions are sized by a bound that IS
+    // monotone in B:  s * tiles <= 296 + tiles  =>  s * B * K <= 296 * 64 * 64 + (B + 64) * (K + 64).
+    const size_t zp_elems = (size_t) 296 * TM * TN + (size_t) (B + TM) * (size_t) (K + TN);
+    p.off_zp = off; off = al(off + sizeof(real_t) * zp_elems);
+    p.off_rp = off; off = al(off + sizeof(real_t) * zp_elems);
     p.off_dt = off; off = al(off + sizeof(real_t) * (size_t) (K * p.bpad));
     p.off_xt = off; off = al(off + sizeof(real_t) * (size_t) (d * p.bpad));
     p.off_terms = off; off = al(off + sizeof(double) * (size_t) (B + K + 2));       // per-sample loss terms, then per-class ||w_k||^2

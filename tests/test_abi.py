@@ -164,3 +164,18 @@ def test_fit_batch_refuses_a_foreign_workspace():
     rc = abi.lib.stochqn_b200_fit_batch(C.cast(fake, C.c_void_p), C.cast(fake, C.c_void_p), 0.1, C.byref(M), C.byref(rows), None, None,
                                         C.byref(task), C.byref(req), C.byref(req_vec), C.byref(rep))
     assert rc == -1000
+
+
+def test_multinomial_work_size_is_monotone_in_the_batch_size():
+    """A work buffer sized for the largest batch (the long batch of a guided fit) must hold the plan of every smaller batch: the
+    size function may not decrease when rows are added (the number of split-k partial products does)."""
+    import numpy as np
+    from stochqn_b200 import _lib
+    for dtype in (np.float64, np.float32):
+        lib = _lib.load(dtype).lib
+        for d, K in ((1836, 159), (8192, 4096), (40, 7), (300, 512)):
+            prev = 0
+            for B in list(range(1, 300)) + list(range(300, 20000, 97)):
+                cur = lib.stochqn_b200_multinomial_work_size(B, d, K)
+                assert cur >= prev, (dtype, d, K, B, prev, cur)
+                prev = cur

@@ -335,26 +335,7 @@ kl_fit_logistic(const FitArgs<T> F, const LoopArgs A, LoopState* __restrict__ st
         stamp(ib, 5);
 
         // ---- S: every CTA reduces the records in the same order, solves, decides, updates its slice ----
-        for (int p0 = 0; p0 < P; p0 += 3 * kFitWarps) {         // a warp sums three entries at a time; lanes read consecutive records
-            double acc[3] = {0.0, 0.0, 0.0};
-            #pragma unroll 5
-            for (int r = lane; r < G; r += 32) {
-                #pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    const int p = p0 + warp + q * kFitWarps;
-                    if (p < P) acc[q] += __ldcg(partials + (size_t) p * G + r);
-                }
-            }
-            #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const int p = p0 + warp + q * kFitWarps;
-                if (p < P) {                                          // warp-uniform
-                    const double v = warp_sum(acc[q]);
-                    if (lane == 0) sums_s[p] = v;
-                }
-            }
-        }
-        __syncthreads();
+        reduce_entry_major(partials, P, G, sums_s, kFitWarps);     // (entry-major records: lanes read consecutive CTAs' values)
         stamp(ib, 12);
         SolveArgs SA;
         SA.msize = m; SA.used = used; SA.oldest = (slot == used) ? 0 : slot; SA.pend = pend; SA.nblocks = 0; SA.do_solve = 1;

@@ -195,18 +195,19 @@ kl_fit_logistic(const FitArgs<T> F, const LoopArgs A, LoopState* __restrict__ st
         // pseudo-columns ne, ne + 1: the sums of the sample weights and of the row weights
         const long long col = j < ne ? e0 + j : (j == ne ? ncols : ncols + 1);
         const bool have = j < ne + 2 && !(j < ne && col >= ncols);           // (col == ncols inside the slice: the sk intercept, taken from r_sum)
-        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        double asum = 0;
         if (have) {
+            // this thread's records q, q + 8, ...: up to ten loads in flight per trip (two trips cover 160 CTAs), added in record order
             const double* pc = colpart + col;
-            int r = q;
-            for (; r + 3 * kFitSlices < G; r += 4 * kFitSlices) {
-                const double v0 = __ldcg(pc + (size_t) r * rec), v1 = __ldcg(pc + (size_t) (r + kFitSlices) * rec);
-                const double v2 = __ldcg(pc + (size_t) (r + 2 * kFitSlices) * rec), v3 = __ldcg(pc + (size_t) (r + 3 * kFitSlices) * rec);
-                a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+            for (int r0 = q; r0 < G; r0 += 10 * kFitSlices) {
+                double v[10];
+                #pragma unroll
+                for (int u = 0; u < 10; ++u) { const int r = r0 + u * kFitSlices; v[u] = r < G ? __ldcg(pc + (size_t) r * rec) : 0.0; }
+                #pragma unroll
+                for (int u = 0; u < 10; ++u) asum += v[u];
             }
-            for (; r < G; r += kFitSlices) a0 += __ldcg(pc + (size_t) r * rec);
         }
-        part[q][j] = (a0 + a1) + (a2 + a3);
+        part[q][j] = asum;
         __syncthreads();
         if (tid < 64) {
             double t = 0;
@@ -240,7 +241,13 @@ kl_fit_logistic(const FitArgs<T> F, const LoopArgs A, LoopState* __restrict__ st
     auto pair_decision = [&]() {
         if (warp < 2) {
             double v = 0;
-            for (int r = lane; r < G; r += 32) v += __ldcg(rec2 + (size_t) r * 2 + warp);
+            for (int r0 = 0; r0 < G; r0 += 5 * 32) {
+                double t[5];
+                #pragma unroll
+                for (int u = 0; u < 5; ++u) { const int r = r0 + u * 32 + lane; t[u] = r < G ? __ldcg(rec2 + (size_t) r * 2 + warp) : 0.0; }
+                #pragma unroll
+                for (int u = 0; u < 5; ++u) v += t[u];
+            }
             v = warp_sum(v);
             if (lane == 0) two_s[warp] = v;
         }

@@ -559,24 +559,34 @@ __device__ __forceinline__ void kl_ada_body(const AdaLoopArgs& A, AdaRing& R, co
         const double hh = sums1[2 * m];
         if (A.check_nan && (!isfinite(hh) || !(sqrt(hh) <= A.limit))) status = ST_REJECT_NONFINITE;
     } else {
-        T cu[MMAX];
-        #pragma unroll
-        for (int j = 0; j < MMAX; ++j) cu[j] = (j < used) ? (T) (-coef_s[m + j]) : (T) 0;
+        // two elements of the slice per trip: 2 * used row loads in flight per thread (the loop is a chain of L2 round trips - half as
+        // many this way); the coefficients u_j are read from shared memory (broadcast) instead of living in registers.  (The same
+        // unrolling of phases A and C costs more in spills than it saves: 128 registers per thread at 512 threads.)
         double acc[MMAX], a_tt = 0;
         #pragma unroll
         for (int j = 0; j < MMAX; ++j) acc[j] = 0;
-        for (long long i = e0 + tid; i < e1; i += kAdaThreads) {
-            T yv[MMAX];
+        for (long long i = e0 + tid; i < e1; i += 2 * kAdaThreads) {
+            const long long i1 = i + kAdaThreads;
+            const bool ok1 = i1 < e1;
+            T y0[MMAX], y1[MMAX];
             #pragma unroll
-            for (int j = 0; j < MMAX; ++j) yv[j] = j < used ? Y[(size_t) j * A.ld + i] : (T) 0;
-            const T gv = g_s[i - e0], h = h_s[i - e0];
-            T t = -gv;
+            for (int j = 0; j < MMAX; ++j) {
+                y0[j] = j < used ? Y[(size_t) j * A.ld + i] : (T) 0;
+                y1[j] = (j < used && ok1) ? Y[(size_t) j * A.ld + i1] : (T) 0;
+            }
+            T t0 = -g_s[i - e0], t1 = ok1 ? -g_s[i1 - e0] : (T) 0;
             #pragma unroll
-            for (int j = 0; j < MMAX; ++j) if (j < used) t = fma(cu[j], yv[j], t);
-            const double ht = (double) (h * t);
-            a_tt = fma(ht, ht, a_tt);
+            for (int j = 0; j < MMAX; ++j) {
+                if (j < used) { const T uj = (T) (-coef_s[m + j]); t0 = fma(uj, y0[j], t0); t1 = fma(uj, y1[j], t1); }
+            }
+            const double ht0 = (double) (h_s[i - e0] * t0);
+            const double ht1 = ok1 ? (double) (h_s[i1 - e0] * t1) : 0.0;
+            a_tt = fma(ht0, ht0, a_tt);
+            a_tt = fma(ht1, ht1, a_tt);
             #pragma unroll
-            for (int j = 0; j < MMAX; ++j) if (j < used) acc[j] = fma((double) yv[j], ht, acc[j]);
+            for (int j = 0; j < MMAX; ++j) {
+                if (j < used) { acc[j] = fma((double) y0[j], ht0, acc[j]); acc[j] = fma((double) y1[j], ht1, acc[j]); }
+            }
         }
         {
             constexpr int NG = MMAX + 1 <= 16 ? 16 : 32;

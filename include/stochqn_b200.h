@@ -144,6 +144,28 @@ int stochqn_b200_all_gather_real(void *comm, const real_t *send_block, real_t *r
    stochqn_b200_all_gather_real. */
 int stochqn_b200_all_gather_p2p(void *comm, const real_t *send_block, size_t block_count, real_t **gathered, void *stream);
 
+/* reduce-scatter over NVLink peer memory, by pulling: the rank barrier (every rank's vector is complete), then ONE kernel
+   in which the owner of block r reads block r of every rank's send vector over NVLink (16-byte loads, all world_size of
+   them in flight) and adds them in rank order (deterministic).  The send vector has to be mapped by the peers, so it
+   belongs to the library: stochqn_b200_p2p_send_buffer returns the vector (world_size * block_count elements) that the
+   NEXT reduce_scatter_p2p call on this communicator reads - let the producing kernel (e.g. multinomial_loss_grad) write
+   straight into it; any other send_full is copied into it first (one extra pass).  Double-buffered: the pointer changes
+   from call to call, ask again after every reduce_scatter_p2p.  Replaces stochqn_b200_reduce_scatter_real
+   (ncclReduceScatter).  -5: no peer-memory path.  Collective: the first call (and a call with another block_count)
+   allocates on every rank. */
+int stochqn_b200_p2p_send_buffer(void *comm, size_t block_count, real_t **send_full);
+int stochqn_b200_reduce_scatter_p2p(void *comm, const real_t *send_full, real_t *recv_block, size_t block_count, void *stream);
+
+/* world_size communicators whose ranks all live in THIS process on the current device (comms[0..world_size)): the
+   peer-memory collectives above, the mailbox all-reduce and the fused reduce-scatter run the very kernels of the
+   one-process-per-GPU case, with the peers' buffers shared by pointer instead of cudaIpc - how the exchange kernels are
+   tested on a single-GPU box.  Give every rank its own non-blocking stream and do not synchronise the host between the
+   ranks' calls of one collective (the waiting kernels of all ranks must be running together).  There is no NCCL behind
+   such a communicator: the *_real collectives answer -5.  Each one is released with stochqn_b200_comm_destroy. */
+int stochqn_b200_comm_init_inprocess(int world_size, void **comms);
+/* 1 once a stand-alone exchange on this communicator gave up waiting for a peer (20 s) - its result is then garbage */
+int stochqn_b200_comm_error(void *comm);
+
 /* ---- bundled device callbacks -------------------------------------------------------------
    Chained Rosenbrock, formulas of the reference's example (example/c_rosen.c:13-41), on a
    contiguous shard x[0..n_local) of a vector of length n_global that starts at global index

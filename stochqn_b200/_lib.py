@@ -28,7 +28,8 @@ EXT_SYMBOLS = (
     "stochqn_b200_logistic_sk_grad", "stochqn_b200_logistic_sk_hess_vec", "stochqn_b200_logistic_sk_loss",
     "stochqn_b200_multinomial_work_size", "stochqn_b200_multinomial_loss_grad", "stochqn_b200_multinomial_hess_vec",
     "stochqn_b200_gemm_tn", "stochqn_b200_fit_batch", "stochqn_b200_fit_batches", "stochqn_b200_multinomial_grad_reduce_scatter",
-    "stochqn_b200_all_gather_p2p",
+    "stochqn_b200_all_gather_p2p", "stochqn_b200_p2p_send_buffer", "stochqn_b200_reduce_scatter_p2p",
+    "stochqn_b200_comm_init_inprocess", "stochqn_b200_comm_error",
 )
 
 OPT_GRAD_WRITEBACK = 1
@@ -133,6 +134,10 @@ def load(dtype=np.float64) -> StochqnABI:
     lib.stochqn_b200_multinomial_hess_vec.argtypes = [vp, ll, vp, ll, vp, vp, ll, ll, ll, ci, vp, vp, real, vp, vp, vp]
     lib.stochqn_b200_multinomial_grad_reduce_scatter.argtypes = [vp, vp, ll, vp, ll, vp, vp, ll, ll, ll, ci, vp, real, vp, ll, vp, vp]
     lib.stochqn_b200_all_gather_p2p.argtypes = [vp, vp, sz, C.POINTER(vp), vp]
+    lib.stochqn_b200_p2p_send_buffer.argtypes = [vp, sz, C.POINTER(vp)]
+    lib.stochqn_b200_reduce_scatter_p2p.argtypes = [vp, vp, vp, sz, vp]
+    lib.stochqn_b200_comm_init_inprocess.argtypes = [ci, C.POINTER(vp)]
+    lib.stochqn_b200_comm_error.argtypes = [vp]
     lib.stochqn_b200_gemm_tn.argtypes = [vp, ll, vp, ll, vp, ll, ci, ci, ci, vp]
     abi.Model = model_struct(real)
     lib.stochqn_b200_fit_batch.argtypes = [vp, vp, real, C.POINTER(abi.Model), C.POINTER(Rows), C.POINTER(Rows), C.POINTER(Rows),

@@ -103,17 +103,26 @@ struct Comm {
     cudaStream_t last_stream = 0;                 // stream the previous exchange was enqueued on
     cudaEvent_t order_ev = nullptr;               // chains exchanges issued on different streams (see next_exchange)
     int* error_flag = nullptr;                    // device word set by a timed-out stand-alone exchange
-    // receive slots of the fused reduce-scatter (multinomial.cu): [2 parities][world senders][rs_blk elements], IPC-shared
-    unsigned char* rs_local = nullptr;
-    unsigned char* rs_peer[kMaxWorld] = {};
-    long long rs_blk = 0;
-    unsigned long long rs_calls = 0;
+    // Buffers that every rank allocates and every rank maps (cudaIpc between processes, plain pointers inside an
+    // in-process group): [2 parities][...], double-buffered by the parity of the call count
+    struct PeerBuf {
+        unsigned char* local = nullptr;
+        unsigned char* peer[kMaxWorld] = {};      // peer[rank] == local
+        long long blk = 0;                        // block length the buffers were sized for (0: not allocated)
+        unsigned long long calls = 0;
+    };
+    PeerBuf rs;                                   // receive slots of the fused reduce-scatter (multinomial.cu): [2][world senders][blk]
+    PeerBuf ag;                                   // gathered vector of the push all-gather: [2][world * blk]
+    PeerBuf rp;                                   // send vectors of the pull reduce-scatter: [2][world * blk]
     double* barrier_scratch = nullptr;
-    // gathered vector of the peer-memory all-gather: [2 parities][world * ag_blk elements], IPC-shared
-    unsigned char* ag_local = nullptr;
-    unsigned char* ag_peer[kMaxWorld] = {};
-    long long ag_blk = 0;
-    unsigned long long ag_calls = 0;
+    struct LocalGroup* group = nullptr;           // stochqn_b200_comm_init_inprocess: the ranks live in this process, no NCCL
+};
+
+// The ranks of an in-process communicator group (several "ranks" driven by one process on one device, each on its own
+// stream: how the peer-memory collectives are exercised on a single-GPU box).  Peer buffers are shared by pointer.
+struct LocalGroup {
+    int world = 0, alive = 0;
+    Comm* member[kMaxWorld] = {};
 };
 
 // PeerArgs of the NEXT exchange on this communicator (world = 0 when there is nothing to exchange or no p2p).
@@ -497,6 +506,7 @@ void launch_avg(Ctx* c, real_t* x_sum, real_t* other, real_t* s_slot, real_t inv
 int allreduce_sums(Ctx* c, double* buf, size_t count)
 {
     if (!c->comm || c->comm->world <= 1) return 0;
+    if (!c->comm->nccl) return fail(-5, "an in-process communicator has no library all-reduce (%zu values do not fit a mailbox)", count);
     int r = g_nccl.AllReduce(buf, buf, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm->nccl, c->stream);
     if (r != 0) return fail(-4, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
     return 0;

@@ -21,18 +21,22 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     res = {}
     xs = {}
-    for mode in ("allreduce", "zero1"):
+    for mode in ("allreduce", "zero1", "p2p"):
         r, x = BC.run_multinomial_sharded("t", np.float64, 64, 40, 32, 512, 45, 5, 0.9, 1e-2, mode=mode, warm_cycles=2, return_x=True, quiet=True)
         res[mode] = dict(x_norm=r["x_norm"], tasks=r["tasks"], infos=r["infos"], mem_used=r["mem_used"])
         xs[mode] = x
     # fp32, tensor-core shapes: the reduce-scatter fused into the GEMM epilogue (peer-memory stores) against ncclReduceScatter
     fused = {}
-    for mode in ("zero1", "fused"):
+    for mode in ("zero1", "fused", "p2p"):
         r, x = BC.run_multinomial_sharded("t32", np.float32, 1024, 512, 256, 2048, 24, 4, 0.9, 1e-3, mode=mode, warm_cycles=1, return_x=True, quiet=True)
         fused[mode] = dict(x=x, tasks=r["tasks"], infos=r["infos"])
     fused_err = float(np.max(np.abs(fused["zero1"]["x"] - fused["fused"]["x"])) / max(np.max(np.abs(fused["zero1"]["x"])), 1e-30))
     fused_same_tasks = fused["zero1"]["tasks"] == fused["fused"]["tasks"] and fused["zero1"]["infos"] == fused["fused"]["infos"]
     fused_moved = float(np.max(np.abs(fused["fused"]["x"])))
+    # push all-gather + pull reduce-scatter over peer memory against the NCCL collectives (same arithmetic up to the order of the sum over ranks)
+    p2p32_err = float(np.max(np.abs(fused["zero1"]["x"] - fused["p2p"]["x"])) / max(np.max(np.abs(fused["zero1"]["x"])), 1e-30))
+    p2p32_same_tasks = fused["zero1"]["tasks"] == fused["p2p"]["tasks"] and fused["zero1"]["infos"] == fused["p2p"]["infos"]
+    p2p_err = float(np.max(np.abs(xs["zero1"] - xs["p2p"])) / np.max(np.abs(xs["zero1"])))
     # the two modes run the same arithmetic up to summation order
     err = float(np.max(np.abs(xs["allreduce"] - xs["zero1"])) / np.max(np.abs(xs["allreduce"])))
     # every rank must hold the same x
@@ -42,7 +46,8 @@ def main():
     same = all(bool(torch.equal(parts[0], p)) for p in parts)
     if rank == 0:
         json.dump(dict(res=res, modes_rel_err=err, ranks_identical=same, moved=float(np.max(np.abs(xs["zero1"]))),
-                       fused_rel_err=fused_err, fused_same_tasks=fused_same_tasks, fused_moved=fused_moved), open(out, "w"))
+                       fused_rel_err=fused_err, fused_same_tasks=fused_same_tasks, fused_moved=fused_moved,
+                       p2p_rel_err=p2p_err, p2p32_rel_err=p2p32_err, p2p32_same_tasks=p2p32_same_tasks), open(out, "w"))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -1,0 +1,47 @@
+"""The peer-memory exchange kernels on ONE GPU (the driver's GPU box has one; tests/test_gpu_multi.py needs two).
+
+`stochqn_b200_comm_init_inprocess` builds world_size communicators inside one process: mailbox all-reduce (the exchange
+fused into K2 / K4 / the Rosenbrock halo), push all-gather, pull reduce-scatter and the reduce-scatter fused into the
+GEMM epilogue run the kernels of the one-process-per-GPU case, each rank on its own stream.  One worker process
+(tests/inprocess_collectives_worker.py) runs every case; results are exact (sums in rank order) except for the
+row-sharded gradients, which are compared with the oracle on the union of the rows."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+CASES = (["allreduce_w%d_c%d" % (w, c) for w in (2, 3, 8) for c in (1, 130, 2048)] +
+         ["allgather_%s_w%d_b%d" % (t, w, b) for t in ("f64", "f32") for w in (2, 4, 8) for b in (1024, 1001)] +
+         ["reduce_scatter_%s_w%d_b%d" % (t, w, b) for t in ("f64", "f32") for w in (2, 3, 4, 8) for b in (4096, 1001, 300000)] +
+         ["rowsharded_pull_f64_w2", "rowsharded_pull_f64_w4", "rowsharded_pull_f32_w2", "rowsharded_pull_f32_w4",
+          "rowsharded_fused_f32_w2", "rowsharded_fused_f32_w4"])
+
+
+@pytest.fixture(scope="module")
+def results(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("inproc") / "res.json")
+    # eager module loading: the first launch of a lazily loaded kernel may wait for the device to drain, which never happens
+    # while rank 0's polling kernel waits for rank 1; 32 connections: every rank's stream gets its own hardware queue
+    # (with the default 8, two ranks' streams can share one and rank 1's launch would sit behind rank 0's dependent kernel)
+    env = dict(os.environ, CUDA_MODULE_LOADING="EAGER", CUDA_DEVICE_MAX_CONNECTIONS="32")
+    r = subprocess.run([sys.executable, os.path.join(HERE, "inprocess_collectives_worker.py"), out], env=env, capture_output=True, text=True, timeout=900)
+    res = json.load(open(out)) if os.path.exists(out) else {}
+    res["_rc"] = r.returncode
+    res["_log"] = r.stdout[-1500:] + r.stderr[-3000:]
+    return res
+
+
+def test_worker_finished(results):
+    assert results["_rc"] == 0, results["_log"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_case(results, case):
+    assert case in results, "the worker did not get to this case:\n" + results["_log"]
+    assert results[case]["ok"], results[case]

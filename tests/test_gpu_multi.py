@@ -67,3 +67,7 @@ def test_row_sharded_multinomial_two_gpus(tmp_path):
     # fp32 / tensor cores: reduce-scatter fused into the GEMM epilogue over peer memory == ncclReduceScatter of the same tiles
     assert res["fused_same_tasks"] and res["fused_moved"] > 1e-4, res
     assert res["fused_rel_err"] <= 1e-5, res
+    # the library's own push all-gather + pull reduce-scatter over peer memory == the NCCL collectives
+    assert res["res"]["p2p"]["tasks"] == res["res"]["zero1"]["tasks"] and res["res"]["p2p"]["infos"] == res["res"]["zero1"]["infos"], res
+    assert res["p2p_rel_err"] <= 1e-9, res
+    assert res["p2p32_same_tasks"] and res["p2p32_rel_err"] <= 1e-5, res

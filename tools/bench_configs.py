@@ -333,9 +333,12 @@ def run_multinomial_sharded(name, dtype, d, K, batch_per_gpu, nrows_per_gpu, ste
     abi = _lib.load(dtype)
     lib = abi.lib
     comm = init_comm(abi, rank, world) if world > 1 else None
+    if comm is not None and mode in ("fused", "p2p") and not lib.stochqn_b200_comm_uses_p2p(comm):      # the same answer on every rank
+        lib.stochqn_b200_comm_destroy(comm)
+        raise RuntimeError("mode %s needs the peer-memory path (no peer access between the devices, or STOCHQN_B200_NO_P2P is set)" % mode)
     n = K * (d + 1)
     assert n % world == 0, "n must divide by the number of ranks for reduce-scatter"
-    sharded_opt = mode in ("zero1", "fused")
+    sharded_opt = mode in ("zero1", "fused", "p2p")
     blk = n // world if sharded_opt else n
     off = rank * blk if sharded_opt else 0
     # this rank's rows of every global batch: global row = b * (world * batch_per_gpu) + rank * batch_per_gpu + i
@@ -404,7 +407,7 @@ def run_multinomial_sharded(name, dtype, d, K, batch_per_gpu, nrows_per_gpu, ste
         mark("grad_done")
 
     def _serve(t, b, r0, cnt):
-        if mode == "fused" and world > 1:                     # gather by pushing over peer memory (one kernel + barrier)
+        if mode in ("fused", "p2p") and world > 1:            # gather by pushing over peer memory (one kernel + barrier)
             gp = C.c_void_p()
             rc = lib.stochqn_b200_all_gather_p2p(comm, req.value, blk, C.byref(gp), None)
             assert rc == 0, (rc, _lib.last_error(abi))
@@ -423,6 +426,18 @@ def run_multinomial_sharded(name, dtype, d, K, batch_per_gpu, nrows_per_gpu, ste
                                                                   work.data_ptr(), None)
             assert rc == 0, (rc, _lib.last_error(abi))
             return
+        if mode == "p2p" and world > 1:
+            # the gradient lands in the library's peer-mapped send vector; the owner of every block then pulls it from all
+            # the ranks over NVLink and adds in rank order (rank barrier + one kernel instead of ncclReduceScatter)
+            sp = C.c_void_p()
+            rc = lib.stochqn_b200_p2p_send_buffer(comm, blk, C.byref(sp))
+            assert rc == 0, (rc, _lib.last_error(abi))
+            assert lib.stochqn_b200_multinomial_loss_grad(X.data_ptr() + r0 * d * esz, d, None, K, lab.data_ptr() + r0 * 4, sw[cnt].data_ptr(), cnt, d, K, 1,
+                                                          point, alpha / world, sp.value, None, work.data_ptr(), None) == 0
+            mark("grad_local")
+            rc = lib.stochqn_b200_reduce_scatter_p2p(comm, sp.value, g_blk.data_ptr(), blk, None)
+            assert rc == 0, (rc, _lib.last_error(abi))
+            return
         # alpha / world per rank: the penalty term is added once in the sum over ranks
         assert lib.stochqn_b200_multinomial_loss_grad(X.data_ptr() + r0 * d * esz, d, None, K, lab.data_ptr() + r0 * 4, sw[cnt].data_ptr(), cnt, d, K, 1,
                                                       point, alpha / world, g_full.data_ptr(), None, work.data_ptr(), None) == 0
@@ -437,6 +452,15 @@ def run_multinomial_sharded(name, dtype, d, K, batch_per_gpu, nrows_per_gpu, ste
         serve(); call()
     torch.cuda.synchronize()
     if world > 1:
+        if mode in ("fused", "p2p"):
+            # a peer-memory exchange that gave up waiting (20 s, sticky) leaves garbage behind: every rank learns of it and
+            # all of them leave together, so that the caller can fall back to the library collectives
+            bad = torch.tensor([float(lib.stochqn_b200_comm_error(comm))], device="cuda")
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+            if float(bad.item()) != 0.0:
+                lib.dealloc_adaQN(ws)
+                lib.stochqn_b200_comm_destroy(comm)
+                raise RuntimeError("a peer-memory exchange timed out in mode %s" % mode)
         dist.barrier()
         torch.cuda.synchronize()
     tasks.clear(); infos.clear()
@@ -482,8 +506,9 @@ def main():
     ap.add_argument("configs", nargs="*", default=["cfg1", "cfg2", "cfg3", "cfg5"])
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--rows-cfg2", type=int, default=1000000)
-    ap.add_argument("--mode", default="zero1", choices=["zero1", "allreduce", "fused"],
-                    help="cfg5s: how the row-sharded gradient is combined (fused: reduce-scatter inside the GEMM epilogue over NVLink peer memory)")
+    ap.add_argument("--mode", default="zero1", choices=["zero1", "allreduce", "fused", "p2p"],
+                    help="cfg5s: how the row-sharded gradient is combined (zero1: ncclReduceScatter / ncclAllGather; p2p: push all-gather + pull "
+                         "reduce-scatter over NVLink peer memory; fused: reduce-scatter inside the GEMM epilogue over peer memory)")
     a = ap.parse_args()
     if "cfg5s" in a.configs:          # row-sharded config 5 (torch.distributed.run, one rank per GPU)
         import torch.distributed as dist

@@ -183,12 +183,17 @@ def case_rowsharded_gradient(abi, tdt, world, how, rows_per_rank=256, d=1024, K=
         want = _oracle_grad(X, lab, w, sw, d, K, alpha)
         outs = [torch.full((blk,), float("nan"), device="cuda", dtype=tdt) for _ in range(world)]
         torch.cuda.synchronize()
+        # two passes over the ranks: the first call of a collective allocates its buffers for the whole group and drains the
+        # device to do so - it must not find rank 0's all-gather waiting for a rank 1 that has not been issued yet
+        points = []
         for r in range(world):
             gp = C.c_void_p()
             rc = lib.stochqn_b200_all_gather_p2p(g.comms[r], w.data_ptr() + r * blk * esz, blk, C.byref(gp), g.st(r))
             assert rc == 0, (rc, _lib.last_error(abi))
+            points.append(gp.value)
+        for r in range(world):
             r0 = r * rows_per_rank
-            args = (X.data_ptr() + r0 * d * esz, d, None, K, lab.data_ptr() + r0 * 4, sw.data_ptr() + r0 * esz, rows_per_rank, d, K, 1, gp.value, alpha / world)
+            args = (X.data_ptr() + r0 * d * esz, d, None, K, lab.data_ptr() + r0 * 4, sw.data_ptr() + r0 * esz, rows_per_rank, d, K, 1, points[r], alpha / world)
             if how == "fused":
                 rc = lib.stochqn_b200_multinomial_grad_reduce_scatter(g.comms[r], *args, outs[r].data_ptr(), blk, work[r].data_ptr(), g.st(r))
                 assert rc == 0, (rc, _lib.last_error(abi))
@@ -213,12 +218,21 @@ def main():
     out = sys.argv[1]
     res = {}
 
+    timed_out = set()
+
     def run(name, fn, *a, **kw):
+        kind = name.split("_")[0]
+        if kind in timed_out:                              # every further case of the kind would wait its 20 s as well
+            res[name] = {"ok": False, "error": "not run: an earlier %s case timed out" % kind}
+            json.dump(res, open(out, "w"), indent=1)
+            return
         try:
             r = fn(*a, **kw) or {}
             r["ok"] = True
         except Exception as e:                             # noqa: BLE001
             r = {"ok": False, "error": "%s: %s" % (type(e).__name__, e), "trace": traceback.format_exc()[-1500:]}
+            if "timed out" in str(e):
+                timed_out.add(kind)
         res[name] = r
         json.dump(res, open(out, "w"), indent=1)
 

@@ -45,3 +45,29 @@ def test_worker_finished(results):
 def test_case(results, case):
     assert case in results, "the worker did not get to this case:\n" + results["_log"]
     assert results[case]["ok"], results[case]
+
+
+# ---- the sharded optimizer itself: one host thread + one stream per rank, all on this GPU -------------------------------------
+SHARDED = ["oLBFGS_w2", "SQN_w2", "oLBFGS_w4", "SQN_w3"]
+
+
+@pytest.fixture(scope="module")
+def sharded_results(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("inproc_sharded") / "res.json")
+    env = dict(os.environ, CUDA_MODULE_LOADING="EAGER", CUDA_DEVICE_MAX_CONNECTIONS="32")
+    try:
+        r = subprocess.run([sys.executable, os.path.join(HERE, "inprocess_sharded_worker.py"), out], env=env, capture_output=True, text=True, timeout=600)
+        rc, log = r.returncode, r.stdout[-1500:] + r.stderr[-3000:]
+    except subprocess.TimeoutExpired as e:
+        rc, log = -9, "worker timed out: %s" % e
+    res = json.load(open(out)) if os.path.exists(out) else {}
+    res["_rc"], res["_log"] = rc, log
+    return res
+
+
+@pytest.mark.parametrize("case", SHARDED)
+def test_sharded_optimizer_in_process(sharded_results, case):
+    """K2's fused exchange, K4's last-CTA exchange and the fused halo exchange of the Rosenbrock gradient, with the vector sharded
+    over 2-4 in-process ranks: same task / counter sequence on every rank and as the oracle on the whole vector, x to 1e-10."""
+    assert case in sharded_results, "the worker did not get to this case:\n" + sharded_results["_log"]
+    assert sharded_results[case]["ok"], sharded_results[case]

@@ -121,13 +121,142 @@ def run_case(kind, n, calls, world):
     return res
 
 
+def run_rowsharded_adaqn(world, d=64, K=40, bpg=160, nb=10, steps=45, L=5, rms=0.9, step=1e-2):
+    """adaQN (RMSProp, gradient-difference pairs) + multinomial gradient with the batch ROWS sharded over in-process ranks
+    and the optimizer state sharded by blocks: per request push all-gather of the point, gradient on the rank's rows into
+    the library's send vector, pull reduce-scatter, sharded run_adaQN (BASELINE config 5's multi-GPU layout at a small
+    size, fp64) - against the same optimisation of the union of the rows on one rank."""
+    abi = _lib.load(np.float64)
+    lib = abi.lib
+    tdt, esz = torch.float64, 8
+    n = K * (d + 1)
+    assert n % world == 0
+    blk = n // world
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    Wt = torch.randn(K, d, device="cuda", dtype=tdt, generator=gen)
+    Xu4 = torch.randn(nb, world, bpg, d, device="cuda", dtype=tdt, generator=gen) / d ** 0.5      # [batch][rank][row]
+    Xu = Xu4.reshape(-1, d).contiguous()
+    labu = torch.argmax(Xu @ Wt.T * 4.0, dim=1).to(torch.int32)
+    Xr = [Xu4[:, r].reshape(-1, d).contiguous() for r in range(world)]
+    labr = [labu.reshape(nb, world, bpg)[:, r].reshape(-1).contiguous() for r in range(world)]
+    alpha = 1e-3
+    big = bpg * L                                        # rows per rank of the long batch (the last L batches)
+
+    def optimise(nranks, comms, streams, X, lab, nrows_batch, x_full):
+        """every rank: the request loop of tools/bench_configs.py run_multinomial_sharded (mode p2p), as a host thread"""
+        cnts = {nrows_batch, nrows_batch * L}
+        sw = {c: torch.full((c,), 1.0 / (c * nranks), device="cuda", dtype=tdt) for c in cnts}
+        work = [torch.empty(lib.stochqn_b200_multinomial_work_size(nrows_batch * L, d, K), device="cuda", dtype=torch.uint8) for _ in range(nranks)]
+        b_loc = n // nranks
+        gblk = [torch.zeros(b_loc, device="cuda", dtype=tdt) for _ in range(nranks)]
+        wss = []
+        for r in range(nranks):
+            ws = lib.initialize_adaQN(b_loc, 10, 1, L, 0.0, 1e-4, 1e-4, rms, 1, 0.0, 1, 1)
+            assert ws, _lib.last_error(abi)
+            if nranks > 1:
+                assert lib.stochqn_b200_set_stream(ws, C.c_void_p(streams[r].cuda_stream)) == 0
+                assert lib.stochqn_b200_set_comm(ws, comms[r], n) == 0
+            wss.append(ws)
+        if nranks > 1:
+            # the first use of a collective allocates for the whole group and drains the device: done here, rank after rank in
+            # two passes, before the rank threads exist
+            for r in range(nranks):
+                gp = C.c_void_p()
+                assert lib.stochqn_b200_all_gather_p2p(comms[r], gblk[r].data_ptr(), b_loc, C.byref(gp), C.c_void_p(streams[r].cuda_stream)) == 0
+            for r in range(nranks):
+                sp = C.c_void_p()
+                assert lib.stochqn_b200_p2p_send_buffer(comms[r], b_loc, C.byref(sp)) == 0
+                assert lib.stochqn_b200_reduce_scatter_p2p(comms[r], sp.value, gblk[r].data_ptr(), b_loc, C.c_void_p(streams[r].cuda_stream)) == 0
+        torch.cuda.synchronize()
+        logs = [dict(tasks={}, infos={}) for _ in range(nranks)]
+        errors = [None] * nranks
+
+        def rank_main(r):
+            try:
+                ws = wss[r]
+                st = C.c_void_p(streams[r].cuda_stream) if nranks > 1 else None
+                x_ptr = x_full.data_ptr() + r * b_loc * esz
+                req, task, info = C.c_void_p(), C.c_int(), C.c_int()
+                b = 0
+
+                def call():
+                    lib.run_adaQN(step, x_ptr, 0.0, gblk[r].data_ptr(), C.byref(req), C.byref(task), ws, C.byref(info))
+                    logs[r]["tasks"][task.value] = logs[r]["tasks"].get(task.value, 0) + 1
+                    logs[r]["infos"][info.value] = logs[r]["infos"].get(info.value, 0) + 1
+
+                call()
+                while int(ws.contents.niter) < steps:
+                    t = task.value
+                    if t == 101:
+                        b = (b + 1) % nb
+                        r0, cnt = b * nrows_batch, nrows_batch
+                    elif t == 103:
+                        cnt = nrows_batch * L
+                        r0 = max(0, (b + 1) * nrows_batch - cnt)
+                    else:
+                        raise RuntimeError("unexpected task %d" % t)
+                    args = (X[r].data_ptr() + r0 * d * esz, d, None, K, lab[r].data_ptr() + r0 * 4, sw[cnt].data_ptr(), cnt, d, K, 1)
+                    if nranks == 1:
+                        rc = lib.stochqn_b200_multinomial_loss_grad(*args, req.value, alpha, gblk[0].data_ptr(), None, work[0].data_ptr(), None)
+                        assert rc == 0, (rc, _lib.last_error(abi))
+                    else:
+                        gp, sp = C.c_void_p(), C.c_void_p()
+                        rc = lib.stochqn_b200_all_gather_p2p(comms[r], req.value, b_loc, C.byref(gp), st)
+                        rc = rc or lib.stochqn_b200_p2p_send_buffer(comms[r], b_loc, C.byref(sp))
+                        rc = rc or lib.stochqn_b200_multinomial_loss_grad(*args, gp.value, alpha / nranks, sp.value, None, work[r].data_ptr(), st)
+                        rc = rc or lib.stochqn_b200_reduce_scatter_p2p(comms[r], sp.value, gblk[r].data_ptr(), b_loc, st)
+                        assert rc == 0, (rc, _lib.last_error(abi))
+                    call()
+            except Exception as e:                         # noqa: BLE001
+                errors[r] = "%s: %s\n%s" % (type(e).__name__, e, traceback.format_exc()[-800:])
+
+        if nranks == 1:
+            rank_main(0)
+        else:
+            threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(nranks)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join(timeout=240)
+            hung = [r for r, t in enumerate(threads) if t.is_alive()]
+            assert not hung, "ranks %s did not finish" % hung
+        assert all(e is None for e in errors), errors
+        torch.cuda.synchronize()
+        used = int(wss[0].contents.bfgs_memory.contents.mem_used)
+        for ws in wss:
+            lib.dealloc_adaQN(ws)
+        return logs, used
+
+    # sharded
+    arr = (C.c_void_p * world)()
+    assert lib.stochqn_b200_comm_init_inprocess(world, arr) == 0, _lib.last_error(abi)
+    comms = [C.c_void_p(arr[r]) for r in range(world)]
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    x_sh = torch.zeros(n, device="cuda", dtype=tdt)
+    logs, used = optimise(world, comms, streams, Xr, labr, bpg, x_sh)
+    timed_out = [int(lib.stochqn_b200_comm_error(c)) for c in comms]
+    for c in comms:
+        lib.stochqn_b200_comm_destroy(c)
+    # the union of the rows on one rank
+    x_un = torch.zeros(n, device="cuda", dtype=tdt)
+    logu, used_u = optimise(1, None, None, [Xu], [labu], bpg * world, x_un)
+    a, bb = x_sh.cpu().numpy(), x_un.cpu().numpy()
+    err = float(np.max(np.abs(a - bb)) / np.max(np.abs(bb)))
+    res = dict(world=world, rel_err=err, moved=float(np.max(np.abs(bb))), pairs=used, pairs_unsharded=used_u, exchange_timeouts=timed_out,
+               same_on_all_ranks=all(l == logs[0] for l in logs), matches_unsharded=(logs[0] == logu[0]), tasks=logs[0]["tasks"])
+    assert res["same_on_all_ranks"] and res["matches_unsharded"] and not any(timed_out), res
+    assert err <= 1e-9 and res["moved"] > 1e-3 and used == used_u and used >= 2, res
+    return res
+
+
 def main():
     out = sys.argv[1]
     res = {}
-    for kind, world in (("oLBFGS", 2), ("SQN", 2), ("oLBFGS", 4), ("SQN", 3)):
-        name = "%s_w%d" % (kind, world)
+    cases = [("%s_w%d" % (kind, world), run_case, (kind, 100003, 90, world)) for kind, world in (("oLBFGS", 2), ("SQN", 2), ("oLBFGS", 4), ("SQN", 3))]
+    cases += [("rowsharded_adaQN_w%d" % world, run_rowsharded_adaqn, (world,)) for world in (2, 4)]
+    for name, fn, a in cases:
         try:
-            r = run_case(kind, 100003, 90, world)
+            r = fn(*a)
             r["ok"] = True
         except Exception as e:                             # noqa: BLE001
             r = {"ok": False, "error": "%s: %s" % (type(e).__name__, e), "trace": traceback.format_exc()[-1500:]}

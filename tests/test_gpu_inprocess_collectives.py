@@ -48,7 +48,7 @@ def test_case(results, case):
 
 
 # ---- the sharded optimizer itself: one host thread + one stream per rank, all on this GPU -------------------------------------
-SHARDED = ["oLBFGS_w2", "SQN_w2", "oLBFGS_w4", "SQN_w3"]
+SHARDED = ["oLBFGS_w2", "SQN_w2", "oLBFGS_w4", "SQN_w3", "rowsharded_adaQN_w2", "rowsharded_adaQN_w4"]
 
 
 @pytest.fixture(scope="module")
@@ -68,6 +68,8 @@ def sharded_results(tmp_path_factory):
 @pytest.mark.parametrize("case", SHARDED)
 def test_sharded_optimizer_in_process(sharded_results, case):
     """K2's fused exchange, K4's last-CTA exchange and the fused halo exchange of the Rosenbrock gradient, with the vector sharded
-    over 2-4 in-process ranks: same task / counter sequence on every rank and as the oracle on the whole vector, x to 1e-10."""
+    over 2-4 in-process ranks: same task / counter sequence on every rank and as the oracle on the whole vector, x to 1e-10.
+    rowsharded_adaQN: adaQN + multinomial gradient with the batch rows AND the optimizer state sharded (push all-gather, pull
+    reduce-scatter, the exchanges fused into the adaQN solves) against the unsharded run on the union of the rows, x to 1e-9."""
     assert case in sharded_results, "the worker did not get to this case:\n" + sharded_results["_log"]
     assert sharded_results[case]["ok"], sharded_results[case]

@@ -31,7 +31,10 @@ from stochqn_b200 import _lib                           # noqa: E402
 from stochqn_b200.distributed import shard_bounds       # noqa: E402
 
 
-def run_case(kind, n, calls, world):
+def run_case(kind, n, calls, world, events=None):
+    """events: {call index: ("remember",) | ("repeat",) | ("poison", global element, value)} - forced events, applied to the
+    gradient that is handed to that call on every rank / on the rank that owns the element, and to the oracle's."""
+    events = events or {}
     abi = _lib.load(np.float64)
     lib = abi.lib
     arr = (C.c_void_p * world)()
@@ -90,10 +93,20 @@ def run_case(kind, n, calls, world):
                     rc = lib.stochqn_b200_rosenbrock_halo(req.value, cnt, r, world, comm, halo, scr, st)
                     rc = rc or lib.stochqn_b200_rosenbrock_grad(req.value, g, cnt, off, n, halo, st)
                 assert rc == 0, (rc, _lib.last_error(abi))
+                ev = events.get(len(trace))
+                if ev:
+                    with torch.cuda.stream(streams[r]):    # behind the gradient kernel on the rank's stream
+                        if ev[0] == "remember":
+                            kept[r].copy_(gs[r])
+                        elif ev[0] == "repeat":            # the same gradient again: y = 0, the pair is rejected (quirk Q1)
+                            gs[r].copy_(kept[r])
+                        elif ev[0] == "poison" and off <= ev[1] < off + cnt:
+                            gs[r][ev[1] - off] = ev[2]
                 call()
         except Exception as e:                             # noqa: BLE001
             errors[r] = "%s: %s\n%s" % (type(e).__name__, e, traceback.format_exc()[-800:])
 
+    kept = [torch.zeros_like(g) for g in gs]
     threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
     for t in threads:
         t.start()
@@ -111,13 +124,35 @@ def run_case(kind, n, calls, world):
         lib.stochqn_b200_comm_destroy(c)
     p = Rosenbrock(n)
     so = HostStepper({"oLBFGS": O.OracleOLBFGS, "SQN": O.OracleSQN}[kind](n, **kw), p.x0())
-    to = run_trace(so, p, calls, step, keep_x=True)
+    held = {}
+
+    def hook(ev):
+        def f(stepper, task, payload):
+            if ev[0] == "remember":
+                held["g"] = payload["grad"].copy()
+            elif ev[0] == "repeat":
+                payload["grad"] = held["g"].copy()
+            else:
+                payload["grad"] = payload["grad"].copy()
+                payload["grad"][ev[1]] = ev[2]
+        return f
+
+    to = run_trace(so, p, calls, step, hooks={c: hook(ev) for c, ev in events.items()}, keep_x=True)
     want = [(r["task"], r["ret"], r["info"], r["niter"], r["section"], r["mem_used"], r["mem_st_ix"]) for r in to]
     err = float(np.max(np.abs(got - to[-1]["x"])) / np.max(np.abs(to[-1]["x"])))
+    infos = sorted(set(t[2] for t in traces[0]))
     res = dict(kind=kind, world=world, rel_err=err, same_on_all_ranks=all(t == traces[0] for t in traces),
-               matches_oracle=(traces[0] == want), pairs=int(to[-1]["mem_used"]), exchange_timeouts=timed_out)
+               matches_oracle=(traces[0] == want), pairs=int(to[-1]["mem_used"]), exchange_timeouts=timed_out, infos=infos)
+    if not res["matches_oracle"]:
+        res["first_difference"] = next(((i, a, b) for i, (a, b) in enumerate(zip(traces[0], want)) if a != b), None)
     assert res["same_on_all_ranks"] and res["matches_oracle"], res
-    assert err <= 1e-10 and res["pairs"] >= 4 and not any(timed_out), res
+    assert err <= 1e-10 and not any(timed_out), res
+    if events:
+        assert 203 in infos, res                                   # a step was rejected and the memory flushed ...
+        if any(e[0] == "repeat" for e in events.values()):
+            assert 202 in infos, res                               # ... and a pair was rejected
+    else:
+        assert res["pairs"] >= 4, res
     return res
 
 
@@ -254,6 +289,12 @@ def main():
     res = {}
     cases = [("%s_w%d" % (kind, world), run_case, (kind, 100003, 90, world)) for kind, world in (("oLBFGS", 2), ("SQN", 2), ("oLBFGS", 4), ("SQN", 3))]
     cases += [("rowsharded_adaQN_w%d" % world, run_rowsharded_adaqn, (world,)) for world in (2, 4)]
+    # forced events with the vector sharded: a repeated gradient (y = 0: pair rejected, slot zeroed), then a NaN / an Inf /
+    # a huge finite entry on ONE rank's shard - every rank must reject that step, flush and carry on exactly as the oracle
+    ev = lambda v: {7: ("remember",), 8: ("repeat",), 21: ("poison", 70001, v)}       # noqa: E731
+    cases += [("events_oLBFGS_w2_nan", run_case, ("oLBFGS", 100003, 40, 2, ev(float("nan")))),
+              ("events_oLBFGS_w4_huge", run_case, ("oLBFGS", 100003, 40, 4, ev(1e14))),
+              ("events_SQN_w3_inf", run_case, ("SQN", 100003, 40, 3, {15: ("poison", 99999, float("inf"))}))]
     for name, fn, a in cases:
         try:
             r = fn(*a)

@@ -48,7 +48,8 @@ def test_case(results, case):
 
 
 # ---- the sharded optimizer itself: one host thread + one stream per rank, all on this GPU -------------------------------------
-SHARDED = ["oLBFGS_w2", "SQN_w2", "oLBFGS_w4", "SQN_w3", "rowsharded_adaQN_w2", "rowsharded_adaQN_w4"]
+SHARDED = ["oLBFGS_w2", "SQN_w2", "oLBFGS_w4", "SQN_w3", "rowsharded_adaQN_w2", "rowsharded_adaQN_w4",
+           "events_oLBFGS_w2_nan", "events_oLBFGS_w4_huge", "events_SQN_w3_inf"]
 
 
 @pytest.fixture(scope="module")

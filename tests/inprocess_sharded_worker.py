@@ -28,7 +28,7 @@ from oracle import stochqn_np as O                      # noqa: E402
 from oracle.driver import HostStepper, run_trace        # noqa: E402
 from oracle.problems import Rosenbrock                  # noqa: E402
 from stochqn_b200 import _lib                           # noqa: E402
-from stochqn_b200.distributed import shard_bounds       # noqa: E402
+from stochqn_b200.distributed import RowShardedCombiner, shard_bounds       # noqa: E402
 
 
 def run_case(kind, n, calls, world, events=None):
@@ -202,6 +202,8 @@ def run_rowsharded_adaqn(world, d=64, K=40, bpg=160, nb=10, steps=45, L=5, rms=0
                 sp = C.c_void_p()
                 assert lib.stochqn_b200_p2p_send_buffer(comms[r], b_loc, C.byref(sp)) == 0
                 assert lib.stochqn_b200_reduce_scatter_p2p(comms[r], sp.value, gblk[r].data_ptr(), b_loc, C.c_void_p(streams[r].cuda_stream)) == 0
+        comb = [RowShardedCombiner(abi, comms[r], n, nranks, stream=C.c_void_p(streams[r].cuda_stream)) for r in range(nranks)] if nranks > 1 else None
+        assert comb is None or all(c.p2p for c in comb)
         torch.cuda.synchronize()
         logs = [dict(tasks={}, infos={}) for _ in range(nranks)]
         errors = [None] * nranks
@@ -234,13 +236,12 @@ def run_rowsharded_adaqn(world, d=64, K=40, bpg=160, nb=10, steps=45, L=5, rms=0
                     if nranks == 1:
                         rc = lib.stochqn_b200_multinomial_loss_grad(*args, req.value, alpha, gblk[0].data_ptr(), None, work[0].data_ptr(), None)
                         assert rc == 0, (rc, _lib.last_error(abi))
-                    else:
-                        gp, sp = C.c_void_p(), C.c_void_p()
-                        rc = lib.stochqn_b200_all_gather_p2p(comms[r], req.value, b_loc, C.byref(gp), st)
-                        rc = rc or lib.stochqn_b200_p2p_send_buffer(comms[r], b_loc, C.byref(sp))
-                        rc = rc or lib.stochqn_b200_multinomial_loss_grad(*args, gp.value, alpha / nranks, sp.value, None, work[r].data_ptr(), st)
-                        rc = rc or lib.stochqn_b200_reduce_scatter_p2p(comms[r], sp.value, gblk[r].data_ptr(), b_loc, st)
+                    else:                                  # the product-level helper (stochqn_b200.distributed)
+                        point = comb[r].gather(req.value)
+                        send = comb[r].send_buffer()
+                        rc = lib.stochqn_b200_multinomial_loss_grad(*args, point, alpha / nranks, send, None, work[r].data_ptr(), st)
                         assert rc == 0, (rc, _lib.last_error(abi))
+                        comb[r].reduce_scatter(gblk[r].data_ptr())
                     call()
             except Exception as e:                         # noqa: BLE001
                 errors[r] = "%s: %s\n%s" % (type(e).__name__, e, traceback.format_exc()[-800:])

@@ -118,6 +118,8 @@ size_t stochqn_b200_row_stride(void *ws);
    (torch.distributed broadcast, MPI, a file ...), every rank calls comm_init. */
 int stochqn_b200_comm_unique_id(void *id128);
 int stochqn_b200_comm_init(const void *id128, int rank, int world_size, void **comm);
+/* comm_destroy frees this rank's mailbox and peer-mapped vectors: let every rank finish its device work and meet at a
+   host barrier first (a peer's kernel may still be reading them) */
 int stochqn_b200_comm_destroy(void *comm);
 /* 1 when the small all-reduces of this communicator are done over NVLink peer memory inside the kernel that
    produces the values (cudaIpc mailboxes, one rank per GPU), 0 when they go through ncclAllReduce

@@ -162,7 +162,11 @@ int stochqn_b200_reduce_scatter_p2p(void *comm, const real_t *send_full, real_t 
    peer-memory collectives above, the mailbox all-reduce and the fused reduce-scatter run the very kernels of the
    one-process-per-GPU case, with the peers' buffers shared by pointer instead of cudaIpc - how the exchange kernels are
    tested on a single-GPU box.  Give every rank its own non-blocking stream and do not synchronise the host between the
-   ranks' calls of one collective (the waiting kernels of all ranks must be running together).  There is no NCCL behind
+   ranks' calls of one collective (the waiting kernels of all ranks must be running together).  Two more conditions of
+   sharing one device: run with CUDA_MODULE_LOADING=EAGER (the first launch of a lazily loaded kernel may wait for the
+   device to drain, which a polling kernel prevents) and CUDA_DEVICE_MAX_CONNECTIONS >= the number of rank streams (on a
+   shared hardware queue rank 1's launch sits behind the kernel that follows rank 0's polling kernel).  The first use of
+   a collective allocates for the whole group and drains the device: issue it while nothing is waiting.  There is no NCCL behind
    such a communicator: the *_real collectives answer -5.  Each one is released with stochqn_b200_comm_destroy. */
 int stochqn_b200_comm_init_inprocess(int world_size, void **comms);
 /* 1 once a stand-alone exchange on this communicator gave up waiting for a peer (20 s) - its result is then garbage */

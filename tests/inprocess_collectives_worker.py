@@ -1,4 +1,4 @@
-"""Worker of tests/test_gpu_inprocess_collectives.py: the peer-memory exchange kernels on ONE GPU.
+"""Worker of tests/test_gpu_zz_inprocess.py: the peer-memory exchange kernels on ONE GPU.
 
 `stochqn_b200_comm_init_inprocess` makes world_size communicators whose ranks all live in this process; every rank gets
 its own non-blocking stream and the calls of one collective are issued rank after rank without a host synchronisation

@@ -1,4 +1,4 @@
-"""Worker of tests/test_gpu_inprocess_collectives.py::test_sharded_*: the SHARDED optimizer on ONE GPU.
+"""Worker of tests/test_gpu_zz_inprocess.py::test_sharded_*: the SHARDED optimizer on ONE GPU.
 
 The parameter vector is split into contiguous blocks over the ranks of an in-process communicator group
 (`stochqn_b200_comm_init_inprocess`); every rank is a host thread with its own workspace and its own stream, serving the

@@ -91,3 +91,61 @@ def test_two_buffers_never_overlap(world, push):
 def test_one_buffer_is_caught(push):
     hazard = _explore(2, 3, 1, push)
     assert hazard is not None and "overlaps" in hazard, hazard
+
+
+# ---- the mailbox all-reduce itself (stochqn_b200/csrc/p2p.cuh) ------------------------------------------------------------------
+# exchange k on every rank:  write my record into slot [parity][me] of EVERY rank's mailbox  ->  raise flag [parity][me] = k + 1
+# in every mailbox (release)  ->  wait until all flags [parity][*] of MY mailbox are >= k + 1 (acquire)  ->  read the records
+# [parity][*] of my mailbox.  Claim (p2p.cuh:13-14): a rank can only start exchange k + 2 (same parity as k) after every peer
+# has posted its flag for k + 1, i.e. after every peer has finished reading k.
+def _explore_mailbox(world, exchanges, nbuf):
+    ops = []
+    for k in range(exchanges):
+        ops += [("wb", k), ("we", k), ("flag", k), ("wait", k), ("rb", k), ("re", k)]
+    idx = {op: i for i, op in enumerate(ops)}
+    start = tuple([0] * world)
+    seen, stack = {start}, [start]
+
+    def flag_value(writer_pc, parity):
+        """what the writer has last stored into its flag of that parity (in any mailbox)"""
+        v = 0
+        for k in range(exchanges):
+            if k % nbuf == parity and writer_pc > idx[("flag", k)]:
+                v = k + 1
+        return v
+
+    while stack:
+        pcs = stack.pop()
+        for b, pc in enumerate(pcs):                      # is a rank reading exchange k while a writer is already past wb(k')?
+            if pc == 0 or ops[pc - 1][0] != "rb":
+                continue
+            k = ops[pc - 1][1]
+            for a in range(world):
+                later = [j for j in range(k + 1, exchanges) if j % nbuf == k % nbuf]
+                if later and pcs[a] > idx[("wb", later[0])]:
+                    return "rank %d overwrites its slot for exchange %d while rank %d reads exchange %d" % (a, later[0], b, k)
+                if pcs[a] <= idx[("we", k)]:
+                    return "rank %d reads exchange %d before rank %d has written it" % (b, k, a)
+        for r in range(world):
+            pc = pcs[r]
+            if pc == len(ops):
+                continue
+            op, k = ops[pc]
+            if op == "wait" and not all(flag_value(pcs[a], k % nbuf) >= k + 1 for a in range(world)):
+                continue
+            nxt = pcs[:r] + (pc + 1,) + pcs[r + 1:]
+            if nxt not in seen:
+                seen.add(nxt)
+                stack.append(nxt)
+    assert tuple([len(ops)] * world) in seen, "the model deadlocked"
+    return None
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_mailbox_double_buffer_is_safe(world):
+    assert _explore_mailbox(world, 5, 2) is None
+
+
+def test_mailbox_single_buffer_is_caught():
+    hazard = _explore_mailbox(2, 3, 1)
+    assert hazard is not None and "overwrites" in hazard, hazard

@@ -226,7 +226,7 @@ class CudaRosen:
     """Free-mode oLBFGS on the chained Rosenbrock function through the C ABI with device pointers; the parameter
     vector is the block [offset, offset + n_local) of a vector of length n when `comm` is given."""
 
-    def __init__(self, torch, abi, n, rank=0, world=1, comm=None, mem=MEM, trace=False):
+    def __init__(self, torch, abi, n, rank=0, world=1, comm=None, mem=MEM, trace=False, min_curv=MIN_CURV):
         from stochqn_b200 import _lib
         from stochqn_b200.distributed import shard_bounds
 
@@ -242,7 +242,7 @@ class CudaRosen:
         self.halo = torch.zeros(2, device="cuda", dtype=torch.float64)
         self.scratch = torch.zeros(2 * max(self.world, 1), device="cuda", dtype=torch.float64)
         lib.stochqn_b200_rosenbrock_x0(self.x.data_ptr(), self.n_local, self.offset, self.stream)
-        self.ws = lib.initialize_oLBFGS(self.n_local, mem, 0.0, 0.0, MIN_CURV, 1, 1)
+        self.ws = lib.initialize_oLBFGS(self.n_local, mem, 0.0, 0.0, min_curv, 1, 1)
         if not self.ws:
             raise SystemExit("initialize_oLBFGS failed: " + _lib.last_error(abi))
         if comm is not None:
@@ -446,6 +446,26 @@ def main_b200(args):
     lib.stochqn_b200_set_option(run.ws, _lib.OPT_PROFILE, 0)
     probes_end = run.probes(dist)
     run.close()
+
+    # "min_curvature = 1e-4 (R / Python default; also report 0)" - the same loop with the curvature test off
+    # (the reference then allocates no backup buffers; here the test is a host decision on two dots K4 computes anyway)
+    mc0 = None
+    if not args.no_checks:
+        r0 = CudaRosen(torch, abi, n, rank, world, comm, min_curv=0.0)
+        r0.run(warm)
+        fence()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r0.run(args.steps)
+        e1.record()
+        fence()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = float(t.item())
+        mc0 = {"value": args.steps / (t * 1e-3), "unit": "steps/s", "ms_per_step": t / args.steps, "blocks": 1, "mem_used": r0.mem_used(),
+               "info_events": int(r0.info_events)}
+        r0.close()
     check.update(after_first_block=probes_first, after_all_blocks={k: probes_end[k] for k in ("iterations", "x_norm", "info_events", "mem_used")},
                  x_norm=probes_end["x_norm"], info_events=probes_end["info_events"], mem_used=probes_end["mem_used"])
 
@@ -536,7 +556,7 @@ def main_b200(args):
             "run": {"n_per_gpu": n_local, "grad_writeback": 1, "value_is": "median of %d blocks of %d iterations, each max over ranks" % (BLOCKS, args.steps),
                     "callbacks": "bundled device Rosenbrock gradient (halo exchange fused in when sharded)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "check": check, "secondary": secondary,
+            "check": check, "min_curvature_0": mc0, "secondary": secondary,
         }
         print(json.dumps(line))
     if dist is not None:
